@@ -1,0 +1,155 @@
+/*
+ * mt_b200.h -- C ABI of the B200-native MusicTransformer hot path (libmt_b200.so).
+ *
+ * The reference (SJTMusicTeam/MusicGeneration, mg/model/MusicTransformer -- "MT/" below) has no
+ * FFI: its boundary is the Python module surface of MT/layers.py, MT/network.py and
+ * MT/criterion.py.  Every entry point here replaces the group of eager PyTorch ops the cited
+ * reference lines execute; the Python mirror in musicgeneration_b200/ binds them with ctypes
+ * (see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless named host_*;
+ *   - the caller owns every buffer (inputs, outputs, workspaces) and keeps it alive until the
+ *     stream reaches the op; the library allocates no device memory;
+ *   - every op only enqueues work on `stream` (a cudaStream_t passed as void*); no host sync,
+ *     CUDA-graph capturable;
+ *   - return 0 on success, a negative MT_E_* code for argument errors, or a positive
+ *     cudaError_t; mt_last_error() returns a thread-local message; nothing throws or exits;
+ *   - dtype codes: MT_F32 = 0, MT_BF16 = 1, MT_F16 = 2.  "lp" = the low-precision activation
+ *     type of the bf16 mode; in fp32 mode lp pointers are NULL or dtype is MT_F32.
+ *   - tensors are row-major and dense unless strides are passed (strides are in ELEMENTS).
+ */
+#ifndef MT_B200_H_
+#define MT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MT_F32 0
+#define MT_BF16 1
+#define MT_F16 2
+
+#define MT_E_ARG (-1)      /* bad pointer / shape / alignment                */
+#define MT_E_UNSUPPORTED (-2) /* combination not built (e.g. dh not in {32,64,128}) */
+#define MT_E_WORKSPACE (-3) /* workspace too small                             */
+
+/* GEMM epilogue flags */
+#define MT_EPI_BIAS 1       /* + bias[n]                                        */
+#define MT_EPI_RELU 2       /* max(.,0)                                         */
+#define MT_EPI_ADD 4        /* + addend[m,n] (fp32, ld = ldc)                   */
+#define MT_EPI_RELU_MASK 8  /* zero where aux[m,n] <= 0 (aux has the input dtype, ld = ldc) */
+
+int mt_version(void);
+const char* mt_last_error(void);
+/* 1 when the running device is sm_100 and the tcgen05 paths are usable */
+int mt_device_ok(void);
+
+/* ---- K3: embedding * sqrt(d) + sinusoid + dropout  (MT/layers.py:226-229, :22-39) -------- */
+int mt_embed_pos_fwd(const int32_t* ids, const float* emb, const float* pe, float* out_f32,
+                     void* out_lp, int lp_dtype, int64_t B, int64_t L, int64_t d, int64_t V,
+                     int64_t pos0, float scale, float p_drop, uint64_t seed, uint64_t site,
+                     void* stream);
+/* demb[V,d] += scatter(dout * scale * dropmask); demb must be zeroed/accumulated by caller */
+int mt_embed_pos_bwd(const int32_t* ids, const float* dout, float* demb, int64_t B, int64_t L,
+                     int64_t d, int64_t V, float scale, float p_drop, uint64_t seed,
+                     uint64_t site, void* stream);
+
+/* ---- K4: out = LayerNorm(dropout(a) + resid)  (MT/layers.py:154-155,159-160) ------------- */
+int mt_add_ln_fwd(const void* a, int a_dtype, const float* resid, const float* gamma,
+                  const float* beta, float* out_f32, void* out_lp, int lp_dtype, float* mean,
+                  float* rstd, int64_t T, int64_t d, float eps, float p_drop, uint64_t seed,
+                  uint64_t site, void* stream);
+/* dz (fp32, may alias dout) = grad wrt (dropout(a)+resid); da (da_dtype) = dropmask * dz;
+ * part[2, nparts, d] receives per-block partial sums of dgamma / dbeta, reduced by
+ * mt_ln_param_grad.  nparts = mt_add_ln_bwd_parts(T). */
+int64_t mt_add_ln_bwd_parts(int64_t T);
+int mt_add_ln_bwd(const float* dout, const void* a, int a_dtype, const float* resid,
+                  const float* gamma, const float* mean, const float* rstd, float* dz,
+                  void* da, int da_dtype, float* part, int64_t T, int64_t d, float p_drop,
+                  uint64_t seed, uint64_t site, void* stream);
+int mt_ln_param_grad(const float* part, float* dgamma, float* dbeta, int64_t nparts, int64_t d,
+                     void* stream);
+
+/* ---- K5: C = epi(op(A)[M,K] . op(B)[K,N])  (nn.Linear fwd/dgrad/wgrad on the path) ------- */
+/* transA: A stored [K,M] (lda = row pitch of the stored matrix); transB: B stored [N,K].
+ * in_dtype applies to A, B (and aux); out_dtype to C.  path: 0 = auto, 1 = SIMT fp32-accumulate
+ * reference-precision kernel, 2 = tcgen05 tensor-core kernel (bf16/f16 inputs only). */
+size_t mt_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int in_dtype, int path);
+int mt_gemm(const void* A, const void* B, void* C, const float* bias, const float* addend,
+            const void* aux, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+            int64_t ldc, int transA, int transB, int in_dtype, int out_dtype, int epilogue,
+            int path, void* workspace, size_t workspace_bytes, void* stream);
+/* out[n] = sum_m X[m,n]  (bias gradients) */
+size_t mt_colsum_workspace_bytes(int64_t M, int64_t N);
+int mt_colsum(const void* X, int dtype, float* out, int64_t M, int64_t N, int64_t ldx,
+              void* workspace, size_t workspace_bytes, void* stream);
+int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+/* dst[c,r] = src[r,c] with dtype conversion (weight shadows for dgrad) */
+int mt_transpose_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t rows,
+                      int64_t cols, void* stream);
+
+/* ---- K1/K2: fused relative global attention  (MT/layers.py:86-106, :111-133) ------------- */
+/* q,k,v: element (b,l,hh,dd) at base[b*sb + l*sl + hh*sh + dd]; O, dO: same addressing with
+ * (ob, ol, oh).  E [max_seq, dh] (dtype).  pad_keys [B,L] uint8 or NULL.  lse [B,h,L] fp32.
+ * S[i,j] = (q_i.k_j + [j<=i] q_i.E[max_seq-1-(i-j)]) / sqrt(dh); causal: keys j>i excluded.
+ * path: 0 auto, 1 SIMT, 2 tcgen05. */
+int mt_rga_fwd(const void* q, const void* k, const void* v, int64_t sb, int64_t sl, int64_t sh,
+               const void* E, const uint8_t* pad_keys, void* O, int64_t ob, int64_t ol,
+               int64_t oh, float* lse, int64_t B, int64_t h, int64_t L, int64_t dh,
+               int64_t max_seq, int causal, int dtype, int path, void* stream);
+/* attention weights P [B,h,L,L] fp32 (eval-mode return of MT/network.py:40) from q,k,E,lse */
+int mt_rga_weights(const void* q, const void* k, int64_t sb, int64_t sl, int64_t sh,
+                   const void* E, const uint8_t* pad_keys, const float* lse, float* P, int64_t B,
+                   int64_t h, int64_t L, int64_t dh, int64_t max_seq, int causal, int dtype,
+                   void* stream);
+/* delta [B,h,L] fp32 workspace.  dq,dk,dv use the q/k/v strides.  dE [max_seq,dh] fp32 is
+ * ACCUMULATED into (caller zeroes it once per layer). */
+int mt_rga_bwd(const void* q, const void* k, const void* v, int64_t sb, int64_t sl, int64_t sh,
+               const void* E, const uint8_t* pad_keys, const void* O, const void* dO, int64_t ob,
+               int64_t ol, int64_t oh, const float* lse, float* delta, void* dq, void* dk,
+               void* dv, float* dE, int64_t B, int64_t h, int64_t L, int64_t dh,
+               int64_t max_seq, int causal, int dtype, int path, void* stream);
+
+/* ---- K6: label-smoothed cross entropy + step metrics  (MT/criterion.py:43-67, ------------
+ *          MT/metrics.py:50-60) */
+/* row_lse: 3*T floats (lse, then per-row loss and per-row flags used by the reduction);
+ * argmax[T]; sums[4] = {loss_sum, n_valid, n_correct(all positions), loss_mean} */
+int mt_smooth_ce_fwd(const float* logits, const int32_t* target, float* row_lse,
+                     int32_t* argmax, float* sums, int64_t T, int64_t V, float eps,
+                     int32_t ignore, void* stream);
+/* dlogits = grad_out * (softmax(z) - q') / n_valid on rows with target != ignore, else 0 */
+int mt_smooth_ce_bwd(const float* logits, const int32_t* target, const float* row_lse,
+                     const float* sums, const float* grad_out, float* dlogits, int64_t T,
+                     int64_t V, float eps, int32_t ignore, void* stream);
+
+/* ---- optimizer ("next" row 1: MT/train.py:143, MT/criterion.py:81-88) -------------------- */
+/* Adam (torch.optim.Adam semantics, no weight decay / amsgrad) over a flat fp32 buffer;
+ * grad_scale multiplies g first (1/world, 1/accum).  p_lp (bf16 shadow) may be NULL. */
+int mt_adam_step(float* p, const float* g, float* m, float* v, void* p_lp, int64_t n, float lr,
+                 float beta1, float beta2, float eps, int64_t step, float grad_scale,
+                 void* stream);
+
+/* ---- K7/K8: KV-cached single-token decode  (MT/network.py:52-77, causal oracle) ---------- */
+/* One decode step for the whole stack is orchestrated by the host mirror from these ops. */
+/* s_j = q.(k_j + E[max_seq-1-(t-j)]) / sqrt(dh), j = 0..t; softmax; .V   -- one new token per
+ * sequence.  q: element (b,hh,dd) at q[b*q_stride_b + hh*dh + dd] (dtype); kcache/vcache
+ * [B, h, max_seq, dh] (dtype), already holding position t; out [B,h,dh] dense (dtype). */
+int mt_rga_decode(const void* q, int64_t q_stride_b, const void* kcache, const void* vcache,
+                  const void* E, void* out, int64_t B, int64_t h, int64_t dh, int64_t max_seq,
+                  int64_t t, int dtype, void* stream);
+/* writes k,v [B,h,dh] of the new token into the caches at position t */
+int mt_kv_append(const void* qkv, void* kcache, void* vcache, int64_t B, int64_t h, int64_t dh,
+                 int64_t max_seq, int64_t t, int dtype, void* stream);
+/* ids_out[b] = sample(logits[b,:]/temperature restricted to top_k) using uniforms u[b];
+ * top_k <= 0 or >= V: full distribution; greedy != 0: argmax (first max).  */
+int mt_sample(const float* logits, const float* u, int32_t* ids_out, int64_t B, int64_t V,
+              float temperature, int32_t top_k, int greedy, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MT_B200_H_ */

@@ -1,0 +1,41 @@
+// Internal declarations shared by the launchers (not part of the C ABI).
+#pragma once
+#include "common.cuh"
+
+namespace mt {
+
+struct RgaArgs {
+  const void* q; const void* k; const void* v;
+  int64_t sb, sl, sh;
+  const void* E; const uint8_t* pad;
+  void* O; const void* dO; int64_t ob, ol, oh;
+  float* lse; float* delta; float* P;
+  void* dq; void* dk; void* dv; float* dE;
+  int B, h, L, max_seq, causal;
+  float inv_scale_div;
+};
+
+// gemm_simt.cu
+size_t gemm_simt_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int gemm_simt(const void* A, const void* B, void* C, const float* bias, const float* addend,
+              const void* aux, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+              int64_t ldc, int transA, int transB, int in_dtype, int out_dtype, int epilogue,
+              void* workspace, size_t workspace_bytes, cudaStream_t stream);
+// rga_simt.cu
+int rga_fwd_simt(const RgaArgs& a, int dh, int dtype, cudaStream_t st);
+int rga_weights_simt(const RgaArgs& a, int dh, int dtype, cudaStream_t st);
+int rga_bwd_simt(const RgaArgs& a, int dh, int dtype, cudaStream_t st);
+// gemm_tc.cu / rga_tc.cu (tcgen05)
+bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc,
+                       int transA, int transB, int in_dtype, int out_dtype, int epilogue,
+                       const void* A, const void* B, const void* C);
+size_t gemm_tc_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int gemm_tc(const void* A, const void* B, void* C, const float* bias, const float* addend,
+            const void* aux, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+            int64_t ldc, int transA, int transB, int in_dtype, int out_dtype, int epilogue,
+            void* workspace, size_t workspace_bytes, cudaStream_t stream);
+bool rga_tc_supported(const RgaArgs& a, int dh, int dtype, bool backward);
+int rga_fwd_tc(const RgaArgs& a, int dh, int dtype, cudaStream_t st);
+int rga_bwd_tc(const RgaArgs& a, int dh, int dtype, cudaStream_t st);
+
+}  // namespace mt

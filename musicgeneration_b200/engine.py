@@ -1,0 +1,278 @@
+"""Host-side orchestration of the MusicTransformer hot path over the C-ABI ops.
+
+Mirrors the op order of the reference (MT/layers.py:152-161 EncoderLayer, :223-233 Encoder,
+:64-109 RelativeGlobalAttention) but every arithmetic step is one of our CUDA kernels; this
+file only allocates buffers, keeps what the backward needs and sequences launches.
+
+Precision modes
+  * "fp32": all activations fp32, FFMA kernels -- the parity mode (logits/loss 1e-5, greedy
+    ids exact).
+  * "bf16": fp32 master weights and fp32 residual stream / LayerNorm / softmax / accumulators;
+    GEMM and attention operands bf16 (activations are written once in bf16 next to the fp32
+    residual by the producing kernel) -- the throughput mode.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+@dataclass
+class StackCfg:
+    d: int
+    h: int
+    max_seq: int
+    p_drop: float = 0.0
+    act: torch.dtype = torch.float32          # activation / GEMM operand dtype
+    gemm_path: int = L.PATH_AUTO
+    attn_path: int = L.PATH_AUTO
+
+    @property
+    def dh(self) -> int:
+        return self.d // self.h
+
+
+@dataclass
+class LayerWeights:
+    """Per-layer operands in the layout the kernels want (act dtype for GEMM operands)."""
+    Wqkv: torch.Tensor      # [3d, d] act   (Wq;Wk;Wv stacked: nn.Linear weights are [out,in])
+    bqkv: torch.Tensor      # [3d] f32
+    Wfc: torch.Tensor       # [d, d] act
+    bfc: torch.Tensor
+    Wpre: torch.Tensor      # [d/2, d] act
+    bpre: torch.Tensor
+    Wsuf: torch.Tensor      # [d, d/2] act
+    bsuf: torch.Tensor
+    E: torch.Tensor         # [max_seq, dh] act
+    g1: torch.Tensor
+    b1: torch.Tensor
+    g2: torch.Tensor
+    b2: torch.Tensor
+
+
+@dataclass
+class Mask:
+    """Structured form of the reference's look-ahead mask (MT/utils.py:58-83): causal part +
+    per-key pad bits.  ``None`` pad_keys = no pad tokens."""
+    causal: bool
+    pad_keys: Optional[torch.Tensor] = None   # uint8 [B, L]
+
+
+def _empty(shape, dtype, like):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+# ---------------------------------------------------------------------------------------
+# linear helpers (all row-major; nn.Linear weight W is [out, in])
+# ---------------------------------------------------------------------------------------
+def linear_fwd(x, W, b, out, cfg: StackCfg, relu=False, ldc=None):
+    """out[T, N] = x[T, K] . W[N, K]^T + b"""
+    T, K = x.shape
+    N = W.shape[0]
+    ops.gemm(x, W, out, T, N, K, x.stride(0), W.stride(0), ldc or out.stride(0), False, True,
+             bias=b, relu=relu, path=cfg.gemm_path)
+
+
+def linear_dgrad(dy, W, out, cfg: StackCfg, addend=None, relu_mask_aux=None, ldy=None):
+    """out[T, K] = dy[T, N] . W[N, K] (+ addend) (masked by aux > 0)"""
+    T = dy.shape[0]
+    N, K = W.shape
+    ops.gemm(dy, W, out, T, K, N, ldy or dy.stride(0), W.stride(0), out.stride(0), False, False,
+             addend=addend, aux=relu_mask_aux, relu_mask=relu_mask_aux is not None,
+             path=cfg.gemm_path)
+
+
+def linear_wgrad(dy, x, dW, db, cfg: StackCfg, ldy=None, n=None):
+    """dW[N, K] = dy[T, N]^T . x[T, K];  db[N] = colsum(dy)"""
+    T, K = x.shape
+    N = n or dy.shape[1]
+    ld = ldy or dy.stride(0)
+    ops.gemm(dy, x, dW, N, K, T, ld, x.stride(0), dW.stride(0), True, False, path=cfg.gemm_path)
+    if db is not None:
+        ops.colsum(dy, db, T, N, ld)
+
+
+# ---------------------------------------------------------------------------------------
+# relative global attention block: QKV projection -> fused attention -> fc
+# ---------------------------------------------------------------------------------------
+def rga_block_fwd(xq, xk, xv, W: LayerWeights, cfg: StackCfg, B: int, Lq: int, mask: Optional[Mask],
+                  need_weights: bool):
+    """xq/xk/xv: [T, d] act dtype (the same tensor for self-attention).  Returns
+    (a [T,d] f32 = fc output incl. bias, saved dict, P or None)."""
+    d, h, dh = cfg.d, cfg.h, cfg.dh
+    T = B * Lq
+    qkv = _empty((T, 3 * d), cfg.act, xq)
+    same = (xq is xk) and (xk is xv)
+    if same:
+        linear_fwd(xq, W.Wqkv, W.bqkv, qkv, cfg)
+    else:
+        for i, x in enumerate((xq, xk, xv)):
+            linear_fwd(x, W.Wqkv[i * d:(i + 1) * d], W.bqkv[i * d:(i + 1) * d], qkv[:, i * d:(i + 1) * d],
+                       cfg, ldc=3 * d)
+    q, k, v = qkv[:, 0:d], qkv[:, d:2 * d], qkv[:, 2 * d:3 * d]
+    strides = (Lq * 3 * d, 3 * d, dh)          # (batch, position, head) in elements
+    O = _empty((T, d), cfg.act, xq)
+    ostrides = (Lq * d, d, dh)
+    lse = _empty((B, h, Lq), torch.float32, xq)
+    causal = bool(mask.causal) if mask is not None else False
+    pad = mask.pad_keys if mask is not None else None
+    ops.rga_fwd(q, k, v, strides, W.E, pad, O, ostrides, lse, B, h, Lq, dh, cfg.max_seq, causal,
+                path=cfg.attn_path)
+    P = None
+    if need_weights:
+        P = _empty((B, h, Lq, Lq), torch.float32, xq)
+        ops.rga_weights(q, k, strides, W.E, pad, lse, P, B, h, Lq, dh, cfg.max_seq, causal)
+    a = _empty((T, d), torch.float32, xq)
+    linear_fwd(O, W.Wfc, W.bfc, a, cfg)
+    saved = dict(xq=xq, xk=xk, xv=xv, same=same, qkv=qkv, O=O, lse=lse, causal=causal, pad=pad,
+                 strides=strides, ostrides=ostrides, B=B, L=Lq)
+    return a, saved, P
+
+
+def rga_block_bwd(d_a, s, W: LayerWeights, cfg: StackCfg, g: Dict[str, torch.Tensor],
+                  dx_addend: Optional[torch.Tensor]):
+    """d_a [T,d] act dtype = grad wrt fc output.  Fills g[...] (fp32 grads) and returns
+    (dxq, dxk, dxv) fp32 [T,d]; for self-attention the three are one tensor that already
+    includes ``dx_addend`` (the residual-path gradient)."""
+    d, h, dh = cfg.d, cfg.h, cfg.dh
+    B, Lq = s["B"], s["L"]
+    T = B * Lq
+    dev = d_a
+    g["Wfc"] = _empty((d, d), torch.float32, dev)
+    g["bfc"] = _empty((d,), torch.float32, dev)
+    linear_wgrad(d_a, s["O"], g["Wfc"], g["bfc"], cfg)
+    dO = _empty((T, d), cfg.act, dev)
+    linear_dgrad(d_a, W.Wfc, dO, cfg)
+    dqkv = _empty((T, 3 * d), cfg.act, dev)
+    delta = _empty((B, h, Lq), torch.float32, dev)
+    g["E"] = torch.zeros((cfg.max_seq, dh), dtype=torch.float32, device=dev.device)
+    qkv = s["qkv"]
+    ops.rga_bwd(qkv[:, 0:d], qkv[:, d:2 * d], qkv[:, 2 * d:3 * d], s["strides"], W.E, s["pad"],
+                s["O"], dO, s["ostrides"], s["lse"], delta, dqkv[:, 0:d], dqkv[:, d:2 * d],
+                dqkv[:, 2 * d:3 * d], g["E"], B, h, Lq, dh, cfg.max_seq, s["causal"],
+                path=cfg.attn_path)
+    g["Wqkv"] = _empty((3 * d, d), torch.float32, dev)
+    g["bqkv"] = _empty((3 * d,), torch.float32, dev)
+    if s["same"]:
+        linear_wgrad(dqkv, s["xq"], g["Wqkv"], g["bqkv"], cfg)
+        dx = _empty((T, d), torch.float32, dev)
+        linear_dgrad(dqkv, W.Wqkv, dx, cfg, addend=dx_addend)
+        return dx, dx, dx
+    outs = []
+    for i, x in enumerate((s["xq"], s["xk"], s["xv"])):
+        sl = dqkv[:, i * d:(i + 1) * d]
+        linear_wgrad(sl, x, g["Wqkv"][i * d:(i + 1) * d], g["bqkv"][i * d:(i + 1) * d], cfg,
+                     ldy=3 * d, n=d)
+        dx = _empty((T, d), torch.float32, dev)
+        linear_dgrad(sl, W.Wqkv[i * d:(i + 1) * d], dx, cfg, ldy=3 * d)
+        outs.append(dx)
+    return tuple(outs)
+
+
+# ---------------------------------------------------------------------------------------
+# encoder layer  (MT/layers.py:152-161)
+# ---------------------------------------------------------------------------------------
+def layer_fwd(x_f32, x_lp, W: LayerWeights, cfg: StackCfg, B: int, Lq: int, mask: Optional[Mask],
+              seed: int, site0: int, training: bool, need_weights: bool):
+    d = cfg.d
+    T = B * Lq
+    p = cfg.p_drop if training else 0.0
+    lp = cfg.act != torch.float32
+    a, s_att, P = rga_block_fwd(x_lp, x_lp, x_lp, W, cfg, B, Lq, mask, need_weights)
+    out1 = _empty((T, d), torch.float32, x_f32)
+    out1_lp = _empty((T, d), cfg.act, x_f32) if lp else None
+    mean1 = _empty((T,), torch.float32, x_f32)
+    rstd1 = _empty((T,), torch.float32, x_f32)
+    ops.add_ln_fwd(a, x_f32, W.g1, W.b1, out1, out1_lp, mean1, rstd1, 1e-6, p, seed, site0)
+    o1 = out1_lp if lp else out1
+    hmid = _empty((T, d // 2), cfg.act, x_f32)
+    linear_fwd(o1, W.Wpre, W.bpre, hmid, cfg, relu=True)
+    f = _empty((T, d), torch.float32, x_f32)
+    linear_fwd(hmid, W.Wsuf, W.bsuf, f, cfg)
+    out2 = _empty((T, d), torch.float32, x_f32)
+    out2_lp = _empty((T, d), cfg.act, x_f32) if lp else None
+    mean2 = _empty((T,), torch.float32, x_f32)
+    rstd2 = _empty((T,), torch.float32, x_f32)
+    ops.add_ln_fwd(f, out1, W.g2, W.b2, out2, out2_lp, mean2, rstd2, 1e-6, p, seed, site0 + 1)
+    saved = dict(att=s_att, x=x_f32, a=a, out1=out1, o1=o1, mean1=mean1, rstd1=rstd1, hmid=hmid,
+                 f=f, mean2=mean2, rstd2=rstd2, p=p, seed=seed, site0=site0)
+    return out2, (out2_lp if lp else out2), saved, P
+
+
+def layer_bwd(dout, s, W: LayerWeights, cfg: StackCfg) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+    """dout [T,d] f32 (may be overwritten).  Returns (dx f32, grads dict keyed like LayerWeights)."""
+    d = cfg.d
+    T = dout.shape[0]
+    g: Dict[str, torch.Tensor] = {}
+    dev = dout
+    p, seed, site0 = s["p"], s["seed"], s["site0"]
+    # LN2
+    g["g2"] = _empty((d,), torch.float32, dev)
+    g["b2"] = _empty((d,), torch.float32, dev)
+    d_f = _empty((T, d), cfg.act, dev)
+    ops.add_ln_bwd(dout, s["f"], s["out1"], W.g2, s["mean2"], s["rstd2"], dout, d_f, g["g2"], g["b2"],
+                   p, seed, site0 + 1)
+    dz2 = dout
+    # FFN_suf
+    g["Wsuf"] = _empty((d, d // 2), torch.float32, dev)
+    g["bsuf"] = _empty((d,), torch.float32, dev)
+    linear_wgrad(d_f, s["hmid"], g["Wsuf"], g["bsuf"], cfg)
+    dh_ = _empty((T, d // 2), cfg.act, dev)
+    linear_dgrad(d_f, W.Wsuf, dh_, cfg, relu_mask_aux=s["hmid"])
+    # FFN_pre
+    g["Wpre"] = _empty((d // 2, d), torch.float32, dev)
+    g["bpre"] = _empty((d // 2,), torch.float32, dev)
+    linear_wgrad(dh_, s["o1"], g["Wpre"], g["bpre"], cfg)
+    linear_dgrad(dh_, W.Wpre, dz2, cfg, addend=dz2)          # d_out1 = dz2 + dh . Wpre (in place)
+    d_out1 = dz2
+    # LN1
+    g["g1"] = _empty((d,), torch.float32, dev)
+    g["b1"] = _empty((d,), torch.float32, dev)
+    d_a = _empty((T, d), cfg.act, dev)
+    ops.add_ln_bwd(d_out1, s["a"], s["x"], W.g1, s["mean1"], s["rstd1"], d_out1, d_a, g["g1"], g["b1"],
+                   p, seed, site0)
+    dz1 = d_out1
+    dx, _, _ = rga_block_bwd(d_a, s["att"], W, cfg, g, dx_addend=dz1)
+    return dx, g
+
+
+# ---------------------------------------------------------------------------------------
+# whole stack  (MT/layers.py:223-233)
+# ---------------------------------------------------------------------------------------
+def encoder_fwd(ids: torch.Tensor, emb: torch.Tensor, pe: torch.Tensor, Ws: List[LayerWeights],
+                cfg: StackCfg, mask: Optional[Mask], seed: int, training: bool, need_weights: bool,
+                pos0: int = 0):
+    B, Lq = ids.shape
+    d = cfg.d
+    T = B * Lq
+    lp = cfg.act != torch.float32
+    p = cfg.p_drop if training else 0.0
+    x = _empty((T, d), torch.float32, emb)
+    x_lp = _empty((T, d), cfg.act, emb) if lp else None
+    ops.embed_pos_fwd(ids, emb, pe, x, x_lp, pos0, math.sqrt(d), p, seed, 0)
+    xl = x_lp if lp else x
+    saved_layers = []
+    weights = []
+    for li, W in enumerate(Ws):
+        x, xl, s, P = layer_fwd(x, xl, W, cfg, B, Lq, mask, seed, 1 + 2 * li, training, need_weights)
+        saved_layers.append(s)
+        weights.append(P)
+    saved = dict(ids=ids, layers=saved_layers, p=p, seed=seed, B=B, L=Lq)
+    return x, xl, saved, weights
+
+
+def encoder_bwd(dhid: torch.Tensor, saved, Ws: List[LayerWeights], cfg: StackCfg, V: int):
+    """dhid [T,d] f32 -> (demb [V,d] f32, [layer grad dicts])."""
+    dx = dhid
+    layer_grads: List[Dict[str, torch.Tensor]] = [None] * len(Ws)
+    for li in range(len(Ws) - 1, -1, -1):
+        dx, layer_grads[li] = layer_bwd(dx, saved["layers"][li], Ws[li], cfg)
+    demb = torch.zeros((V, cfg.d), dtype=torch.float32, device=dhid.device)
+    ops.embed_pos_bwd(saved["ids"], dx, demb, math.sqrt(cfg.d), saved["p"], saved["seed"], 0)
+    return demb, layer_grads

@@ -1,0 +1,194 @@
+"""Thin torch-tensor wrappers over the C ABI (one function per exported op).
+
+PyTorch is only plumbing here: it owns device memory and the current stream; every function
+below enqueues exactly the kernels of one ``mt_*`` entry point on that stream."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: L.MT_F32, torch.bfloat16: L.MT_BF16, torch.float16: L.MT_F16}
+
+
+def dt(t_or_dtype) -> int:
+    d = t_or_dtype.dtype if isinstance(t_or_dtype, torch.Tensor) else t_or_dtype
+    return _DT[d]
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("musicgeneration_b200 runs on CUDA tensors only (no CPU fallback); "
+                               "move the module and its inputs to a B200 device")
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes: int, device) -> Optional[torch.Tensor]:
+    """Per-device scratch reused by ops that take a caller-owned workspace (stream-ordered)."""
+    if nbytes <= 0:
+        return None
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 22), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def embed_pos_fwd(ids, emb, pe, out_f32, out_lp, pos0, scale, p_drop, seed, site):
+    _need_cuda(ids, emb, pe, out_f32)
+    B, Lq = ids.shape
+    V, d = emb.shape
+    L.check(L.load().mt_embed_pos_fwd(_ptr(ids), _ptr(emb), _ptr(pe), _ptr(out_f32), _ptr(out_lp),
+                                      dt(out_lp) if out_lp is not None else L.MT_F32, B, Lq, d, V,
+                                      pos0, scale, p_drop, seed, site, _stream()), "embed_pos_fwd")
+
+
+def embed_pos_bwd(ids, dout, demb, scale, p_drop, seed, site):
+    _need_cuda(ids, dout, demb)
+    B, Lq = ids.shape
+    V, d = demb.shape
+    L.check(L.load().mt_embed_pos_bwd(_ptr(ids), _ptr(dout), _ptr(demb), B, Lq, d, V, scale, p_drop,
+                                      seed, site, _stream()), "embed_pos_bwd")
+
+
+def add_ln_fwd(a, resid, gamma, beta, out_f32, out_lp, mean, rstd, eps, p_drop, seed, site):
+    _need_cuda(a, resid, out_f32)
+    T, d = resid.shape
+    L.check(L.load().mt_add_ln_fwd(_ptr(a), dt(a), _ptr(resid), _ptr(gamma), _ptr(beta),
+                                   _ptr(out_f32), _ptr(out_lp),
+                                   dt(out_lp) if out_lp is not None else L.MT_F32, _ptr(mean),
+                                   _ptr(rstd), T, d, eps, p_drop, seed, site, _stream()), "add_ln_fwd")
+
+
+def add_ln_bwd(dout, a, resid, gamma, mean, rstd, dz, da, dgamma, dbeta, p_drop, seed, site):
+    _need_cuda(dout, a, resid)
+    T, d = resid.shape
+    lib = L.load()
+    nparts = lib.mt_add_ln_bwd_parts(T)
+    part = torch.empty((2, nparts, d), dtype=torch.float32, device=dout.device)
+    L.check(lib.mt_add_ln_bwd(_ptr(dout), _ptr(a), dt(a), _ptr(resid), _ptr(gamma), _ptr(mean),
+                              _ptr(rstd), _ptr(dz), _ptr(da), dt(da), _ptr(part), T, d, p_drop, seed,
+                              site, _stream()), "add_ln_bwd")
+    L.check(lib.mt_ln_param_grad(_ptr(part), _ptr(dgamma), _ptr(dbeta), nparts, d, _stream()),
+            "ln_param_grad")
+
+
+def gemm(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, bias=None, addend=None, aux=None,
+         relu=False, relu_mask=False, path=L.PATH_AUTO):
+    """C[M,N] = epi(op(A) . op(B)); see include/mt_b200.h."""
+    _need_cuda(A, B, C)
+    lib = L.load()
+    epi = 0
+    if bias is not None:
+        epi |= L.EPI_BIAS
+    if addend is not None:
+        epi |= L.EPI_ADD
+    if relu:
+        epi |= L.EPI_RELU
+    if relu_mask:
+        epi |= L.EPI_RELU_MASK
+    nws = lib.mt_gemm_workspace_bytes(M, N, K, dt(A), path)
+    ws = workspace(nws, A.device)
+    L.check(lib.mt_gemm(_ptr(A), _ptr(B), _ptr(C), _ptr(bias), _ptr(addend), _ptr(aux), M, N, K, lda,
+                        ldb, ldc, int(transA), int(transB), dt(A), dt(C), epi, path, _ptr(ws),
+                        ws.numel() if ws is not None else 0, _stream()), "gemm")
+
+
+def colsum(X, out, M, N, ldx):
+    _need_cuda(X, out)
+    lib = L.load()
+    nws = lib.mt_colsum_workspace_bytes(M, N)
+    ws = workspace(nws, X.device)
+    L.check(lib.mt_colsum(_ptr(X), dt(X), _ptr(out), M, N, ldx, _ptr(ws),
+                          ws.numel() if ws is not None else 0, _stream()), "colsum")
+
+
+def cast(src, dst, n=None):
+    _need_cuda(src, dst)
+    n = src.numel() if n is None else n
+    L.check(L.load().mt_cast(_ptr(src), dt(src), _ptr(dst), dt(dst), n, _stream()), "cast")
+
+
+def transpose_cast(src, dst, rows, cols):
+    _need_cuda(src, dst)
+    L.check(L.load().mt_transpose_cast(_ptr(src), dt(src), _ptr(dst), dt(dst), rows, cols, _stream()),
+            "transpose_cast")
+
+
+def rga_fwd(q, k, v, strides, E, pad_keys, O, ostrides, lse, B, h, Lq, dh, max_seq, causal,
+            path=L.PATH_AUTO):
+    _need_cuda(q, k, v, E, O, lse)
+    sb, sl, sh = strides
+    ob, ol, oh = ostrides
+    L.check(L.load().mt_rga_fwd(_ptr(q), _ptr(k), _ptr(v), sb, sl, sh, _ptr(E), _ptr(pad_keys),
+                                _ptr(O), ob, ol, oh, _ptr(lse), B, h, Lq, dh, max_seq, int(causal),
+                                dt(q), path, _stream()), "rga_fwd")
+
+
+def rga_weights(q, k, strides, E, pad_keys, lse, P, B, h, Lq, dh, max_seq, causal):
+    _need_cuda(q, k, E, lse, P)
+    sb, sl, sh = strides
+    L.check(L.load().mt_rga_weights(_ptr(q), _ptr(k), sb, sl, sh, _ptr(E), _ptr(pad_keys), _ptr(lse),
+                                    _ptr(P), B, h, Lq, dh, max_seq, int(causal), dt(q), _stream()),
+            "rga_weights")
+
+
+def rga_bwd(q, k, v, strides, E, pad_keys, O, dO, ostrides, lse, delta, dq, dk, dv, dE, B, h, Lq, dh,
+            max_seq, causal, path=L.PATH_AUTO):
+    _need_cuda(q, k, v, E, O, dO, lse, delta, dq, dk, dv, dE)
+    sb, sl, sh = strides
+    ob, ol, oh = ostrides
+    L.check(L.load().mt_rga_bwd(_ptr(q), _ptr(k), _ptr(v), sb, sl, sh, _ptr(E), _ptr(pad_keys),
+                                _ptr(O), _ptr(dO), ob, ol, oh, _ptr(lse), _ptr(delta), _ptr(dq),
+                                _ptr(dk), _ptr(dv), _ptr(dE), B, h, Lq, dh, max_seq, int(causal),
+                                dt(q), path, _stream()), "rga_bwd")
+
+
+def smooth_ce_fwd(logits, target, row_ws, argmax, sums, eps, ignore):
+    _need_cuda(logits, target)
+    T, V = logits.shape
+    L.check(L.load().mt_smooth_ce_fwd(_ptr(logits), _ptr(target), _ptr(row_ws), _ptr(argmax),
+                                      _ptr(sums), T, V, eps, ignore, _stream()), "smooth_ce_fwd")
+
+
+def smooth_ce_bwd(logits, target, row_ws, sums, grad_out, dlogits, eps, ignore):
+    T, V = logits.shape
+    L.check(L.load().mt_smooth_ce_bwd(_ptr(logits), _ptr(target), _ptr(row_ws), _ptr(sums),
+                                      _ptr(grad_out), _ptr(dlogits), T, V, eps, ignore, _stream()),
+            "smooth_ce_bwd")
+
+
+def adam_step(p, g, m, v, p_lp, lr, beta1, beta2, eps, step, grad_scale):
+    _need_cuda(p, g, m, v)
+    L.check(L.load().mt_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p_lp), p.numel(), lr,
+                                  beta1, beta2, eps, step, grad_scale, _stream()), "adam_step")
+
+
+def rga_decode(q, q_stride_b, kcache, vcache, E, out, B, h, dh, max_seq, t):
+    L.check(L.load().mt_rga_decode(_ptr(q), q_stride_b, _ptr(kcache), _ptr(vcache), _ptr(E),
+                                   _ptr(out), B, h, dh, max_seq, t, dt(q), _stream()), "rga_decode")
+
+
+def kv_append(qkv, kcache, vcache, B, h, dh, max_seq, t):
+    L.check(L.load().mt_kv_append(_ptr(qkv), _ptr(kcache), _ptr(vcache), B, h, dh, max_seq, t,
+                                  dt(qkv), _stream()), "kv_append")
+
+
+def sample(logits, u, ids_out, temperature, top_k, greedy):
+    B, V = logits.shape
+    L.check(L.load().mt_sample(_ptr(logits), _ptr(u), _ptr(ids_out), B, V, temperature, top_k,
+                               int(greedy), _stream()), "sample")

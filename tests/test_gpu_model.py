@@ -1,0 +1,217 @@
+"""End-to-end GPU parity of the drop-in MusicTransformer (through the module API, which calls the
+C ABI) against the reference-generated fixtures and the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import restate as O  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    z = np.load(os.path.join(GOLD, name))
+    return {k: z[k] for k in z.files}
+
+
+def params_of(z):
+    return {k[2:]: torch.from_numpy(v) for k, v in z.items() if k.startswith("p:")}
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def build_model(z, dev, **kw):
+    import musicgeneration_b200 as mtb
+    d, V, pad, layers, L = [int(v) for v in z["meta"][:5]]
+    mtb.config.pad_token = pad
+    m = mtb.MusicTransformer(embedding_dim=d, vocab_size=V, num_layer=layers, max_seq=L, dropout=0.0,
+                             **kw).to(dev)
+    missing = m.load_state_dict(params_of(z), strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return m, (d, V, pad, layers, L)
+
+
+def test_state_dict_layout_matches_reference():
+    import musicgeneration_b200 as mtb
+    z = load("train_small.npz")
+    d, V, pad, layers, L, B = z["meta"].tolist()
+    m = mtb.MusicTransformer(embedding_dim=d, vocab_size=V, num_layer=layers, max_seq=L)
+    ours = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    ref = {k[2:]: tuple(v.shape) for k, v in z.items() if k.startswith("p:")}
+    assert ours == ref
+    assert list(m.state_dict().keys()) == [k[2:] for k in z if k.startswith("p:")]
+
+
+def test_train_small_fp32_logits_loss_grads():
+    import musicgeneration_b200 as mtb
+    dev = torch.device("cuda:0")
+    z = load("train_small.npz")
+    m, (d, V, pad, layers, L) = build_model(z, dev)
+    x, y = torch.from_numpy(z["x"]).to(dev), torch.from_numpy(z["y"]).to(dev)
+    m.train()
+    logits = m(x)
+    assert logits.shape == (x.shape[0], L, V) and logits.dtype == torch.float32 and logits.is_contiguous()
+    ref = torch.from_numpy(z["logits"])
+    assert rel(logits.detach().cpu(), ref) < 1e-5
+    crit = mtb.SmoothCrossEntropyLoss(0.1, V, pad)
+    loss = crit(logits, y)
+    assert abs(float(loss) - float(z["loss"])) < 1e-5 * float(z["loss"])
+    loss.backward()
+    for k, p in m.named_parameters():
+        g = z["g:" + k]
+        err = np.abs(p.grad.cpu().numpy() - g).max()
+        assert err <= 2e-6 + 3e-4 * np.abs(g).max(), (k, err, np.abs(g).max())
+    # step metrics (MT/metrics.py) from the same kernel pass and standalone
+    acc = mtb.metrics.CategoricalAccuracy()(logits, y)
+    assert float(acc) == pytest.approx(float(z["acc"]))
+    assert (mtb.metrics.LogitsBucketting(V)(logits, y).cpu().numpy() == z["bucket"]).all()
+    assert (crit.last_argmax.cpu().numpy() == z["bucket"]).all()
+
+
+def test_train_small_eval_returns_attention_weights():
+    dev = torch.device("cuda:0")
+    z = load("train_small.npz")
+    m, (d, V, pad, layers, L) = build_model(z, dev)
+    m.eval()
+    with torch.no_grad():
+        logits, ws = m(torch.from_numpy(z["x"]).to(dev))
+    assert rel(logits.cpu(), torch.from_numpy(z["logits"])) < 1e-5
+    assert len(ws) == layers
+    np.testing.assert_allclose(ws[0].cpu().numpy(), z["w0"], atol=3e-6)
+    np.testing.assert_allclose(ws[1].cpu().numpy(), z["w1"], atol=3e-6)
+
+
+def test_forward_requires_max_seq_like_reference():
+    dev = torch.device("cuda:0")
+    z = load("train_small.npz")
+    m, (d, V, pad, layers, L) = build_model(z, dev)
+    with pytest.raises(RuntimeError, match="must match the size"):
+        m(torch.zeros(2, L // 2, dtype=torch.int32, device=dev))
+    hid, _ = m.Decoder(torch.zeros(2, L // 2, dtype=torch.int32, device=dev), None)   # like generate()
+    assert hid.shape == (2, L // 2, d)
+
+
+def test_train_small_bf16_within_tolerance():
+    import musicgeneration_b200 as mtb
+    dev = torch.device("cuda:0")
+    z = load("train_small.npz")
+    m, (d, V, pad, layers, L) = build_model(z, dev, precision="bf16")
+    x, y = torch.from_numpy(z["x"]).to(dev), torch.from_numpy(z["y"]).to(dev)
+    m.train()
+    logits = m(x)
+    ref = torch.from_numpy(z["logits"])
+    assert rel(logits.detach().cpu(), ref) < 1e-2          # north-star bf16 bar
+    loss = mtb.SmoothCrossEntropyLoss(0.1, V, pad)(logits, y)
+    assert abs(float(loss) - float(z["loss"])) < 1e-2 * float(z["loss"])
+    loss.backward()
+    worst = 0.0
+    for k, p in m.named_parameters():
+        g = torch.from_numpy(z["g:" + k])
+        worst = max(worst, rel(p.grad.cpu(), g))
+    assert worst < 5e-2, worst
+
+
+def test_decode_small_greedy_ids_bit_exact():
+    dev = torch.device("cuda:0")
+    z = load("decode_small.npz")
+    import musicgeneration_b200 as mtb
+    d, V, pad, layers, max_seq, steps, thr = z["meta"].tolist()
+    m, _ = build_model(z, dev)
+    m.eval()
+    prior = torch.from_numpy(z["prior"]).to(dev)
+    ids, step_logits = m.generate(prior, length=steps, greedy=True, return_logits=True)
+    assert (ids.cpu().numpy() == z["causal_ids"]).all()
+    assert float((step_logits.cpu() - torch.from_numpy(z["causal_logits"])).abs().max()) < 5e-5
+    # the reference loop as written (no mask, sliding window), greedy branch
+    mtb.config.threshold_len = thr
+    try:
+        lit = m.generate_literal(prior, length=steps, greedy=True)
+    finally:
+        mtb.config.threshold_len = 500
+    assert (lit.cpu().numpy() == z["literal_ids"]).all()
+    # infer-mode forward returns a python list of lists (MT/network.py:42)
+    m.test()
+    m.greedy = True
+    out = m(prior, 5)
+    assert isinstance(out, list) and out == z["causal_ids"][:, :prior.shape[1] + 5].tolist()
+
+
+def test_decode_sampling_matches_oracle_given_uniforms():
+    dev = torch.device("cuda:0")
+    z = load("decode_small.npz")
+    d, V, pad, layers, max_seq, steps, thr = z["meta"].tolist()
+    m, _ = build_model(z, dev)
+    m.eval()
+    p = params_of(z)
+    prior = torch.from_numpy(z["prior"])
+    g = torch.Generator().manual_seed(0)
+    u = torch.rand(10, prior.shape[0], generator=g)
+    ids = m.generate(prior.to(dev), length=10, temperature=0.9, top_k=8, greedy=False,
+                     uniforms=u.to(dev)).cpu()
+    dec = prior.clone()
+    with torch.no_grad():
+        for s in range(10):
+            mask = O.look_ahead_mask(dec, pad, dec.size(1))
+            hid, _ = O.encoder_forward(dec, p, max_seq, mask)
+            zl = torch.nn.functional.linear(hid[:, -1], p["fc.weight"], p["fc.bias"])
+            nxt = O.sample_topk_from_uniform(zl, u[s], 0.9, 8)
+            dec = torch.cat((dec, nxt[:, None]), -1)
+    assert (ids == dec).all()
+
+
+def test_config_a_fp32_against_oracle():
+    """BASELINE config A (V=390/pad 388, 6L, d256, h=4, L=2048, B=2): logits and loss within
+    1e-5 of the CPU oracle on identical weights and ids."""
+    import musicgeneration_b200 as mtb
+    dev = torch.device("cuda:0")
+    d, V, pad, layers, L, B = 256, 390, 388, 6, 2048, 2
+    mtb.config.pad_token = pad
+    p = O.init_params(d, V, layers, L, seed=0)
+    x, y = O.synthetic_ids(B, L, pad)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    with torch.no_grad():
+        ref = O.model_forward(x, p, L, pad)
+        ref_loss = O.smooth_ce(ref, y, 0.1, V, pad)
+    m = mtb.MusicTransformer(embedding_dim=d, vocab_size=V, num_layer=layers, max_seq=L, dropout=0.0).to(dev)
+    m.load_state_dict(p, strict=True)
+    m.train()
+    logits = m(x.to(dev))
+    loss = mtb.SmoothCrossEntropyLoss(0.1, V, pad)(logits, y.to(dev))
+    assert rel(logits.detach().cpu(), ref) < 1e-5
+    assert abs(float(loss) - float(ref_loss)) < 1e-5 * float(ref_loss)
+    loss.backward()
+    assert all(torch.isfinite(q.grad).all() for q in m.parameters())
+    # bf16 mode on the same weights: north-star tolerance 1e-2 relative
+    m.set_precision("bf16")
+    lb = m(x.to(dev))
+    lossb = mtb.SmoothCrossEntropyLoss(0.1, V, pad)(lb, y.to(dev))
+    print("config A bf16 logits rel err", rel(lb.detach().cpu(), ref), "loss", float(lossb), float(ref_loss))
+    assert abs(float(lossb) - float(ref_loss)) < 1e-2 * float(ref_loss)
+
+
+def test_causality_and_batch_independence_property():
+    """Size-independent properties at a larger shape: logits at position i do not depend on
+    tokens after i, nor on the other sequences of the batch."""
+    import musicgeneration_b200 as mtb
+    dev = torch.device("cuda:0")
+    d, V, pad, layers, L, B = 256, 390, 388, 2, 512, 4
+    mtb.config.pad_token = pad
+    m = mtb.MusicTransformer(embedding_dim=d, vocab_size=V, num_layer=layers, max_seq=L, dropout=0.0).to(dev)
+    m.load_state_dict(O.init_params(d, V, layers, L, seed=2), strict=True)
+    m.train()
+    x, _ = O.synthetic_ids(B, L, pad, seed=8)
+    x = x.to(dev)
+    with torch.no_grad():
+        base = m(x)
+        x2 = x.clone()
+        x2[:, 300:] = (x2[:, 300:] + 7) % pad
+        x2[1:] = x2[1:].flip(0)
+        other = m(x2)
+    assert torch.equal(base[0, :300], other[0, :300])
+    assert not torch.equal(base[0, 300:], other[0, 300:])

@@ -1,0 +1,146 @@
+"""GPU parity of the fused relative global attention (K1/K2) through the C ABI against the CPU
+oracle's closed form (fp64) and against the reference-generated fixtures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import restate as O  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+PATHS = {"simt": 1, "tc": 2}
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def run_case(B, h, L, dh, max_seq, causal, pad, dtype, path, seed=0, scale=1.0):
+    from musicgeneration_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(seed)
+    d = h * dh
+    qkv = (torch.randn(B, L, 3, h, dh, generator=g) * scale).to(dtype)
+    E = torch.randn(max_seq, dh, generator=g).to(dtype)
+    dO = torch.randn(B, L, h, dh, generator=g).to(dtype)
+    pad_keys = None
+    if pad:
+        pad_keys = torch.zeros(B, L, dtype=torch.bool)
+        pad_keys[0, L // 2:L // 2 + 3] = True
+        pad_keys[B - 1, L - 5:] = True
+    # ---- oracle in fp64 on the (rounded) inputs
+    q, k, v = [qkv[:, :, i].permute(0, 2, 1, 3).double().requires_grad_(True) for i in range(3)]
+    E64 = E.double().requires_grad_(True)
+    o_ref, lse_ref = O.rga_closed_form(q, k, v, E64, max_seq, causal, pad_keys)
+    (o_ref * dO.permute(0, 2, 1, 3).double()).sum().backward()
+    # ---- CUDA
+    qkv_d = qkv.to(dev)
+    Ed = E.to(dev)
+    Od = torch.empty(B, L, h, dh, dtype=dtype, device=dev)
+    lse = torch.empty(B, h, L, device=dev)
+    strides = (L * 3 * d, 3 * d, dh)
+    ostr = (L * d, d, dh)
+    qd, kd, vd = qkv_d[:, :, 0], qkv_d[:, :, 1], qkv_d[:, :, 2]
+    pk = pad_keys.to(torch.uint8).to(dev) if pad_keys is not None else None
+    ops.rga_fwd(qd, kd, vd, strides, Ed, pk, Od, ostr, lse, B, h, L, dh, max_seq, causal, path=path)
+    dqkv = torch.zeros(B, L, 3, h, dh, dtype=dtype, device=dev)
+    dE = torch.zeros(max_seq, dh, device=dev)
+    delta = torch.empty(B, h, L, device=dev)
+    ops.rga_bwd(qd, kd, vd, strides, Ed, pk, Od, dO.to(dev), ostr, lse, delta, dqkv[:, :, 0],
+                dqkv[:, :, 1], dqkv[:, :, 2], dE, B, h, L, dh, max_seq, causal, path=path)
+    res = dict(
+        o=rel(Od.float().cpu().permute(0, 2, 1, 3), o_ref.detach()),
+        lse=float((lse.cpu().double() - lse_ref.detach()).abs().max()),
+        dq=rel(dqkv[:, :, 0].float().cpu().permute(0, 2, 1, 3), q.grad),
+        dk=rel(dqkv[:, :, 1].float().cpu().permute(0, 2, 1, 3), k.grad),
+        dv=rel(dqkv[:, :, 2].float().cpu().permute(0, 2, 1, 3), v.grad),
+        dE=rel(dE.cpu(), E64.grad))
+    # weights kernel (eval-mode return)
+    P = torch.empty(B, h, L, L, device=dev)
+    ops.rga_weights(qd, kd, strides, Ed, pk, lse, P, B, h, L, dh, max_seq, causal)
+    with torch.no_grad():
+        i = torch.arange(L)[:, None]
+        j = torch.arange(L)[None, :]
+        qe = torch.einsum("bhld,md->bhlm", q, E64)
+        idx = (max_seq - 1 - (i - j)).clamp(0, max_seq - 1)
+        srel = torch.gather(qe, 3, idx.expand(B, h, L, L)) * (j <= i)
+        s = (q @ k.transpose(-1, -2) + srel) / dh ** 0.5
+        dead = torch.zeros(B, 1, L, L, dtype=torch.bool)
+        if causal:
+            dead = dead | (j > i)
+        if pad_keys is not None:
+            dead = dead | pad_keys[:, None, None, :]
+        p_ref = torch.softmax(s.masked_fill(dead, float("-inf")), -1)
+    res["P"] = float((P.cpu().double() - p_ref).abs().max())
+    return res
+
+
+@pytest.mark.parametrize("B,h,L,dh,max_seq,causal,pad", [
+    (2, 2, 64, 64, 64, True, False),
+    (2, 2, 48, 64, 64, True, False),        # L < max_seq, L not a tile multiple
+    (1, 4, 200, 32, 256, True, True),
+    (2, 1, 130, 128, 130, True, False),
+    (2, 2, 96, 64, 96, False, False),       # generate(): mask=None, rel term only for j<=i
+    (1, 2, 77, 64, 128, False, True),
+    (1, 4, 512, 64, 512, True, False),
+])
+def test_rga_simt_fp32(B, h, L, dh, max_seq, causal, pad):
+    r = run_case(B, h, L, dh, max_seq, causal, pad, torch.float32, PATHS["simt"], seed=L)
+    assert r["o"] < 2e-6 and r["lse"] < 2e-5 and r["P"] < 2e-6, r
+    assert max(r["dq"], r["dk"], r["dv"], r["dE"]) < 1e-5, r
+
+
+def test_rga_simt_fp32_large_logits():
+    # layer-0-like statistics: |q|,|k| ~ 13 -> logits in the hundreds
+    r = run_case(1, 2, 256, 64, 256, True, False, torch.float32, PATHS["simt"], seed=5, scale=6.0)
+    assert r["o"] < 1e-5 and r["P"] < 1e-4, r
+
+
+@pytest.mark.parametrize("B,h,L,dh,max_seq,causal", [(2, 2, 128, 64, 128, True), (1, 2, 96, 64, 128, False)])
+def test_rga_simt_bf16_io(B, h, L, dh, max_seq, causal):
+    r = run_case(B, h, L, dh, max_seq, causal, False, torch.bfloat16, PATHS["simt"], seed=1)
+    assert r["o"] < 4e-3 and max(r["dq"], r["dk"], r["dv"], r["dE"]) < 8e-3, r
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c", "d"])
+@pytest.mark.parametrize("tag", ["none", "causal"])
+def test_rga_module_against_reference_fixture(case, tag):
+    import musicgeneration_b200 as mtb
+    z = np.load(os.path.join(GOLD, "rga_small.npz"))
+    h, d, max_seq, L = z["meta"]["abcd".index(case)].tolist()
+    dev = torch.device("cuda:0")
+    rga = mtb.RelativeGlobalAttention(h=h, d=d, max_seq=max_seq).to(dev)
+    sd = {k[len(case) + 3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(case + ":p:")}
+    rga.load_state_dict(sd, strict=True)
+    rga.need_weights = True
+    x = torch.from_numpy(z[case + ":x"]).to(dev).requires_grad_(True)
+    ar = torch.arange(L, device=dev)
+    mask = (ar[None, :] > ar[:, None])[None, None] if tag == "causal" else None
+    out, w = rga([x, x, x], mask)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), z[f"{case}:{tag}:out"], atol=5e-5)
+    if case == "a":
+        np.testing.assert_allclose(w.cpu().numpy(), z[f"{case}:{tag}:w"], atol=3e-6)
+    wgt = torch.cos(torch.arange(out.numel(), dtype=torch.float32)).reshape(out.shape).to(dev)
+    (out * wgt).sum().backward()
+    np.testing.assert_allclose(x.grad.cpu().numpy(), z[f"{case}:{tag}:dx"], atol=1e-3, rtol=2e-4)
+    for k, p in rga.named_parameters():
+        g = z[f"{case}:{tag}:g:{k}"]
+        assert np.abs(p.grad.cpu().numpy() - g).max() <= 2e-5 + 3e-4 * np.abs(g).max(), k
+
+
+def test_rga_argument_errors():
+    from musicgeneration_b200 import ops
+    dev = torch.device("cuda:0")
+    q = torch.zeros(1, 8, 3, 1, 48, device=dev)
+    E = torch.zeros(8, 48, device=dev)
+    O_ = torch.zeros(1, 8, 1, 48, device=dev)
+    lse = torch.zeros(1, 1, 8, device=dev)
+    with pytest.raises(RuntimeError, match="head dim"):
+        ops.rga_fwd(q[:, :, 0], q[:, :, 1], q[:, :, 2], (8 * 144, 144, 48), E, None, O_, (8 * 48, 48, 48),
+                    lse, 1, 1, 8, 48, 8, True, path=1)
+    with pytest.raises(RuntimeError, match="bad shape"):
+        ops.rga_fwd(q[:, :, 0], q[:, :, 1], q[:, :, 2], (8 * 144, 144, 48), E, None, O_, (8 * 48, 48, 48),
+                    lse, 1, 1, 8, 64, 4, True, path=1)

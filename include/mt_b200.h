@@ -137,9 +137,11 @@ int mt_adam_step(float* p, const float* g, float* m, float* v, void* p_lp, int64
 /* One decode step for the whole stack is orchestrated by the host mirror from these ops. */
 /* s_j = q.(k_j + E[max_seq-1-(t-j)]) / sqrt(dh), j = 0..t; softmax; .V   -- one new token per
  * sequence.  q: element (b,hh,dd) at q[b*q_stride_b + hh*dh + dd] (dtype); kcache/vcache
- * [B, h, max_seq, dh] (dtype), already holding position t; out [B,h,dh] dense (dtype). */
+ * [B, h, max_seq, dh] (dtype), already holding position t; pad_keys [B, max_seq] uint8 or NULL
+ * (1 = the token at that position is the pad token: key excluded, MT/utils.py:73);
+ * out [B,h,dh] dense (dtype). */
 int mt_rga_decode(const void* q, int64_t q_stride_b, const void* kcache, const void* vcache,
-                  const void* E, void* out, int64_t B, int64_t h, int64_t dh, int64_t max_seq,
+                  const void* E, const uint8_t* pad_keys, void* out, int64_t B, int64_t h, int64_t dh, int64_t max_seq,
                   int64_t t, int dtype, void* stream);
 /* writes k,v [B,h,dh] of the new token into the caches at position t */
 int mt_kv_append(const void* qkv, void* kcache, void* vcache, int64_t B, int64_t h, int64_t dh,

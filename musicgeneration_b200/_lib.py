@@ -46,7 +46,7 @@ SIGNATURES = {
     "mt_smooth_ce_fwd": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _f, _i32, _p]),
     "mt_smooth_ce_bwd": (_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _f, _i32, _p]),
     "mt_adam_step": (_int, [_p, _p, _p, _p, _p, _i64, _f, _f, _f, _f, _i64, _f, _p]),
-    "mt_rga_decode": (_int, [_p, _i64, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _p]),
+    "mt_rga_decode": (_int, [_p, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _p]),
     "mt_kv_append": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _p]),
     "mt_sample": (_int, [_p, _p, _p, _i64, _i64, _f, _i32, _int, _p]),
 }

@@ -10,8 +10,8 @@ namespace mt {
 template <typename T, int DH>
 __global__ void __launch_bounds__(128)
 rga_decode_kernel(const T* __restrict__ q, const T* __restrict__ kc, const T* __restrict__ vc,
-                  const T* __restrict__ E, T* __restrict__ out, int64_t q_stride_b, int h,
-                  int max_seq, int t, float sqrt_dh) {
+                  const T* __restrict__ E, const uint8_t* __restrict__ pad_keys, T* __restrict__ out,
+                  int64_t q_stride_b, int h, int max_seq, int t, float sqrt_dh) {
   extern __shared__ float sm[];
   float* qs = sm;              // [DH]
   float* red = qs + DH;        // [128]
@@ -21,6 +21,7 @@ rga_decode_kernel(const T* __restrict__ q, const T* __restrict__ kc, const T* __
   const int64_t bh = (int64_t)b * h + hh;
   if (tid < DH) qs[tid] = to_f<T>(q[(int64_t)b * q_stride_b + (int64_t)hh * DH + tid]);
   __syncthreads();
+  const uint8_t* pad = pad_keys ? pad_keys + (int64_t)b * max_seq : nullptr;
   const T* kb = kc + bh * (int64_t)max_seq * DH;
   const T* vb = vc + bh * (int64_t)max_seq * DH;
   float mx = -INFINITY;
@@ -36,7 +37,7 @@ rga_decode_kernel(const T* __restrict__ q, const T* __restrict__ kc, const T* __
       acc = fmaf(qs[d + 2], kv.z + ev.z, acc);
       acc = fmaf(qs[d + 3], kv.w + ev.w, acc);
     }
-    acc = acc / sqrt_dh;
+    acc = (pad && pad[j]) ? -INFINITY : acc / sqrt_dh;
     sc[j] = acc;
     mx = fmaxf(mx, acc);
   }
@@ -47,7 +48,7 @@ rga_decode_kernel(const T* __restrict__ q, const T* __restrict__ kc, const T* __
   __syncthreads();
   float sum = 0.f;
   for (int j = tid; j < n; j += 128) {
-    float pv = expf(sc[j] - mx);
+    float pv = (sc[j] == -INFINITY) ? 0.f : expf(sc[j] - mx);
     sc[j] = pv;
     sum += pv;
   }
@@ -69,7 +70,7 @@ rga_decode_kernel(const T* __restrict__ q, const T* __restrict__ kc, const T* __
       float tot = 0.f;
 #pragma unroll
       for (int g = 0; g < NG; ++g) tot += red[g * DH + tid];
-      out[bh * DH + tid] = from_f<T>(tot / sum);
+      out[bh * DH + tid] = from_f<T>(sum > 0.f ? tot / sum : 0.f);
     }
   }
 }
@@ -172,7 +173,7 @@ using namespace mt;
 extern "C" {
 
 int mt_rga_decode(const void* q, int64_t q_stride_b, const void* kcache, const void* vcache,
-                  const void* E, void* out, int64_t B, int64_t h, int64_t dh, int64_t max_seq,
+                  const void* E, const uint8_t* pad_keys, void* out, int64_t B, int64_t h, int64_t dh, int64_t max_seq,
                   int64_t t, int dtype, void* stream) {
   MT_REQUIRE(q && kcache && vcache && E && out, "rga_decode: null pointer");
   MT_REQUIRE(B > 0 && h > 0 && max_seq > 0 && t >= 0 && t < max_seq, "rga_decode: bad shape (t=%ld max_seq=%ld)", (long)t, (long)max_seq);
@@ -184,7 +185,7 @@ int mt_rga_decode(const void* q, int64_t q_stride_b, const void* kcache, const v
   {                                                                                        \
     auto kern = rga_decode_kernel<T, DHC>;                                                 \
     if (smem > 48 * 1024) ae = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    kern<<<grid, 128, smem, as_stream(stream)>>>((const T*)q, (const T*)kcache, (const T*)vcache, (const T*)E, (T*)out, q_stride_b, (int)h, (int)max_seq, (int)t, sqrtf((float)dh)); \
+    kern<<<grid, 128, smem, as_stream(stream)>>>((const T*)q, (const T*)kcache, (const T*)vcache, (const T*)E, pad_keys, (T*)out, q_stride_b, (int)h, (int)max_seq, (int)t, sqrtf((float)dh)); \
   }
   MT_DISPATCH_F32_BF16(dtype, T, {
     if (dh == 32) MT_LAUNCH_DEC(T, 32)

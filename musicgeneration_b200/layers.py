@@ -98,25 +98,26 @@ def _pack_rows(params: Sequence[torch.nn.Parameter]) -> torch.Tensor:
     """Make ``params`` (same trailing shape) adjacent rows of ONE buffer and return that buffer;
     each ``param.data`` becomes a view, so state_dict keys / optimizers are unaffected."""
     first = params[0]
-    ok = all(p.data.is_contiguous() for p in params)
+    tail = tuple(first.shape[1:])
+    rows = sum(p.shape[0] for p in params)
+    es = first.data.element_size()
+    store = first.data.untyped_storage()
+    total = sum(p.data.numel() for p in params)
+    # adjacent means: views of ONE storage at consecutive offsets (address adjacency of separate
+    # allocations does not count -- set_() past the end of a storage would reallocate it)
+    ok = all(p.data.is_contiguous() and p.data.untyped_storage().data_ptr() == store.data_ptr()
+             for p in params)
+    ok = ok and (first.data.storage_offset() + total) * es <= store.nbytes()
     if ok:
-        base = first.data.data_ptr()
-        es = first.data.element_size()
-        off = 0
+        off = first.data.storage_offset()
         for p in params:
-            if p.data.data_ptr() != base + off * es:
+            if p.data.storage_offset() != off:
                 ok = False
                 break
             off += p.data.numel()
-    tail = tuple(first.shape[1:])
-    rows = sum(p.shape[0] for p in params)
     if ok:
-        try:
-            flat = torch.empty(0, dtype=first.dtype, device=first.device).set_(
-                first.data.untyped_storage(), first.data.storage_offset(), (rows,) + tail)
-            return flat
-        except RuntimeError:
-            pass
+        return torch.empty(0, dtype=first.dtype, device=first.device).set_(
+            store, first.data.storage_offset(), (rows,) + tail)
     flat = torch.empty((rows,) + tail, dtype=first.dtype, device=first.device)
     r = 0
     for p in params:

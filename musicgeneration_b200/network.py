@@ -158,6 +158,9 @@ class _DecodeSession:
         shape = (B, cfg.h, cfg.max_seq, cfg.dh)
         self.kc = [torch.zeros(shape, dtype=cfg.act, device=dev) for _ in self.Ws]
         self.vc = [torch.zeros(shape, dtype=cfg.act, device=dev) for _ in self.Ws]
+        # pad bit per cached position: a generated/prior pad token is masked as a key, exactly as
+        # the look-ahead mask of MT/utils.py:73 does in the reference's recompute
+        self.pad_bits = torch.zeros((B, cfg.max_seq), dtype=torch.uint8, device=dev)
 
     def step(self, tok: torch.Tensor, t: int) -> torch.Tensor:
         """tok int32 [B] at position t -> logits fp32 [B, V] for position t+1."""
@@ -166,6 +169,7 @@ class _DecodeSession:
         lp = cfg.act != torch.float32
         dev = self.emb.device
         ids = tok.reshape(B, 1).contiguous()
+        self.pad_bits[:, t] = (tok == config.pad_token)
         x = torch.empty((B, d), dtype=torch.float32, device=dev)
         x_lp = torch.empty((B, d), dtype=cfg.act, device=dev) if lp else None
         ops.embed_pos_fwd(ids, self.emb, self.pe, x, x_lp, t, math.sqrt(d), 0.0, 0, 0)
@@ -175,7 +179,7 @@ class _DecodeSession:
             engine.linear_fwd(xl, W.Wqkv, W.bqkv, qkv, cfg)
             ops.kv_append(qkv, self.kc[li], self.vc[li], B, h, dh, cfg.max_seq, t)
             o = torch.empty((B, d), dtype=cfg.act, device=dev)
-            ops.rga_decode(qkv, 3 * d, self.kc[li], self.vc[li], W.E, o, B, h, dh, cfg.max_seq, t)
+            ops.rga_decode(qkv, 3 * d, self.kc[li], self.vc[li], W.E, self.pad_bits, o, B, h, dh, cfg.max_seq, t)
             a = torch.empty((B, d), dtype=torch.float32, device=dev)
             engine.linear_fwd(o, W.Wfc, W.bfc, a, cfg)
             out1 = torch.empty((B, d), dtype=torch.float32, device=dev)

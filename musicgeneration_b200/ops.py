@@ -22,7 +22,11 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+LAUNCH_CALLS = [0]      # number of launching C-ABI calls made so far (each enqueues >= 1 kernel)
+
+
 def _stream():
+    LAUNCH_CALLS[0] += 1
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -178,9 +182,9 @@ def adam_step(p, g, m, v, p_lp, lr, beta1, beta2, eps, step, grad_scale):
                                   beta1, beta2, eps, step, grad_scale, _stream()), "adam_step")
 
 
-def rga_decode(q, q_stride_b, kcache, vcache, E, out, B, h, dh, max_seq, t):
+def rga_decode(q, q_stride_b, kcache, vcache, E, pad_keys, out, B, h, dh, max_seq, t):
     L.check(L.load().mt_rga_decode(_ptr(q), q_stride_b, _ptr(kcache), _ptr(vcache), _ptr(E),
-                                   _ptr(out), B, h, dh, max_seq, t, dt(q), _stream()), "rga_decode")
+                                   _ptr(pad_keys), _ptr(out), B, h, dh, max_seq, t, dt(q), _stream()), "rga_decode")
 
 
 def kv_append(qkv, kcache, vcache, B, h, dh, max_seq, t):

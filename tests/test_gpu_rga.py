@@ -122,7 +122,7 @@ def test_rga_module_against_reference_fixture(case, tag):
     out, w = rga([x, x, x], mask)
     np.testing.assert_allclose(out.detach().cpu().numpy(), z[f"{case}:{tag}:out"], atol=5e-5)
     if case == "a":
-        np.testing.assert_allclose(w.cpu().numpy(), z[f"{case}:{tag}:w"], atol=3e-6)
+        np.testing.assert_allclose(w.cpu().numpy(), z[f"{case}:{tag}:w"], atol=2e-5)
     wgt = torch.cos(torch.arange(out.numel(), dtype=torch.float32)).reshape(out.shape).to(dev)
     (out * wgt).sum().backward()
     np.testing.assert_allclose(x.grad.cpu().numpy(), z[f"{case}:{tag}:dx"], atol=1e-3, rtol=2e-4)

@@ -1,12 +1,380 @@
-// tcgen05 GEMM -- placeholder until the tensor-core kernel lands (next commit).
+// tcgen05 GEMM for the nn.Linear layers of the path (K5): C[M,N] = epi(op(A) . op(B)),
+// bf16 (or f16) operands, fp32 accumulation in TMEM, fused bias / ReLU / residual-add /
+// ReLU-mask epilogue, fp32 or bf16 output.
+//
+//   * 128 x 128 output tile per CTA, K blocked by 64; operands arrive by TMA
+//     (cp.async.bulk.tensor, 128B swizzle) into a 3-stage shared-memory ring;
+//   * one elected thread issues tcgen05.mma (M=128, N=128, K=16) with the accumulator in
+//     128 TMEM columns; tcgen05.commit releases ring slots and signals the epilogue;
+//   * warp roles: 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = epilogue
+//     (tcgen05.ld 32x32b, lane = output row);
+//   * both operand majors are supported through the UMMA descriptors, so forward (A K-major,
+//     B = W[N,K] K-major), dgrad (B = W[N,K] read as [K,N]: MN-major) and wgrad (A = dY[T,N]
+//     read as [N,T]^T: MN-major, B = X[T,K]: MN-major) need no transposed copies;
+//   * ~100 KB of shared memory and 128 TMEM columns per CTA -> two CTAs per SM, so one CTA's
+//     epilogue overlaps the other's main loop; skinny outputs (weight gradients) use a
+//     deterministic split-K through the caller's workspace.
 #include "ops.cuh"
+#include "tc_common.cuh"
+
 namespace mt {
-bool gemm_tc_supported(int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, int, int, int,
-                       const void*, const void*, const void*) { return false; }
-size_t gemm_tc_workspace_bytes(int64_t, int64_t, int64_t) { return 0; }
-int gemm_tc(const void*, const void*, void*, const float*, const float*, const void*, int64_t, int64_t,
-            int64_t, int64_t, int64_t, int64_t, int, int, int, int, int, void*, size_t, cudaStream_t) {
-  set_error("gemm_tc: not built");
-  return MT_E_UNSUPPORTED;
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 2;          // 16 KB per operand tile
+constexpr int TC_THREADS = 192;
+constexpr int TMEM_COLS = 128;
+constexpr size_t SMEM_BYTES = 2 * STAGES * TILE_BYTES + 256 + 1024;
+
+struct TcGemmParams {
+  void* C;
+  const float* bias;
+  const float* addend;
+  const void* aux;
+  int64_t M, N, K, ldc;
+  int epi, out_bf16, vec_ok;
+  int splits;
+  int64_t k_per_split;
+  float* part;
+};
+
+__device__ __forceinline__ void epilogue_row(const TcGemmParams& p, int64_t row, int64_t n, const float (&v)[32]) {
+  // v[j] = accumulator at (row, n + j)
+  if (p.splits > 1) {
+    float* dst = p.part + ((int64_t)blockIdx.z * p.M + row) * p.N + n;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n + j < p.N) dst[j] = v[j];
+    return;
+  }
+  const int64_t off = row * p.ldc + n;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    float o[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
+    const bool full = (n + j + 3 < p.N);
+    if (full && p.vec_ok) {
+      if (p.epi & MT_EPI_BIAS) {
+        float4 b = *reinterpret_cast<const float4*>(p.bias + n + j);
+        o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
+      }
+      if (p.epi & MT_EPI_ADD) {
+        float4 a = *reinterpret_cast<const float4*>(p.addend + off + j);
+        o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
+      }
+      if (p.epi & MT_EPI_RELU) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) o[t] = fmaxf(o[t], 0.f);
+      }
+      if (p.epi & MT_EPI_RELU_MASK) {
+        float4 m = load4<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + off + j);
+        if (!(m.x > 0.f)) o[0] = 0.f;
+        if (!(m.y > 0.f)) o[1] = 0.f;
+        if (!(m.z > 0.f)) o[2] = 0.f;
+        if (!(m.w > 0.f)) o[3] = 0.f;
+      }
+      float4 r = make_float4(o[0], o[1], o[2], o[3]);
+      if (p.out_bf16) store4<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.C) + off + j, r);
+      else store4<float>(reinterpret_cast<float*>(p.C) + off + j, r);
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int64_t nn = n + j + t;
+        if (nn >= p.N) continue;
+        float x = o[t];
+        if (p.epi & MT_EPI_BIAS) x += p.bias[nn];
+        if (p.epi & MT_EPI_ADD) x += p.addend[off + j + t];
+        if (p.epi & MT_EPI_RELU) x = fmaxf(x, 0.f);
+        if (p.epi & MT_EPI_RELU_MASK) {
+          if (!(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.aux)[off + j + t]) > 0.f)) x = 0.f;
+        }
+        if (p.out_bf16) reinterpret_cast<__nv_bfloat16*>(p.C)[off + j + t] = __float2bfloat16_rn(x);
+        else reinterpret_cast<float*>(p.C)[off + j + t] = x;
+      }
+    }
+  }
 }
+
+template <int A_MN, int B_MN>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TcGemmParams p, const int fmt) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * TILE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * TILE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int64_t kbeg = (int64_t)blockIdx.z * p.k_per_split;
+  const int64_t kend = min(p.K, kbeg + p.k_per_split);
+  const int nkb = (int)((kend - kbeg + BK - 1) / BK);
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmA);
+    tc::tma_prefetch_desc(&tmB);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(&full[s], 1);
+      tc::mbar_init(&empty[s], 1);
+    }
+    tc::mbar_init(tmem_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        tc::mbar_wait(&empty[s], ph ^ 1);
+        tc::mbar_arrive_expect_tx(&full[s], 2 * TILE_BYTES);
+        const int k = (int)(kbeg + (int64_t)kb * BK);
+        uint8_t* a = sA + s * TILE_BYTES;
+        uint8_t* b = sB + s * TILE_BYTES;
+        if (A_MN) {
+          tc::tma_load_2d(a, &tmA, &full[s], m0, k);
+          tc::tma_load_2d(a + TILE_BYTES / 2, &tmA, &full[s], m0 + 64, k);
+        } else {
+          tc::tma_load_2d(a, &tmA, &full[s], k, m0);
+        }
+        if (B_MN) {
+          tc::tma_load_2d(b, &tmB, &full[s], n0, k);
+          tc::tma_load_2d(b + TILE_BYTES / 2, &tmB, &full[s], n0 + 64, k);
+        } else {
+          tc::tma_load_2d(b, &tmB, &full[s], k, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc(BM, BN, fmt, fmt, A_MN, B_MN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        tc::mbar_wait(&full[s], ph);
+        tc::tc_fence_after();
+        const uint32_t a_base = tc::smem_u32(sA + s * TILE_BYTES);
+        const uint32_t b_base = tc::smem_u32(sB + s * TILE_BYTES);
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 16; ++k4) {
+          // K-major: 16 elements = 32 B inside the 128 B swizzle row; 8-row groups 1024 B apart.
+          // MN-major: 16 k-rows of 128 B = 2048 B; the two 64-wide MN halves are 8192 B apart.
+          const uint64_t ad = A_MN ? tc::make_sdesc(a_base + k4 * 2048, TILE_BYTES / 2, 1024)
+                                   : tc::make_sdesc(a_base + k4 * 32, 16, 1024);
+          const uint64_t bd = B_MN ? tc::make_sdesc(b_base + k4 * 2048, TILE_BYTES / 2, 1024)
+                                   : tc::make_sdesc(b_base + k4 * 32, 16, 1024);
+          tc::umma_f16(tmem_base, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
+        }
+        tc::umma_commit(&empty[s]);
+      }
+      tc::umma_commit(tmem_full);
+    }
+  } else {
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    tc::mbar_wait(tmem_full, 0);
+    tc::tc_fence_after();
+    const int64_t row = (int64_t)m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      tc::tmem_ld_wait();
+      if (row < p.M && n0 + c * 32 < p.N) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        epilogue_row(p, row, (int64_t)n0 + c * 32, v);
+      }
+    }
+    tc::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+__global__ void __launch_bounds__(256) tc_splitk_fold_kernel(TcGemmParams p) {
+  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= p.M * p.N) return;
+  int64_t m = idx / p.N, n = idx - m * p.N;
+  float s = 0.f;
+  for (int z = 0; z < p.splits; ++z) s += p.part[((int64_t)z * p.M + m) * p.N + n];
+  if (p.epi & MT_EPI_BIAS) s += p.bias[n];
+  if (p.epi & MT_EPI_ADD) s += p.addend[m * p.ldc + n];
+  if (p.epi & MT_EPI_RELU) s = fmaxf(s, 0.f);
+  if (p.epi & MT_EPI_RELU_MASK) {
+    if (!(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.aux)[m * p.ldc + n]) > 0.f)) s = 0.f;
+  }
+  if (p.out_bf16) reinterpret_cast<__nv_bfloat16*>(p.C)[m * p.ldc + n] = __float2bfloat16_rn(s);
+  else reinterpret_cast<float*>(p.C)[m * p.ldc + n] = s;
+}
+
+int tc_splits(int64_t M, int64_t N, int64_t K) {
+  int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  if (tiles >= sm_count() || K < 2048) return 1;
+  int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;
+  int64_t maxs = K / 512;
+  if (want > maxs) want = maxs;
+  if (want > 32) want = 32;
+  return want < 1 ? 1 : (int)want;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// tensor maps (driver entry point resolved at run time)
+// ---------------------------------------------------------------------------------------
+namespace tc {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                 int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return MT_E_UNSUPPORTED; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(2d rows=%ld cols=%ld ld=%ld box=%dx%d) failed: %d", (long)rows, (long)cols,
+              (long)ld, box_cols, box_rows, (int)r);
+    return MT_E_ARG;
+  }
+  return 0;
+}
+
+int make_tmap_3d(CUtensorMap* map, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t s1_elems,
+                 int64_t s2_elems, int box0, int box1, int box2) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return MT_E_UNSUPPORTED; }
+  cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t strides[2] = {(cuuint64_t)s1_elems * 2, (cuuint64_t)s2_elems * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, (cuuint32_t)box2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d %ldx%ldx%ld) failed: %d", (long)d0, (long)d1, (long)d2, (int)r);
+    return MT_E_ARG;
+  }
+  return 0;
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------
+// launcher
+// ---------------------------------------------------------------------------------------
+bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int transA,
+                       int transB, int in_dtype, int out_dtype, int epilogue, const void* A, const void* B,
+                       const void* C) {
+  (void)epilogue; (void)C;
+  if (in_dtype != MT_BF16 && in_dtype != MT_F16) return false;
+  if (out_dtype != MT_F32 && out_dtype != MT_BF16) return false;
+  if (transA && !(transA && !transB)) return false;                 // TN only (wgrad form)
+  if (!aligned(A, 16) || !aligned(B, 16)) return false;
+  if (lda % 8 || ldb % 8) return false;
+  if (M < 64 || N < 8 || K < 16) return false;                      // tiny problems: SIMT path
+  if (M > (1ll << 31) - 256 || N > (1ll << 31) - 256 || K > (1ll << 31) - 256) return false;
+  (void)ldc;
+  return mt_device_ok() != 0;
+}
+
+size_t gemm_tc_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+  int s = tc_splits(M, N, K);
+  return s > 1 ? (size_t)s * M * N * sizeof(float) : 0;
+}
+
+int gemm_tc(const void* A, const void* B, void* C, const float* bias, const float* addend, const void* aux,
+            int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int transA, int transB,
+            int in_dtype, int out_dtype, int epilogue, void* workspace, size_t workspace_bytes,
+            cudaStream_t stream) {
+  CUtensorMap tmA, tmB;
+  int rc;
+  const int a_mn = transA ? 1 : 0;        // stored [K, M]: M contiguous
+  const int b_mn = transB ? 0 : 1;        // stored [K, N]: N contiguous
+  if (a_mn) rc = tc::make_tmap_2d(&tmA, A, K, M, lda, 64, BK);
+  else rc = tc::make_tmap_2d(&tmA, A, M, K, lda, BK, BM);
+  if (rc) return rc;
+  if (b_mn) rc = tc::make_tmap_2d(&tmB, B, K, N, ldb, 64, BK);
+  else rc = tc::make_tmap_2d(&tmB, B, N, K, ldb, BK, BN);
+  if (rc) return rc;
+
+  TcGemmParams p;
+  p.C = C; p.bias = bias; p.addend = addend; p.aux = aux;
+  p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.epi = epilogue;
+  p.out_bf16 = (out_dtype == MT_BF16);
+  const int oes = p.out_bf16 ? 2 : 4;
+  p.vec_ok = (ldc % 4 == 0) && aligned(C, 4 * oes) && (!(epilogue & MT_EPI_BIAS) || aligned(bias, 16)) &&
+             (!(epilogue & MT_EPI_ADD) || aligned(addend, 16)) && (!(epilogue & MT_EPI_RELU_MASK) || aligned(aux, 8));
+  p.splits = tc_splits(M, N, K);
+  if (p.splits > 1 && (!workspace || workspace_bytes < (size_t)p.splits * M * N * sizeof(float))) p.splits = 1;
+  p.k_per_split = K;
+  if (p.splits > 1) {
+    int64_t kps = (((K + p.splits - 1) / p.splits + BK - 1) / BK) * BK;
+    p.k_per_split = kps;
+    p.splits = (int)((K + kps - 1) / kps);            // every split owns at least one k-block
+  }
+  p.part = reinterpret_cast<float*>(workspace);
+  const int fmt = (in_dtype == MT_BF16) ? 1 : 0;
+
+  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)p.splits);
+  cudaError_t e = cudaSuccess;
+#define MT_TC_LAUNCH(AM, BMJ)                                                                         \
+  {                                                                                                   \
+    auto kern = gemm_tc_kernel<AM, BMJ>;                                                              \
+    static bool attr_done = false;                                                                    \
+    if (!attr_done) {                                                                                 \
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);   \
+      attr_done = (e == cudaSuccess);                                                                 \
+    }                                                                                                 \
+    if (e == cudaSuccess) kern<<<grid, TC_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p, fmt);           \
+  }
+  if (!a_mn && !b_mn) MT_TC_LAUNCH(0, 0)
+  else if (!a_mn && b_mn) MT_TC_LAUNCH(0, 1)
+  else if (a_mn && b_mn) MT_TC_LAUNCH(1, 1)
+  else { set_error("gemm_tc: unsupported operand majors"); return MT_E_UNSUPPORTED; }
+#undef MT_TC_LAUNCH
+  if (e != cudaSuccess) { set_error("gemm_tc: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+  rc = check_launch("gemm_tc");
+  if (rc) return rc;
+  if (p.splits > 1) {
+    int64_t n = M * N;
+    tc_splitk_fold_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p);
+    rc = check_launch("gemm_tc_fold");
+  }
+  return rc;
+}
+
 }  // namespace mt

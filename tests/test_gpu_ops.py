@@ -267,3 +267,63 @@ def test_sampler(dev):
     freq = torch.stack([(o2.cpu() == i).float().mean() for i in (1, 2, 3)])
     assert set(o2.cpu().tolist()) <= {1, 2, 3}
     assert (freq - pr).abs().max() < 0.015
+
+
+# ---------------------------------------------------------------------------------------
+# tcgen05 GEMM (path=2): same contract as the SIMT kernel, bf16 operands
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (384, 512, 512), (300, 390, 512),
+                                   (4096, 1536, 512), (200, 136, 200), (1000, 256, 72)])
+@pytest.mark.parametrize("tA,tB", [(False, True), (False, False), (True, False)])
+def test_gemm_tc(dev, M, N, K, tA, tB):
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + N * 3 + K * 5 + tA * 11 + tB * 13)
+
+    def pad8(n):
+        return (n + 7) // 8 * 8
+    # leading dimensions padded to a multiple of 8 elements (TMA needs 16-byte row pitch)
+    a_shape = (K, M) if tA else (M, K)
+    b_shape = (N, K) if tB else (K, N)
+    A_full = torch.randn(a_shape[0], pad8(a_shape[1]), generator=g).to(torch.bfloat16)
+    B_full = torch.randn(b_shape[0], pad8(b_shape[1]), generator=g).to(torch.bfloat16)
+    A = A_full[:, :a_shape[1]]
+    B = B_full[:, :b_shape[1]]
+    bias = torch.randn(N, generator=g)
+    ldc = pad8(N)
+    add = torch.randn(M, ldc, generator=g)
+    aux = torch.randn(M, ldc, generator=g).to(torch.bfloat16)
+    ref = (A.double().t() if tA else A.double()) @ (B.double().t() if tB else B.double())
+    Ad, Bd = A_full.to(dev), B_full.to(dev)
+    C = torch.full((M, ldc), 7.0, dtype=torch.float32, device=dev)
+    ops.gemm(Ad, Bd, C, M, N, K, Ad.stride(0), Bd.stride(0), ldc, tA, tB, path=2)
+    assert rel(C[:, :N].cpu(), ref) < 2e-6, rel(C[:, :N].cpu(), ref)
+    if ldc > N:
+        assert float((C[:, N:] - 7.0).abs().max()) == 0.0      # nothing written past N
+    C2 = torch.zeros((M, ldc), dtype=torch.bfloat16, device=dev)
+    ops.gemm(Ad, Bd, C2, M, N, K, Ad.stride(0), Bd.stride(0), ldc, tA, tB, bias=bias.to(dev),
+             addend=add.to(dev), relu=True, path=2)
+    ref2 = torch.relu(ref + bias.double() + add[:, :N].double())
+    assert rel(C2[:, :N].float().cpu(), ref2) < 4e-3
+    C3 = torch.zeros((M, ldc), dtype=torch.float32, device=dev)
+    ops.gemm(Ad, Bd, C3, M, N, K, Ad.stride(0), Bd.stride(0), ldc, tA, tB, aux=aux.to(dev), relu_mask=True,
+             path=2)
+    assert rel(C3[:, :N].cpu(), ref * (aux[:, :N].double() > 0)) < 2e-6
+    # unpadded ldc (scalar store path), e.g. the logits [T, 390]
+    C4 = torch.empty((M, N), dtype=torch.float32, device=dev)
+    ops.gemm(Ad, Bd, C4, M, N, K, Ad.stride(0), Bd.stride(0), N, tA, tB, bias=bias.to(dev), path=2)
+    assert rel(C4.cpu(), ref + bias.double()) < 2e-6
+
+
+def test_gemm_tc_split_k_weight_gradient_shape(dev):
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    T, N, K = 8192, 512, 256                    # dW[N,K] = dY[T,N]^T . X[T,K]
+    dY = torch.randn(T, N, generator=g).to(torch.bfloat16)
+    X = torch.randn(T, K, generator=g).to(torch.bfloat16)
+    ref = dY.double().t() @ X.double()
+    dW = torch.empty(N, K, dtype=torch.float32, device=dev)
+    ops.gemm(dY.to(dev), X.to(dev), dW, N, K, T, N, K, K, True, False, path=2)
+    assert rel(dW.cpu(), ref) < 3e-6
+    dW2 = torch.empty(N, K, dtype=torch.float32, device=dev)
+    ops.gemm(dY.to(dev), X.to(dev), dW2, N, K, T, N, K, K, True, False, path=2)
+    assert torch.equal(dW, dW2)                 # deterministic split-K

@@ -291,6 +291,26 @@ int make_tmap_3d(CUtensorMap* map, const void* base, int64_t d0, int64_t d1, int
   return 0;
 }
 
+int make_tmap_blhd(CUtensorMap* map, const void* base, int64_t dh, int64_t L, int64_t h, int64_t B, int64_t sl,
+                   int64_t sh, int64_t sb, int box_d, int box_l) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return MT_E_UNSUPPORTED; }
+  // dimension order {dh, h, L, B}: strides increase (sh < sl < sb for the packed qkv / O layouts)
+  cuuint64_t dims[4] = {(cuuint64_t)dh, (cuuint64_t)h, (cuuint64_t)L, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)sh * 2, (cuuint64_t)sl * 2, (cuuint64_t)sb * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_d, 1, (cuuint32_t)box_l, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d dh=%ld L=%ld h=%ld B=%ld sl=%ld sh=%ld sb=%ld) failed: %d", (long)dh,
+              (long)L, (long)h, (long)B, (long)sl, (long)sh, (long)sb, (int)r);
+    return MT_E_ARG;
+  }
+  return 0;
+}
+
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------

@@ -105,6 +105,56 @@ def test_rga_simt_bf16_io(B, h, L, dh, max_seq, causal):
     assert r["o"] < 4e-3 and max(r["dq"], r["dk"], r["dv"], r["dE"]) < 8e-3, r
 
 
+def run_fwd_tc(B, h, L, dh, max_seq, causal, pad, dtype, seed=0, scale=1.0):
+    """tcgen05 forward (path=2) vs the fp64 oracle on the same 16-bit-rounded inputs."""
+    from musicgeneration_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(seed)
+    d = h * dh
+    qkv = (torch.randn(B, L, 3, h, dh, generator=g) * scale).to(dtype)
+    E = torch.randn(max_seq, dh, generator=g).to(dtype)
+    pad_keys = None
+    if pad:
+        pad_keys = torch.zeros(B, L, dtype=torch.bool)
+        pad_keys[0, L // 2:L // 2 + 3] = True
+        pad_keys[B - 1, L - 5:] = True
+    q, k, v = [qkv[:, :, i].permute(0, 2, 1, 3).double() for i in range(3)]
+    o_ref, lse_ref = O.rga_closed_form(q, k, v, E.double(), max_seq, causal, pad_keys)
+    qkv_d, Ed = qkv.to(dev), E.to(dev)
+    Od = torch.zeros(B, L, h, dh, dtype=dtype, device=dev)
+    lse = torch.zeros(B, h, L, device=dev)
+    pk = pad_keys.to(torch.uint8).to(dev) if pad_keys is not None else None
+    ops.rga_fwd(qkv_d[:, :, 0], qkv_d[:, :, 1], qkv_d[:, :, 2], (L * 3 * d, 3 * d, dh), Ed, pk, Od,
+                (L * d, d, dh), lse, B, h, L, dh, max_seq, causal, path=2)
+    torch.cuda.synchronize()
+    o = Od.float().cpu().permute(0, 2, 1, 3)
+    return dict(o=rel(o, o_ref), lse=float((lse.cpu().double() - lse_ref).abs().max()),
+                omax=float((o.double() - o_ref).abs().max()))
+
+
+@pytest.mark.parametrize("B,h,L,max_seq,causal,pad", [
+    (1, 1, 128, 128, True, False),
+    (2, 2, 256, 256, True, False),
+    (2, 4, 512, 512, True, False),
+    (1, 2, 200, 256, True, False),          # ragged L, L < max_seq
+    (1, 2, 384, 512, True, True),           # max_seq - L not a tile multiple of the band, pads
+    (2, 2, 256, 256, False, False),         # generate(): no mask
+    (1, 2, 300, 300, False, True),
+    (1, 8, 2048, 2048, True, False),        # BASELINE shape (one sequence)
+])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_rga_fwd_tcgen05(B, h, L, max_seq, causal, pad, dtype):
+    r = run_fwd_tc(B, h, L, 64, max_seq, causal, pad, dtype, seed=L + h)
+    # operands are exact; P is rounded to 16 bits before P.V and the output is 16-bit
+    tol = 6e-3 if dtype == torch.bfloat16 else 1.5e-3
+    assert r["o"] < tol and r["lse"] < 2e-3, r
+
+
+def test_rga_fwd_tcgen05_large_logits():
+    r = run_fwd_tc(1, 2, 256, 64, 256, True, False, torch.bfloat16, seed=5, scale=6.0)
+    assert r["o"] < 8e-3 and r["lse"] < 2e-2, r
+
+
 @pytest.mark.parametrize("case", ["a", "b", "c", "d"])
 @pytest.mark.parametrize("tag", ["none", "causal"])
 def test_rga_module_against_reference_fixture(case, tag):

@@ -25,6 +25,7 @@ int gemm_simt(const void* A, const void* B, void* C, const float* bias, const fl
 int rga_fwd_simt(const RgaArgs& a, int dh, int dtype, cudaStream_t st);
 int rga_weights_simt(const RgaArgs& a, int dh, int dtype, cudaStream_t st);
 int rga_bwd_simt(const RgaArgs& a, int dh, int dtype, cudaStream_t st);
+int rga_delta_launch(const RgaArgs& a, int dh, int dtype, cudaStream_t st);   // delta = rowsum(dO * O)
 // gemm_tc.cu / rga_tc.cu (tcgen05)
 bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc,
                        int transA, int transB, int in_dtype, int out_dtype, int epilogue,

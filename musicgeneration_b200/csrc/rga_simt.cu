@@ -496,6 +496,14 @@ int rga_weights_simt(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
   return check_launch("rga_weights");
 }
 
+int rga_delta_launch(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
+  MT_DISPATCH_DTYPE(dtype, T, {
+    int64_t rows = (int64_t)a.B * a.h * a.L;
+    rga_delta_kernel<T><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(a, dh);
+  });
+  return check_launch("rga_delta");
+}
+
 int rga_bwd_simt(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
   int rc = 0;
   MT_DISPATCH_F32_BF16(dtype, T, MT_DISPATCH_DH(dh, DHC, {

@@ -330,8 +330,10 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
 }  // namespace
 
+bool rga_bwd_tc_supported(const RgaArgs& a, int dh, int dtype);   // rga_tc_bwd.cu
+
 bool rga_tc_supported(const RgaArgs& a, int dh, int dtype, bool backward) {
-  if (backward) return false;
+  if (backward) return rga_bwd_tc_supported(a, dh, dtype);
   if (dh != DHC) return false;
   if (dtype != MT_BF16 && dtype != MT_F16) return false;
   if (a.sl % 8 || a.sh % 8 || a.sb % 8) return false;
@@ -363,11 +365,6 @@ int rga_fwd_tc(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
   dim3 grid((a.L + QT - 1) / QT, a.h, a.B);
   rga_fwd_tc_kernel<<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmQ, tmK, tmV, tmE, p);
   return check_launch("rga_fwd_tc");
-}
-
-int rga_bwd_tc(const RgaArgs&, int, int, cudaStream_t) {
-  set_error("rga_bwd_tc: not built");
-  return MT_E_UNSUPPORTED;
 }
 
 }  // namespace mt

@@ -1,0 +1,540 @@
+// Backward of the fused relative global attention on tcgen05 / TMEM / TMA (K2), head dim 64, bf16,
+// causal (+ key padding).  Math (per (b,h)):
+//     P = exp(S - lse),  S = (Q K^T + skew(Q E_band^T)) / sqrt(dh)
+//     dP = dO V^T ;  dS = P o (dP - D) / sqrt(dh),  D = rowsum(dO o O)
+//     dV = P^T dO ;  dK = dS^T Q ;  dQ = dS K + dG E_band ;  dE_band = dG^T Q,
+// where dG is dS written back into band coordinates (dG[a][127-a+b] = dS[a][b]) -- the inverse of
+// the forward skew.  One kernel template, three roles, all sharing the "recompute the P / dS tile"
+// core (TMA loads -> S, G_lo, G_hi, dP on the tensor cores -> skew through a row-private shared
+// scratch -> P, dS, dG written as 128B-swizzled UMMA operands):
+//   * DKV : CTA owns a key tile, walks the query tiles at or below it; dK, dV accumulate in TMEM;
+//   * DQ  : CTA owns a query tile, walks its key tiles; dQ (both the K and the relative-embedding
+//           part) accumulates in TMEM;
+//   * DE  : CTA owns one tile-diagonal (i0 - j0 fixed => the same two 128-row blocks of E for every
+//           step) and walks down it over a slice of (batch, head); dE accumulates in TMEM over the
+//           whole walk and is added to global memory once per CTA.
+// No output needs per-step global atomics; the price is that S/P are recomputed per role.
+// The same shared-memory tile serves as K-major and as MN-major UMMA operand (rows of 128 bytes,
+// 8-row swizzle atoms), so no transposed copies exist anywhere.
+#include "ops.cuh"
+#include "tc_common.cuh"
+
+namespace mt {
+
+namespace {
+
+constexpr int TT = 128;                 // tile edge (queries and keys)
+constexpr int DHC = 64;
+constexpr int TILE = TT * DHC * 2;      // 16 KB
+constexpr int SCR_PITCH = 52;           // floats; == 20 mod 32 -> conflict-free 128-bit row stores
+constexpr int SCR_BYTES = TT * SCR_PITCH * 4;
+constexpr int BWD_THREADS = 192;
+constexpr float LOG2E = 1.4426950408889634f;
+
+enum { MODE_DKV = 0, MODE_DQ = 1, MODE_DE = 2 };
+
+// TMEM columns
+constexpr uint32_t TM_S = 0, TM_GLO = 128, TM_GHI = 256, TM_ACC0 = 384, TM_ACC1 = 448;
+constexpr uint32_t TM_DP = TM_GLO;      // dP reuses the G_lo columns once the skew has been read
+
+template <int MODE> struct Lay;
+template <> struct Lay<MODE_DKV> {       // K,V resident; {Q,dO,E_lo,E_hi} double buffered
+  static constexpr int NST = 2;
+  static constexpr int K = 0, V = TILE, STAGE0 = 2 * TILE, STAGE_BYTES = 4 * TILE;
+  static constexpr int sQ = 0, sDO = TILE, sELO = 2 * TILE, sEHI = 3 * TILE;
+  static constexpr int P = STAGE0 + 2 * STAGE_BYTES, DS = P + 2 * TILE, BAR = DS + 2 * TILE;
+  static constexpr int RES_TILES = 2, STAGE_TILES = 4;
+};
+template <> struct Lay<MODE_DQ> {        // Q,dO resident; {K,V,E_lo,E_hi} per step
+  static constexpr int NST = 1;
+  static constexpr int Q = 0, DO = TILE, STAGE0 = 2 * TILE, STAGE_BYTES = 4 * TILE;
+  static constexpr int sK = 0, sV = TILE, sELO = 2 * TILE, sEHI = 3 * TILE;
+  static constexpr int DS = STAGE0 + STAGE_BYTES, DG = DS + 2 * TILE, SCR = DG + 4 * TILE, BAR = SCR + SCR_BYTES;
+  static constexpr int RES_TILES = 2, STAGE_TILES = 4;
+};
+template <> struct Lay<MODE_DE> {        // E_lo,E_hi resident; {Q,dO,K,V} per step
+  static constexpr int NST = 1;
+  static constexpr int ELO = 0, EHI = TILE, STAGE0 = 2 * TILE, STAGE_BYTES = 4 * TILE;
+  static constexpr int sQ = 0, sDO = TILE, sK = 2 * TILE, sV = 3 * TILE;
+  static constexpr int DG = STAGE0 + STAGE_BYTES, SCR = DG + 4 * TILE, BAR = SCR + SCR_BYTES;
+  static constexpr int RES_TILES = 2, STAGE_TILES = 4;
+};
+template <int MODE> constexpr int smem_bytes() { return Lay<MODE>::BAR + 256 + 1024; }
+
+struct BwdParams {
+  void* dq; void* dk; void* dv;          // 16-bit, q/k/v addressing
+  int64_t sb, sl, sh;
+  float* dE;
+  const float* lse; const float* delta;
+  const uint8_t* pad;
+  int B, h, L, max_seq, nT;
+  int bh_per_cta;                        // DE role
+  float scale, scale_log2;
+};
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+struct StepInfo { int it, jt, b, hh; };
+
+template <int MODE>
+__device__ __forceinline__ int num_steps(const BwdParams& p, int& bh0) {
+  bh0 = 0;
+  if (MODE == MODE_DKV) return p.nT - (int)blockIdx.x;
+  if (MODE == MODE_DQ) return p.nT - (int)blockIdx.x;          // it = nT-1-blockIdx.x  -> it+1 steps
+  bh0 = (int)blockIdx.y * p.bh_per_cta;
+  int nbh = min(p.bh_per_cta, p.B * p.h - bh0);
+  return nbh > 0 ? nbh * (p.nT - (int)blockIdx.x) : 0;
+}
+template <int MODE>
+__device__ __forceinline__ StepInfo step_info(const BwdParams& p, int n, int bh0) {
+  StepInfo s;
+  if (MODE == MODE_DKV) { s.jt = blockIdx.x; s.it = s.jt + n; s.hh = blockIdx.y; s.b = blockIdx.z; }
+  else if (MODE == MODE_DQ) { s.it = p.nT - 1 - (int)blockIdx.x; s.jt = n; s.hh = blockIdx.y; s.b = blockIdx.z; }
+  else {
+    const int per = p.nT - (int)blockIdx.x;
+    const int bh = bh0 + n / per, k = n % per;
+    s.it = (int)blockIdx.x + k; s.jt = k; s.b = bh / p.h; s.hh = bh % p.h;
+  }
+  return s;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                  const __grid_constant__ CUtensorMap tmE, const BwdParams p) {
+  using LY = Lay<MODE>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LY::BAR);
+  uint64_t* bar_res = bars + 0;
+  uint64_t* ld_full = bars + 1;       // [2]
+  uint64_t* ld_empty = bars + 3;      // [2]
+  uint64_t* sg_full = bars + 5;
+  uint64_t* sg_consumed = bars + 6;
+  uint64_t* dp_full = bars + 7;
+  uint64_t* ds_ready = bars + 8;
+  uint64_t* step_done = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint8_t* spad = reinterpret_cast<uint8_t*>(bars + 11);      // [128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int bh0;
+  const int nsteps = num_steps<MODE>(p, bh0);
+
+  if (warp == 4 && lane == 0) {
+    tc::tma_prefetch_desc(&tmQ); tc::tma_prefetch_desc(&tmK); tc::tma_prefetch_desc(&tmV);
+    tc::tma_prefetch_desc(&tmDO); tc::tma_prefetch_desc(&tmE);
+    tc::mbar_init(bar_res, 1);
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&ld_full[s], 1); tc::mbar_init(&ld_empty[s], 1); }
+    tc::mbar_init(sg_full, 1);
+    tc::mbar_init(sg_consumed, 128);
+    tc::mbar_init(dp_full, 1);
+    tc::mbar_init(ds_ready, 128);
+    tc::mbar_init(step_done, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 5) tc::tmem_alloc(tmem_slot, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (nsteps <= 0) {            // (DE role: empty slice) -- uniform for the whole CTA
+    __syncthreads();
+    if (warp == 5) tc::tmem_dealloc(tmem, 512);
+    return;
+  }
+
+  // per-mode buffer lookup
+  auto buf_q = [&](int st) -> uint8_t* {
+    if (MODE == MODE_DKV) return smem + Lay<MODE_DKV>::STAGE0 + st * Lay<MODE_DKV>::STAGE_BYTES + Lay<MODE_DKV>::sQ;
+    if (MODE == MODE_DQ) return smem + Lay<MODE_DQ>::Q;
+    return smem + Lay<MODE_DE>::STAGE0 + Lay<MODE_DE>::sQ;
+  };
+  auto buf_do = [&](int st) -> uint8_t* {
+    if (MODE == MODE_DKV) return smem + Lay<MODE_DKV>::STAGE0 + st * Lay<MODE_DKV>::STAGE_BYTES + Lay<MODE_DKV>::sDO;
+    if (MODE == MODE_DQ) return smem + Lay<MODE_DQ>::DO;
+    return smem + Lay<MODE_DE>::STAGE0 + Lay<MODE_DE>::sDO;
+  };
+  auto buf_k = [&](int st) -> uint8_t* {
+    if (MODE == MODE_DKV) return smem + Lay<MODE_DKV>::K;
+    if (MODE == MODE_DQ) return smem + Lay<MODE_DQ>::STAGE0 + Lay<MODE_DQ>::sK;
+    return smem + Lay<MODE_DE>::STAGE0 + Lay<MODE_DE>::sK;
+  };
+  auto buf_v = [&](int st) -> uint8_t* {
+    if (MODE == MODE_DKV) return smem + Lay<MODE_DKV>::V;
+    if (MODE == MODE_DQ) return smem + Lay<MODE_DQ>::STAGE0 + Lay<MODE_DQ>::sV;
+    return smem + Lay<MODE_DE>::STAGE0 + Lay<MODE_DE>::sV;
+  };
+  auto buf_elo = [&](int st) -> uint8_t* {
+    if (MODE == MODE_DKV) return smem + Lay<MODE_DKV>::STAGE0 + st * Lay<MODE_DKV>::STAGE_BYTES + Lay<MODE_DKV>::sELO;
+    if (MODE == MODE_DQ) return smem + Lay<MODE_DQ>::STAGE0 + Lay<MODE_DQ>::sELO;
+    return smem + Lay<MODE_DE>::ELO;
+  };
+  auto buf_ehi = [&](int st) -> uint8_t* {
+    if (MODE == MODE_DKV) return smem + Lay<MODE_DKV>::STAGE0 + st * Lay<MODE_DKV>::STAGE_BYTES + Lay<MODE_DKV>::sEHI;
+    if (MODE == MODE_DQ) return smem + Lay<MODE_DQ>::STAGE0 + Lay<MODE_DQ>::sEHI;
+    return smem + Lay<MODE_DE>::EHI;
+  };
+
+  if (warp == 4) {
+    // ================================ TMA producer ==========================================
+    if (lane == 0) {
+      const StepInfo s0 = step_info<MODE>(p, 0, bh0);
+      tc::mbar_arrive_expect_tx(bar_res, LY::RES_TILES * TILE);
+      if (MODE == MODE_DKV) {
+        tc::tma_load_4d(buf_k(0), &tmK, bar_res, 0, s0.hh, s0.jt * TT, s0.b);
+        tc::tma_load_4d(buf_v(0), &tmV, bar_res, 0, s0.hh, s0.jt * TT, s0.b);
+      } else if (MODE == MODE_DQ) {
+        tc::tma_load_4d(buf_q(0), &tmQ, bar_res, 0, s0.hh, s0.it * TT, s0.b);
+        tc::tma_load_4d(buf_do(0), &tmDO, bar_res, 0, s0.hh, s0.it * TT, s0.b);
+      } else {
+        const int c0 = p.max_seq - 1 - (int)blockIdx.x * TT;
+        tc::tma_load_2d(buf_elo(0), &tmE, bar_res, 0, c0 - (TT - 1));
+        tc::tma_load_2d(buf_ehi(0), &tmE, bar_res, 0, c0 + 1);
+      }
+      for (int n = 0; n < nsteps; ++n) {
+        const StepInfo s = step_info<MODE>(p, n, bh0);
+        const int st = (LY::NST == 2) ? (n & 1) : 0;
+        const uint32_t ph = (LY::NST == 2) ? ((n >> 1) & 1) : (n & 1);
+        tc::mbar_wait(&ld_empty[st], ph ^ 1);
+        tc::mbar_arrive_expect_tx(&ld_full[st], LY::STAGE_TILES * TILE);
+        const int c0 = p.max_seq - 1 - (s.it - s.jt) * TT;
+        if (MODE != MODE_DQ) {
+          tc::tma_load_4d(buf_q(st), &tmQ, &ld_full[st], 0, s.hh, s.it * TT, s.b);
+          tc::tma_load_4d(buf_do(st), &tmDO, &ld_full[st], 0, s.hh, s.it * TT, s.b);
+        }
+        if (MODE != MODE_DKV) {
+          tc::tma_load_4d(buf_k(st), &tmK, &ld_full[st], 0, s.hh, s.jt * TT, s.b);
+          tc::tma_load_4d(buf_v(st), &tmV, &ld_full[st], 0, s.hh, s.jt * TT, s.b);
+        }
+        if (MODE != MODE_DE) {
+          tc::tma_load_2d(buf_elo(st), &tmE, &ld_full[st], 0, c0 - (TT - 1));
+          tc::tma_load_2d(buf_ehi(st), &tmE, &ld_full[st], 0, c0 + 1);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ================================ MMA issuer ============================================
+    if (lane == 0) {
+      const uint32_t id_kk = tc::make_idesc(TT, TT, 1, 1, 0, 0);      // S, G, dP : K-major x K-major, N = 128
+      const uint32_t id_kmn = tc::make_idesc(TT, DHC, 1, 1, 0, 1);    // dQ      : A K-major, B MN-major, N = 64
+      const uint32_t id_mnmn = tc::make_idesc(TT, DHC, 1, 1, 1, 1);   // dK/dV/dE: A MN-major, B MN-major, N = 64
+      tc::mbar_wait(bar_res, 0);
+      for (int n = 0; n < nsteps; ++n) {
+        const int st = (LY::NST == 2) ? (n & 1) : 0;
+        const uint32_t ph = (LY::NST == 2) ? ((n >> 1) & 1) : (n & 1);
+        const uint32_t par = n & 1;
+        tc::mbar_wait(&ld_full[st], ph);
+        tc::tc_fence_after();
+        const uint32_t qb = tc::smem_u32(buf_q(st)), dob = tc::smem_u32(buf_do(st));
+        const uint32_t kb = tc::smem_u32(buf_k(st)), vb = tc::smem_u32(buf_v(st));
+        const uint32_t elo = tc::smem_u32(buf_elo(st)), ehi = tc::smem_u32(buf_ehi(st));
+        // ---- phase A: S = Q K^T, G_lo = Q E_lo^T, G_hi = Q E_hi^T
+#pragma unroll
+        for (int k4 = 0; k4 < DHC / 16; ++k4) {
+          const uint64_t qd = tc::make_sdesc(qb + k4 * 32, 16, 1024);
+          tc::umma_f16(tmem + TM_S, qd, tc::make_sdesc(kb + k4 * 32, 16, 1024), id_kk, k4 != 0);
+          tc::umma_f16(tmem + TM_GLO, qd, tc::make_sdesc(elo + k4 * 32, 16, 1024), id_kk, k4 != 0);
+          tc::umma_f16(tmem + TM_GHI, qd, tc::make_sdesc(ehi + k4 * 32, 16, 1024), id_kk, k4 != 0);
+        }
+        tc::umma_commit(sg_full);
+        // ---- phase C: dP = dO V^T into the G_lo columns (after the softmax warps read S / G)
+        tc::mbar_wait(sg_consumed, par);
+        tc::tc_fence_after();
+#pragma unroll
+        for (int k4 = 0; k4 < DHC / 16; ++k4)
+          tc::umma_f16(tmem + TM_DP, tc::make_sdesc(dob + k4 * 32, 16, 1024),
+                       tc::make_sdesc(vb + k4 * 32, 16, 1024), id_kk, k4 != 0);
+        tc::umma_commit(dp_full);
+        // ---- phase E: role MMAs on the P / dS / dG operands written by the softmax warps
+        tc::mbar_wait(ds_ready, par);
+        tc::tc_fence_after();
+        if (MODE == MODE_DKV) {
+          const uint32_t pb = tc::smem_u32(smem + Lay<MODE_DKV>::P), dsb = tc::smem_u32(smem + Lay<MODE_DKV>::DS);
+#pragma unroll
+          for (int k16 = 0; k16 < TT / 16; ++k16) {      // contraction over the 128 query rows
+            const uint64_t dod = tc::make_sdesc(dob + k16 * 2048, 1024, 1024);
+            const uint64_t qd = tc::make_sdesc(qb + k16 * 2048, 1024, 1024);
+            tc::umma_f16(tmem + TM_ACC1, tc::make_sdesc(pb + k16 * 2048, TILE, 1024), dod, id_mnmn, (n | k16) != 0);
+            tc::umma_f16(tmem + TM_ACC0, tc::make_sdesc(dsb + k16 * 2048, TILE, 1024), qd, id_mnmn, (n | k16) != 0);
+          }
+        } else if (MODE == MODE_DQ) {
+          const uint32_t dsb = tc::smem_u32(smem + Lay<MODE_DQ>::DS), dgb = tc::smem_u32(smem + Lay<MODE_DQ>::DG);
+#pragma unroll
+          for (int k16 = 0; k16 < TT / 16; ++k16)         // dS . K_j (contraction over the 128 keys)
+            tc::umma_f16(tmem + TM_ACC0, tc::make_sdesc(dsb + (k16 >> 2) * TILE + (k16 & 3) * 32, 16, 1024),
+                         tc::make_sdesc(kb + k16 * 2048, 1024, 1024), id_kmn, (n | k16) != 0);
+#pragma unroll
+          for (int k16 = 0; k16 < 2 * TT / 16; ++k16)     // dG . [E_lo; E_hi] (contraction over the band)
+            tc::umma_f16(tmem + TM_ACC0, tc::make_sdesc(dgb + (k16 >> 2) * TILE + (k16 & 3) * 32, 16, 1024),
+                         tc::make_sdesc((k16 < 8 ? elo + k16 * 2048 : ehi + (k16 - 8) * 2048), 1024, 1024), id_kmn, 1);
+        } else {
+          const uint32_t dgb = tc::smem_u32(smem + Lay<MODE_DE>::DG);
+#pragma unroll
+          for (int k16 = 0; k16 < TT / 16; ++k16) {       // dG_blk^T . Q (contraction over the query rows)
+            const uint64_t qd = tc::make_sdesc(qb + k16 * 2048, 1024, 1024);
+            tc::umma_f16(tmem + TM_ACC0, tc::make_sdesc(dgb + k16 * 2048, TILE, 1024), qd, id_mnmn, (n | k16) != 0);
+            tc::umma_f16(tmem + TM_ACC1, tc::make_sdesc(dgb + 2 * TILE + k16 * 2048, TILE, 1024), qd, id_mnmn,
+                         (n | k16) != 0);
+          }
+        }
+        tc::umma_commit(&ld_empty[st]);
+        tc::umma_commit(step_done);
+      }
+    }
+  } else {
+    // ================================ softmax / dS warps =====================================
+    const int a = threadIdx.x;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    float* scr = nullptr;
+    if (MODE == MODE_DQ) scr = reinterpret_cast<float*>(smem + Lay<MODE_DQ>::SCR) + a * SCR_PITCH;
+    if (MODE == MODE_DE) scr = reinterpret_cast<float*>(smem + Lay<MODE_DE>::SCR) + a * SCR_PITCH;
+    uint8_t* dg_base = nullptr;
+    if (MODE == MODE_DQ) dg_base = smem + Lay<MODE_DQ>::DG;
+    if (MODE == MODE_DE) dg_base = smem + Lay<MODE_DE>::DG;
+    if (MODE != MODE_DKV) {
+      // dG is zero outside the 128 band columns each row owns; those positions never change
+      uint4* z = reinterpret_cast<uint4*>(dg_base);
+      for (int x = a; x < 4 * TILE / 16; x += 128) z[x] = make_uint4(0, 0, 0, 0);
+      tc::fence_proxy_async();
+      tc::named_bar_sync(1, 128);
+    }
+    const int base_w = (127 - a) >> 1;          // first 32-bit word of this row's band run in dG
+    const bool odd = (a & 1) != 0;
+
+    for (int n = 0; n < nsteps; ++n) {
+      const StepInfo s = step_info<MODE>(p, n, bh0);
+      const uint32_t par = n & 1;
+      const int st = (LY::NST == 2) ? (n & 1) : 0;
+      const int i0 = s.it * TT, j0 = s.jt * TT;
+      const int i = i0 + a;
+      const bool row_ok = i < p.L;
+      const int64_t rowidx = ((int64_t)s.b * p.h + s.hh) * p.L + i;
+      const float lse2 = row_ok ? p.lse[rowidx] * LOG2E : 0.f;
+      const float Dv = row_ok ? p.delta[rowidx] : 0.f;
+      if (p.pad) {
+        tc::named_bar_sync(1, 128);
+        spad[a] = (j0 + a < p.L) ? p.pad[(int64_t)s.b * p.L + j0 + a] : 1;
+        tc::named_bar_sync(1, 128);
+      }
+      if (MODE == MODE_DKV)      // scratch = the E_lo/E_hi buffers of this stage (dead once G is computed)
+        scr = reinterpret_cast<float*>(buf_elo(st)) + a * SCR_PITCH;
+
+      tc::mbar_wait(sg_full, par);
+      tc::tc_fence_after();
+      float pv[TT];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32(tmem + TM_S + lane_base + c * 32, r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int x = 0; x < 32; ++x) pv[c * 32 + x] = __uint_as_float(r[x]);
+      }
+      // skew: Srel[a][b] = [G_lo | G_hi][a][127 - a + b], 16 output columns per pass
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int w0 = 96 - 32 * warp + 16 * q;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int cc = w0 + 16 * c;
+          uint32_t r[16];
+          tc::tmem_ld_32x16((cc < 128 ? tmem + TM_GLO + cc : tmem + TM_GHI + (cc - 128)) + lane_base, r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int x = 0; x < 16; x += 4)
+            *reinterpret_cast<uint4*>(scr + c * 16 + x) = make_uint4(r[x], r[x + 1], r[x + 2], r[x + 3]);
+        }
+        const float* rd = scr + (31 - lane);
+#pragma unroll
+        for (int x = 0; x < 16; ++x) pv[q * 16 + x] += rd[x];
+      }
+      tc::tc_fence_before();
+      tc::mbar_arrive(sg_consumed);
+
+      // P = exp(S - lse) with the reference's mask (causal on the diagonal tile, key padding, tails)
+      const bool diag = (i0 == j0);
+      const bool tail = (j0 + TT > p.L);
+#pragma unroll
+      for (int x = 0; x < TT; ++x) {
+        bool ok = row_ok;
+        if (diag) ok = ok && (x <= a);
+        if (tail) ok = ok && (j0 + x < p.L);
+        if (p.pad) ok = ok && (spad[x] == 0);
+        pv[x] = ok ? tc::fast_exp2(pv[x] * p.scale_log2 - lse2) : 0.f;
+      }
+      // the previous step's role MMAs read P / dS / dG: they must be done before we overwrite
+      if (n > 0) tc::mbar_wait(step_done, (n - 1) & 1);
+      if (MODE == MODE_DKV) {
+        uint8_t* prow = smem + Lay<MODE_DKV>::P + a * 128;
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float* v = pv + sub * 64 + c * 8;
+            *reinterpret_cast<uint4*>(prow + sub * TILE + ((c ^ (a & 7)) << 4)) =
+                make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+          }
+      }
+      // dS = P o (dP - D) / sqrt(dh)
+      tc::mbar_wait(dp_full, par);
+      tc::tc_fence_after();
+      uint32_t prevA = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32(tmem + TM_DP + lane_base + c * 32, r);
+        tc::tmem_ld_wait();
+        uint32_t A[16];
+#pragma unroll
+        for (int x = 0; x < 16; ++x) {
+          const float d0 = pv[c * 32 + 2 * x] * (__uint_as_float(r[2 * x]) - Dv) * p.scale;
+          const float d1 = pv[c * 32 + 2 * x + 1] * (__uint_as_float(r[2 * x + 1]) - Dv) * p.scale;
+          A[x] = pack2(d0, d1);
+        }
+        if (MODE != MODE_DE) {          // rectangular dS, K-major rows of 128 B (2 sub-tiles of 64 keys)
+          uint8_t* dsrow = smem + (MODE == MODE_DKV ? Lay<MODE_DKV>::DS : Lay<MODE_DQ>::DS) + (c >> 1) * TILE + a * 128;
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const int chunk = (c & 1) * 4 + cc;
+            *reinterpret_cast<uint4*>(dsrow + ((chunk ^ (a & 7)) << 4)) =
+                make_uint4(A[4 * cc], A[4 * cc + 1], A[4 * cc + 2], A[4 * cc + 3]);
+          }
+        }
+        if (MODE != MODE_DKV) {         // band dG: row a owns columns [127-a, 254-a]
+#pragma unroll
+          for (int x = 0; x < 16; ++x) {
+            const uint32_t mis = __byte_perm(x == 0 ? prevA : A[x - 1], A[x], 0x5432);   // (ds[2k-1], ds[2k])
+            const uint32_t val = odd ? A[x] : mis;
+            const int wd = base_w + c * 16 + x;
+            const int sub = wd >> 5, win = wd & 31;
+            *reinterpret_cast<uint32_t*>(dg_base + sub * TILE + a * 128 + ((((win >> 2) ^ (a & 7)) << 4) | ((win & 3) << 2))) = val;
+          }
+          prevA = A[15];
+        }
+      }
+      if (MODE != MODE_DKV && !odd) {   // even rows: the last element shares a word with a zero
+        const int wd = base_w + 64;
+        const int sub = wd >> 5, win = wd & 31;
+        *reinterpret_cast<uint32_t*>(dg_base + sub * TILE + a * 128 + ((((win >> 2) ^ (a & 7)) << 4) | ((win & 3) << 2))) =
+            __byte_perm(prevA, 0u, 0x5432);
+      }
+      tc::fence_proxy_async();
+      tc::tc_fence_before();
+      tc::mbar_arrive(ds_ready);
+    }
+
+    // ---- epilogue: accumulators out of TMEM
+    tc::mbar_wait(step_done, (nsteps - 1) & 1);
+    tc::tc_fence_after();
+    if (MODE == MODE_DE) {
+      const int c0 = p.max_seq - 1 - (int)blockIdx.x * TT;
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk) {
+        const int erow = (blk == 0 ? c0 - (TT - 1) : c0 + 1) + a;
+#pragma unroll
+        for (int c = 0; c < DHC / 32; ++c) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(tmem + (blk == 0 ? TM_ACC0 : TM_ACC1) + lane_base + c * 32, r);
+          tc::tmem_ld_wait();
+          if (erow >= 0 && erow < p.max_seq) {
+#pragma unroll
+            for (int x = 0; x < 32; ++x) atomicAdd(p.dE + (int64_t)erow * DHC + c * 32 + x, __uint_as_float(r[x]));
+          }
+        }
+      }
+    } else {
+      const StepInfo s = step_info<MODE>(p, 0, bh0);
+      const int row = (MODE == MODE_DKV ? s.jt : s.it) * TT + a;
+#pragma unroll
+      for (int which = 0; which < (MODE == MODE_DKV ? 2 : 1); ++which) {
+        uint32_t packed[DHC / 2];
+#pragma unroll
+        for (int c = 0; c < DHC / 32; ++c) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(tmem + (which == 0 ? TM_ACC0 : TM_ACC1) + lane_base + c * 32, r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int x = 0; x < 32; x += 2)
+            packed[c * 16 + x / 2] = pack2(__uint_as_float(r[x]), __uint_as_float(r[x + 1]));
+        }
+        if (row < p.L) {
+          void* base = (MODE == MODE_DQ) ? p.dq : (which == 0 ? p.dk : p.dv);
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(base) + (int64_t)s.b * p.sb +
+                                                (int64_t)row * p.sl + (int64_t)s.hh * p.sh);
+#pragma unroll
+          for (int x = 0; x < DHC / 8; ++x)
+            dst[x] = make_uint4(packed[4 * x], packed[4 * x + 1], packed[4 * x + 2], packed[4 * x + 3]);
+        }
+      }
+    }
+    tc::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem, 512);
+  }
+}
+
+template <int MODE>
+int launch_mode(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmDO,
+                const CUtensorMap& tmE, const BwdParams& p, dim3 grid, cudaStream_t st) {
+  auto kern = rga_bwd_tc_kernel<MODE>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<MODE>());
+    if (e != cudaSuccess) { set_error("rga_bwd_tc: smem attribute (%d B): %s", smem_bytes<MODE>(), cudaGetErrorString(e)); return (int)e; }
+    attr_done = true;
+  }
+  kern<<<grid, BWD_THREADS, smem_bytes<MODE>(), st>>>(tmQ, tmK, tmV, tmDO, tmE, p);
+  return check_launch("rga_bwd_tc");
+}
+
+}  // namespace
+
+bool rga_bwd_tc_supported(const RgaArgs& a, int dh, int dtype) {
+  if (dh != DHC || dtype != MT_BF16 || !a.causal) return false;
+  if (a.sl % 8 || a.sh % 8 || a.sb % 8 || a.ol % 8 || a.oh % 8 || a.ob % 8) return false;
+  if (!aligned(a.q, 16) || !aligned(a.k, 16) || !aligned(a.v, 16) || !aligned(a.E, 16) || !aligned(a.dO, 16) ||
+      !aligned(a.dq, 16) || !aligned(a.dk, 16) || !aligned(a.dv, 16))
+    return false;
+  return mt_device_ok() != 0;
+}
+
+int rga_bwd_tc(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
+  int rc;
+  if ((rc = rga_delta_launch(a, dh, dtype, st))) return rc;
+  CUtensorMap tmQ, tmK, tmV, tmDO, tmE;
+  if ((rc = tc::make_tmap_blhd(&tmQ, a.q, dh, a.L, a.h, a.B, a.sl, a.sh, a.sb, DHC, TT))) return rc;
+  if ((rc = tc::make_tmap_blhd(&tmK, a.k, dh, a.L, a.h, a.B, a.sl, a.sh, a.sb, DHC, TT))) return rc;
+  if ((rc = tc::make_tmap_blhd(&tmV, a.v, dh, a.L, a.h, a.B, a.sl, a.sh, a.sb, DHC, TT))) return rc;
+  if ((rc = tc::make_tmap_blhd(&tmDO, a.dO, dh, a.L, a.h, a.B, a.ol, a.oh, a.ob, DHC, TT))) return rc;
+  if ((rc = tc::make_tmap_2d(&tmE, a.E, a.max_seq, dh, dh, DHC, TT))) return rc;
+  BwdParams p;
+  p.dq = a.dq; p.dk = a.dk; p.dv = a.dv; p.sb = a.sb; p.sl = a.sl; p.sh = a.sh;
+  p.dE = a.dE; p.lse = a.lse; p.delta = a.delta; p.pad = a.pad;
+  p.B = a.B; p.h = a.h; p.L = a.L; p.max_seq = a.max_seq;
+  p.nT = (a.L + TT - 1) / TT;
+  p.scale = 1.f / a.inv_scale_div;
+  p.scale_log2 = LOG2E / a.inv_scale_div;
+  p.bh_per_cta = 1;
+  dim3 grid(p.nT, a.h, a.B);
+  if ((rc = launch_mode<MODE_DKV>(tmQ, tmK, tmV, tmDO, tmE, p, grid, st))) return rc;
+  if ((rc = launch_mode<MODE_DQ>(tmQ, tmK, tmV, tmDO, tmE, p, grid, st))) return rc;
+  // dE: one CTA per (tile diagonal, slice of (b,h)); about two CTAs per SM's worth of slices
+  const int bh = a.B * a.h;
+  int slices = (2 * sm_count() + p.nT - 1) / p.nT;
+  if (slices > bh) slices = bh;
+  if (slices < 1) slices = 1;
+  p.bh_per_cta = (bh + slices - 1) / slices;
+  slices = (bh + p.bh_per_cta - 1) / p.bh_per_cta;
+  dim3 grid_e(p.nT, slices, 1);
+  return launch_mode<MODE_DE>(tmQ, tmK, tmV, tmDO, tmE, p, grid_e, st);
+}
+
+}  // namespace mt

@@ -150,6 +150,50 @@ def test_rga_fwd_tcgen05(B, h, L, max_seq, causal, pad, dtype):
     assert r["o"] < tol and r["lse"] < 2e-3, r
 
 
+@pytest.mark.parametrize("B,h,L,max_seq,pad", [
+    (1, 1, 128, 128, False),
+    (2, 2, 256, 256, False),
+    (1, 2, 200, 256, False),           # ragged L < max_seq
+    (1, 2, 384, 512, True),
+    (2, 4, 512, 512, False),
+    (1, 8, 1024, 2048, True),
+])
+def test_rga_bwd_tcgen05(B, h, L, max_seq, pad):
+    """forward + backward both on the tcgen05 path; bf16 operands, fp64 oracle on the same inputs."""
+    r = run_case(B, h, L, 64, max_seq, True, pad, torch.bfloat16, PATHS["tc"], seed=L + 3 * h)
+    assert r["o"] < 6e-3, r
+    # P and dS are rounded to bf16 before the gradient GEMMs
+    assert max(r["dq"], r["dk"], r["dv"]) < 1.2e-2 and r["dE"] < 1.2e-2, r
+
+
+def test_rga_bwd_tcgen05_matches_simt_backward():
+    """Same bf16 inputs through both backward implementations (SIMT fp32 math vs tensor cores)."""
+    from musicgeneration_b200 import ops
+    dev = torch.device("cuda:0")
+    B, h, L, dh, max_seq = 2, 4, 640, 64, 1024
+    d = h * dh
+    g = torch.Generator().manual_seed(77)
+    qkv = torch.randn(B, L, 3, h, dh, generator=g).to(torch.bfloat16).to(dev)
+    E = torch.randn(max_seq, dh, generator=g).to(torch.bfloat16).to(dev)
+    dO = torch.randn(B, L, h, dh, generator=g).to(torch.bfloat16).to(dev)
+    strides, ostr = (L * 3 * d, 3 * d, dh), (L * d, d, dh)
+    outs = {}
+    for name, path in PATHS.items():
+        Od = torch.empty(B, L, h, dh, dtype=torch.bfloat16, device=dev)
+        lse = torch.empty(B, h, L, device=dev)
+        ops.rga_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], strides, E, None, Od, ostr, lse, B, h, L, dh,
+                    max_seq, True, path=path)
+        dqkv = torch.zeros(B, L, 3, h, dh, dtype=torch.bfloat16, device=dev)
+        dE = torch.zeros(max_seq, dh, device=dev)
+        delta = torch.empty(B, h, L, device=dev)
+        ops.rga_bwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], strides, E, None, Od, dO, ostr, lse, delta,
+                    dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], dE, B, h, L, dh, max_seq, True, path=path)
+        outs[name] = (dqkv.float().cpu(), dE.cpu())
+    assert rel(outs["tc"][0], outs["simt"][0]) < 1.2e-2
+    assert rel(outs["tc"][1], outs["simt"][1]) < 1.2e-2
+    assert float(outs["tc"][1][:max_seq - L].abs().max()) == 0.0      # only rows max_seq-L.. get gradient
+
+
 def test_rga_fwd_tcgen05_large_logits():
     r = run_fwd_tc(1, 2, 256, 64, 256, True, False, torch.bfloat16, seed=5, scale=6.0)
     assert r["o"] < 8e-3 and r["lse"] < 2e-2, r

@@ -5,7 +5,7 @@
 //     dV = P^T dO ;  dK = dS^T Q ;  dQ = dS K + dG E_band ;  dE_band = dG^T Q,
 // where dG is dS written back into band coordinates (dG[a][127-a+b] = dS[a][b]) -- the inverse of
 // the forward skew.  One kernel template, three roles, all sharing the "recompute the P / dS tile"
-// core (TMA loads -> S, G_lo, G_hi, dP on the tensor cores -> skew through a row-private shared
+// core (TMA loads -> S, G_lo, G_hi, dP on the tensor cores -> skew through a private shared
 // scratch -> P, dS, dG written as 128B-swizzled UMMA operands):
 //   * DKV : CTA owns a key tile, walks the query tiles at or below it; dK, dV accumulate in TMEM;
 //   * DQ  : CTA owns a query tile, walks its key tiles; dQ (both the K and the relative-embedding
@@ -16,20 +16,15 @@
 // No output needs per-step global atomics; the price is that S/P are recomputed per role.
 // The same shared-memory tile serves as K-major and as MN-major UMMA operand (rows of 128 bytes,
 // 8-row swizzle atoms), so no transposed copies exist anywhere.
+// Warps 0-7: P / dS math (row a = 32*(w&3)+lane, key columns 64*(w>>2)..+63), 8: TMA, 9: MMA.
 #include "ops.cuh"
-#include "tc_common.cuh"
+#include "rga_tc_common.cuh"
 
 namespace mt {
 
-namespace {
+using namespace rga;
 
-constexpr int TT = 128;                 // tile edge (queries and keys)
-constexpr int DHC = 64;
-constexpr int TILE = TT * DHC * 2;      // 16 KB
-constexpr int SCR_PITCH = 52;           // floats; == 20 mod 32 -> conflict-free 128-bit row stores
-constexpr int SCR_BYTES = TT * SCR_PITCH * 4;
-constexpr int BWD_THREADS = 192;
-constexpr float LOG2E = 1.4426950408889634f;
+namespace {
 
 enum { MODE_DKV = 0, MODE_DQ = 1, MODE_DE = 2 };
 
@@ -60,6 +55,7 @@ template <> struct Lay<MODE_DE> {        // E_lo,E_hi resident; {Q,dO,K,V} per s
   static constexpr int RES_TILES = 2, STAGE_TILES = 4;
 };
 template <int MODE> constexpr int smem_bytes() { return Lay<MODE>::BAR + 256 + 1024; }
+static_assert(SCR_BYTES <= 2 * TILE, "DKV role parks the skew scratch in the stage's E_lo/E_hi buffers");
 
 struct BwdParams {
   void* dq; void* dk; void* dv;          // 16-bit, q/k/v addressing
@@ -71,11 +67,6 @@ struct BwdParams {
   int bh_per_cta;                        // DE role
   float scale, scale_log2;
 };
-
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
 
 struct StepInfo { int it, jt, b, hh; };
 
@@ -102,7 +93,7 @@ __device__ __forceinline__ StepInfo step_info(const BwdParams& p, int n, int bh0
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(BWD_THREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                   const __grid_constant__ CUtensorMap tmE, const BwdParams p) {
@@ -125,26 +116,26 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   int bh0;
   const int nsteps = num_steps<MODE>(p, bh0);
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tc::tma_prefetch_desc(&tmQ); tc::tma_prefetch_desc(&tmK); tc::tma_prefetch_desc(&tmV);
     tc::tma_prefetch_desc(&tmDO); tc::tma_prefetch_desc(&tmE);
     tc::mbar_init(bar_res, 1);
     for (int s = 0; s < 2; ++s) { tc::mbar_init(&ld_full[s], 1); tc::mbar_init(&ld_empty[s], 1); }
     tc::mbar_init(sg_full, 1);
-    tc::mbar_init(sg_consumed, 128);
+    tc::mbar_init(sg_consumed, SM_THREADS);
     tc::mbar_init(dp_full, 1);
-    tc::mbar_init(ds_ready, 128);
+    tc::mbar_init(ds_ready, SM_THREADS);
     tc::mbar_init(step_done, 1);
     tc::fence_barrier_init();
   }
-  if (warp == 5) tc::tmem_alloc(tmem_slot, 512);
+  if (warp == 9) tc::tmem_alloc(tmem_slot, 512);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (nsteps <= 0) {            // (DE role: empty slice) -- uniform for the whole CTA
     __syncthreads();
-    if (warp == 5) tc::tmem_dealloc(tmem, 512);
+    if (warp == 9) tc::tmem_dealloc(tmem, 512);
     return;
   }
 
@@ -180,7 +171,7 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     return smem + Lay<MODE_DE>::EHI;
   };
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ================================ TMA producer ==========================================
     if (lane == 0) {
       const StepInfo s0 = step_info<MODE>(p, 0, bh0);
@@ -217,7 +208,7 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ================================ MMA issuer ============================================
     if (lane == 0) {
       const uint32_t id_kk = tc::make_idesc(TT, TT, 1, 1, 0, 0);      // S, G, dP : K-major x K-major, N = 128
@@ -242,7 +233,7 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           tc::umma_f16(tmem + TM_GHI, qd, tc::make_sdesc(ehi + k4 * 32, 16, 1024), id_kk, k4 != 0);
         }
         tc::umma_commit(sg_full);
-        // ---- phase C: dP = dO V^T into the G_lo columns (after the softmax warps read S / G)
+        // ---- phase C: dP = dO V^T into the G_lo columns (after the math warps read S / G)
         tc::mbar_wait(sg_consumed, par);
         tc::tc_fence_after();
 #pragma unroll
@@ -250,7 +241,7 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           tc::umma_f16(tmem + TM_DP, tc::make_sdesc(dob + k4 * 32, 16, 1024),
                        tc::make_sdesc(vb + k4 * 32, 16, 1024), id_kk, k4 != 0);
         tc::umma_commit(dp_full);
-        // ---- phase E: role MMAs on the P / dS / dG operands written by the softmax warps
+        // ---- phase E: role MMAs on the P / dS / dG operands written by the math warps
         tc::mbar_wait(ds_ready, par);
         tc::tc_fence_after();
         if (MODE == MODE_DKV) {
@@ -287,23 +278,24 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
     }
   } else {
-    // ================================ softmax / dS warps =====================================
-    const int a = threadIdx.x;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    float* scr = nullptr;
-    if (MODE == MODE_DQ) scr = reinterpret_cast<float*>(smem + Lay<MODE_DQ>::SCR) + a * SCR_PITCH;
-    if (MODE == MODE_DE) scr = reinterpret_cast<float*>(smem + Lay<MODE_DE>::SCR) + a * SCR_PITCH;
+    // ================================ P / dS math warps ======================================
+    const int w4 = warp & 3, wg = warp >> 2;
+    const int a = w4 * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(w4 * 32) << 16;
+    uint32_t* scr = nullptr;
+    if (MODE == MODE_DQ) scr = reinterpret_cast<uint32_t*>(smem + Lay<MODE_DQ>::SCR) + threadIdx.x * SCR_WORDS;
+    if (MODE == MODE_DE) scr = reinterpret_cast<uint32_t*>(smem + Lay<MODE_DE>::SCR) + threadIdx.x * SCR_WORDS;
     uint8_t* dg_base = nullptr;
     if (MODE == MODE_DQ) dg_base = smem + Lay<MODE_DQ>::DG;
     if (MODE == MODE_DE) dg_base = smem + Lay<MODE_DE>::DG;
     if (MODE != MODE_DKV) {
       // dG is zero outside the 128 band columns each row owns; those positions never change
       uint4* z = reinterpret_cast<uint4*>(dg_base);
-      for (int x = a; x < 4 * TILE / 16; x += 128) z[x] = make_uint4(0, 0, 0, 0);
+      for (int x = threadIdx.x; x < 4 * TILE / 16; x += SM_THREADS) z[x] = make_uint4(0, 0, 0, 0);
       tc::fence_proxy_async();
-      tc::named_bar_sync(1, 128);
+      tc::named_bar_sync(1, SM_THREADS);
     }
-    const int base_w = (127 - a) >> 1;          // first 32-bit word of this row's band run in dG
+    const int base_w = ((127 - a) >> 1) + 32 * wg;   // first 32-bit word of this thread's band run in dG
     const bool odd = (a & 1) != 0;
 
     for (int n = 0; n < nsteps; ++n) {
@@ -317,118 +309,99 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const float lse2 = row_ok ? p.lse[rowidx] * LOG2E : 0.f;
       const float Dv = row_ok ? p.delta[rowidx] : 0.f;
       if (p.pad) {
-        tc::named_bar_sync(1, 128);
-        spad[a] = (j0 + a < p.L) ? p.pad[(int64_t)s.b * p.L + j0 + a] : 1;
-        tc::named_bar_sync(1, 128);
+        tc::named_bar_sync(1, SM_THREADS);
+        if (wg == 0) spad[a] = (j0 + a < p.L) ? p.pad[(int64_t)s.b * p.L + j0 + a] : 1;
+        tc::named_bar_sync(1, SM_THREADS);
       }
       if (MODE == MODE_DKV)      // scratch = the E_lo/E_hi buffers of this stage (dead once G is computed)
-        scr = reinterpret_cast<float*>(buf_elo(st)) + a * SCR_PITCH;
+        scr = reinterpret_cast<uint32_t*>(buf_elo(st)) + threadIdx.x * SCR_WORDS;
 
       tc::mbar_wait(sg_full, par);
       tc::tc_fence_after();
-      float pv[TT];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32(tmem + TM_S + lane_base + c * 32, r);
+      float pv[64];
+      {
+        uint32_t r0[32], r1[32];
+        tc::tmem_ld_32x32(tmem + TM_S + lane_base + wg * 64, r0);
+        tc::tmem_ld_32x32(tmem + TM_S + lane_base + wg * 64 + 32, r1);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int x = 0; x < 32; ++x) pv[c * 32 + x] = __uint_as_float(r[x]);
+        for (int x = 0; x < 32; ++x) { pv[x] = __uint_as_float(r0[x]); pv[32 + x] = __uint_as_float(r1[x]); }
       }
-      // skew: Srel[a][b] = [G_lo | G_hi][a][127 - a + b], 16 output columns per pass
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int w0 = 96 - 32 * warp + 16 * q;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const int cc = w0 + 16 * c;
-          uint32_t r[16];
-          tc::tmem_ld_32x16((cc < 128 ? tmem + TM_GLO + cc : tmem + TM_GHI + (cc - 128)) + lane_base, r);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int x = 0; x < 16; x += 4)
-            *reinterpret_cast<uint4*>(scr + c * 16 + x) = make_uint4(r[x], r[x + 1], r[x + 2], r[x + 3]);
-        }
-        const float* rd = scr + (31 - lane);
-#pragma unroll
-        for (int x = 0; x < 16; ++x) pv[q * 16 + x] += rd[x];
-      }
+      skew_add_64(pv, tmem + TM_GLO, tmem + TM_GHI, lane_base, w4, wg, lane, scr);
       tc::tc_fence_before();
       tc::mbar_arrive(sg_consumed);
 
       // P = exp(S - lse) with the reference's mask (causal on the diagonal tile, key padding, tails)
       const bool diag = (i0 == j0);
-      const bool tail = (j0 + TT > p.L);
+      const bool tail = (j0 + TT > p.L) || (i0 + TT > p.L);
 #pragma unroll
-      for (int x = 0; x < TT; ++x) {
-        bool ok = row_ok;
-        if (diag) ok = ok && (x <= a);
-        if (tail) ok = ok && (j0 + x < p.L);
-        if (p.pad) ok = ok && (spad[x] == 0);
-        pv[x] = ok ? tc::fast_exp2(pv[x] * p.scale_log2 - lse2) : 0.f;
+      for (int x = 0; x < 64; ++x) pv[x] = tc::fast_exp2(fmaf(pv[x], p.scale_log2, -lse2));
+      if (diag || tail || p.pad != nullptr) {
+#pragma unroll
+        for (int x = 0; x < 64; ++x) {
+          const int bcol = wg * 64 + x;
+          bool ok = row_ok;
+          if (diag) ok = ok && (bcol <= a);
+          ok = ok && (j0 + bcol < p.L);
+          if (p.pad) ok = ok && (spad[bcol] == 0);
+          if (!ok) pv[x] = 0.f;
+        }
       }
       // the previous step's role MMAs read P / dS / dG: they must be done before we overwrite
       if (n > 0) tc::mbar_wait(step_done, (n - 1) & 1);
       if (MODE == MODE_DKV) {
-        uint8_t* prow = smem + Lay<MODE_DKV>::P + a * 128;
+        uint8_t* ptile = smem + Lay<MODE_DKV>::P + wg * TILE;
 #pragma unroll
-        for (int sub = 0; sub < 2; ++sub)
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float* v = pv + sub * 64 + c * 8;
-            *reinterpret_cast<uint4*>(prow + sub * TILE + ((c ^ (a & 7)) << 4)) =
-                make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-          }
+        for (int c = 0; c < 8; ++c) {
+          const float* v = pv + c * 8;
+          *reinterpret_cast<uint4*>(ptile + swz_chunk(a, c)) =
+              make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                         pack_bf16x2(v[6], v[7]));
+        }
       }
       // dS = P o (dP - D) / sqrt(dh)
       tc::mbar_wait(dp_full, par);
       tc::tc_fence_after();
-      uint32_t prevA = 0;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32(tmem + TM_DP + lane_base + c * 32, r);
+      uint32_t A[32];
+      {
+        uint32_t r0[32], r1[32];
+        tc::tmem_ld_32x32(tmem + TM_DP + lane_base + wg * 64, r0);
+        tc::tmem_ld_32x32(tmem + TM_DP + lane_base + wg * 64 + 32, r1);
         tc::tmem_ld_wait();
-        uint32_t A[16];
 #pragma unroll
         for (int x = 0; x < 16; ++x) {
-          const float d0 = pv[c * 32 + 2 * x] * (__uint_as_float(r[2 * x]) - Dv) * p.scale;
-          const float d1 = pv[c * 32 + 2 * x + 1] * (__uint_as_float(r[2 * x + 1]) - Dv) * p.scale;
-          A[x] = pack2(d0, d1);
-        }
-        if (MODE != MODE_DE) {          // rectangular dS, K-major rows of 128 B (2 sub-tiles of 64 keys)
-          uint8_t* dsrow = smem + (MODE == MODE_DKV ? Lay<MODE_DKV>::DS : Lay<MODE_DQ>::DS) + (c >> 1) * TILE + a * 128;
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            const int chunk = (c & 1) * 4 + cc;
-            *reinterpret_cast<uint4*>(dsrow + ((chunk ^ (a & 7)) << 4)) =
-                make_uint4(A[4 * cc], A[4 * cc + 1], A[4 * cc + 2], A[4 * cc + 3]);
-          }
-        }
-        if (MODE != MODE_DKV) {         // band dG: row a owns columns [127-a, 254-a]
-#pragma unroll
-          for (int x = 0; x < 16; ++x) {
-            const uint32_t mis = __byte_perm(x == 0 ? prevA : A[x - 1], A[x], 0x5432);   // (ds[2k-1], ds[2k])
-            const uint32_t val = odd ? A[x] : mis;
-            const int wd = base_w + c * 16 + x;
-            const int sub = wd >> 5, win = wd & 31;
-            *reinterpret_cast<uint32_t*>(dg_base + sub * TILE + a * 128 + ((((win >> 2) ^ (a & 7)) << 4) | ((win & 3) << 2))) = val;
-          }
-          prevA = A[15];
+          A[x] = pack_bf16x2(pv[2 * x] * (__uint_as_float(r0[2 * x]) - Dv) * p.scale,
+                             pv[2 * x + 1] * (__uint_as_float(r0[2 * x + 1]) - Dv) * p.scale);
+          A[16 + x] = pack_bf16x2(pv[32 + 2 * x] * (__uint_as_float(r1[2 * x]) - Dv) * p.scale,
+                                  pv[32 + 2 * x + 1] * (__uint_as_float(r1[2 * x + 1]) - Dv) * p.scale);
         }
       }
-      if (MODE != MODE_DKV && !odd) {   // even rows: the last element shares a word with a zero
-        const int wd = base_w + 64;
-        const int sub = wd >> 5, win = wd & 31;
-        *reinterpret_cast<uint32_t*>(dg_base + sub * TILE + a * 128 + ((((win >> 2) ^ (a & 7)) << 4) | ((win & 3) << 2))) =
-            __byte_perm(prevA, 0u, 0x5432);
+      if (MODE != MODE_DE) {            // rectangular dS: sub-tile wg of row a
+        uint8_t* dstile = smem + (MODE == MODE_DKV ? Lay<MODE_DKV>::DS : Lay<MODE_DQ>::DS) + wg * TILE;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(dstile + swz_chunk(a, c)) = make_uint4(A[4 * c], A[4 * c + 1], A[4 * c + 2], A[4 * c + 3]);
+      }
+      if (MODE != MODE_DKV) {           // band dG: this thread's 64 values start at band column 127-a+64*wg
+        auto word_ptr = [&](int wd) -> uint8_t* { return dg_base + (wd >> 5) * TILE + swz_word(a, wd & 31); };
+        if (odd) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) *reinterpret_cast<uint32_t*>(word_ptr(base_w + k)) = A[k];
+        } else {
+          // run starts at an odd column: first / last element share a word with the neighbour run
+          *reinterpret_cast<uint16_t*>(word_ptr(base_w) + 2) = (uint16_t)(A[0] & 0xffffu);
+#pragma unroll
+          for (int k = 1; k < 32; ++k)
+            *reinterpret_cast<uint32_t*>(word_ptr(base_w + k)) = __byte_perm(A[k - 1], A[k], 0x5432);
+          *reinterpret_cast<uint16_t*>(word_ptr(base_w + 32)) = (uint16_t)(A[31] >> 16);
+        }
       }
       tc::fence_proxy_async();
       tc::tc_fence_before();
       tc::mbar_arrive(ds_ready);
     }
 
-    // ---- epilogue: accumulators out of TMEM
+    // ---- epilogue: accumulators out of TMEM (each thread: 32 of the 64 columns of its row)
     tc::mbar_wait(step_done, (nsteps - 1) & 1);
     tc::tc_fence_after();
     if (MODE == MODE_DE) {
@@ -436,15 +409,12 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
       for (int blk = 0; blk < 2; ++blk) {
         const int erow = (blk == 0 ? c0 - (TT - 1) : c0 + 1) + a;
+        uint32_t r[32];
+        tc::tmem_ld_32x32(tmem + (blk == 0 ? TM_ACC0 : TM_ACC1) + lane_base + wg * 32, r);
+        tc::tmem_ld_wait();
+        if (erow >= 0 && erow < p.max_seq) {
 #pragma unroll
-        for (int c = 0; c < DHC / 32; ++c) {
-          uint32_t r[32];
-          tc::tmem_ld_32x32(tmem + (blk == 0 ? TM_ACC0 : TM_ACC1) + lane_base + c * 32, r);
-          tc::tmem_ld_wait();
-          if (erow >= 0 && erow < p.max_seq) {
-#pragma unroll
-            for (int x = 0; x < 32; ++x) atomicAdd(p.dE + (int64_t)erow * DHC + c * 32 + x, __uint_as_float(r[x]));
-          }
+          for (int x = 0; x < 32; ++x) atomicAdd(p.dE + (int64_t)erow * DHC + wg * 32 + x, __uint_as_float(r[x]));
         }
       }
     } else {
@@ -452,22 +422,17 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const int row = (MODE == MODE_DKV ? s.jt : s.it) * TT + a;
 #pragma unroll
       for (int which = 0; which < (MODE == MODE_DKV ? 2 : 1); ++which) {
-        uint32_t packed[DHC / 2];
+        uint32_t r[32], packed[16];
+        tc::tmem_ld_32x32(tmem + (which == 0 ? TM_ACC0 : TM_ACC1) + lane_base + wg * 32, r);
+        tc::tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < DHC / 32; ++c) {
-          uint32_t r[32];
-          tc::tmem_ld_32x32(tmem + (which == 0 ? TM_ACC0 : TM_ACC1) + lane_base + c * 32, r);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int x = 0; x < 32; x += 2)
-            packed[c * 16 + x / 2] = pack2(__uint_as_float(r[x]), __uint_as_float(r[x + 1]));
-        }
+        for (int x = 0; x < 32; x += 2) packed[x / 2] = pack_bf16x2(__uint_as_float(r[x]), __uint_as_float(r[x + 1]));
         if (row < p.L) {
           void* base = (MODE == MODE_DQ) ? p.dq : (which == 0 ? p.dk : p.dv);
           uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(base) + (int64_t)s.b * p.sb +
-                                                (int64_t)row * p.sl + (int64_t)s.hh * p.sh);
+                                                (int64_t)row * p.sl + (int64_t)s.hh * p.sh + wg * 32);
 #pragma unroll
-          for (int x = 0; x < DHC / 8; ++x)
+          for (int x = 0; x < 4; ++x)
             dst[x] = make_uint4(packed[4 * x], packed[4 * x + 1], packed[4 * x + 2], packed[4 * x + 3]);
         }
       }
@@ -475,7 +440,7 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     tc::tc_fence_before();
   }
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc::tc_fence_after();
     tc::tmem_dealloc(tmem, 512);
   }
@@ -491,7 +456,7 @@ int launch_mode(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMa
     if (e != cudaSuccess) { set_error("rga_bwd_tc: smem attribute (%d B): %s", smem_bytes<MODE>(), cudaGetErrorString(e)); return (int)e; }
     attr_done = true;
   }
-  kern<<<grid, BWD_THREADS, smem_bytes<MODE>(), st>>>(tmQ, tmK, tmV, tmDO, tmE, p);
+  kern<<<grid, NTHREADS, smem_bytes<MODE>(), st>>>(tmQ, tmK, tmV, tmDO, tmE, p);
   return check_launch("rga_bwd_tc");
 }
 

@@ -1,0 +1,88 @@
+// Pieces shared by the tcgen05 relative-attention kernels (forward and backward).
+//
+// Thread organisation of the "softmax" part of both kernels: 8 warps = 2 warpgroups.  Warp w
+// works on TMEM lanes 32*(w&3) .. +31 (the only lanes it may address), i.e. query row
+// a = 32*(w&3) + lane of the 128-row tile; warpgroup wg = w>>2 owns key columns [64*wg, 64*wg+64)
+// of that row.  Two warps per scheduler hide each other's TMEM / shared-memory / MUFU latency.
+#pragma once
+
+#include "tc_common.cuh"
+
+namespace mt {
+namespace rga {
+
+constexpr int TT = 128;                 // tile edge (queries and keys)
+constexpr int DHC = 64;                 // head dim
+constexpr int TILE = TT * DHC * 2;      // 16 KB: one [128 x 64] 16-bit operand tile
+constexpr int SM_WARPS = 8;             // softmax warps
+constexpr int SM_THREADS = SM_WARPS * 32;
+constexpr int NTHREADS = SM_THREADS + 64;   // + TMA producer warp + MMA issuer warp
+constexpr int SCR_WORDS = 28;           // per-thread skew scratch (== 28 mod 32: conflict-free v4 stores)
+constexpr int SCR_BYTES = SM_THREADS * SCR_WORDS * 4;
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack16(float a, float b, int fmt) {
+  return fmt == 1 ? pack_bf16x2(a, b) : pack_f16x2(a, b);
+}
+
+// The skew (MT/layers.py:116-125) as index arithmetic.  Adds
+//     Srel[a][64*wg + x] = [G_lo | G_hi][a][127 - a + 64*wg + x],   x in [0, 64)
+// to sv[x].  TMEM column addresses are warp-uniform, so per pass of 16 output columns the warp
+// loads the 48-column window common to its 32 rows, parks it (packed to f16 pairs) in a private
+// 28-word shared-memory scratch and reads it back at the per-lane offset 31 - lane; an odd offset
+// is a 16-bit funnel shift of adjacent words.
+__device__ __forceinline__ void skew_add_64(float (&sv)[64], uint32_t g_lo, uint32_t g_hi, uint32_t lane_base,
+                                            int w4, int wg, int lane, uint32_t* scr) {
+  const int o = 31 - lane;
+  const uint32_t sh = (uint32_t)(o & 1) * 16u;
+  const uint32_t* rd = scr + (o >> 1);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int w0 = 96 - 32 * w4 + 64 * wg + 16 * q;     // multiple of 16: each x16 load is in lo or in hi
+    uint32_t r[3][16];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int cc = w0 + 16 * c;
+      tc::tmem_ld_32x16((cc < 128 ? g_lo + cc : g_hi + (cc - 128)) + lane_base, r[c]);
+    }
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int x = 0; x < 16; x += 8)
+        *reinterpret_cast<uint4*>(scr + c * 8 + x / 2) =
+            make_uint4(pack_f16x2(__uint_as_float(r[c][x]), __uint_as_float(r[c][x + 1])),
+                       pack_f16x2(__uint_as_float(r[c][x + 2]), __uint_as_float(r[c][x + 3])),
+                       pack_f16x2(__uint_as_float(r[c][x + 4]), __uint_as_float(r[c][x + 5])),
+                       pack_f16x2(__uint_as_float(r[c][x + 6]), __uint_as_float(r[c][x + 7])));
+    uint32_t w[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w[k] = rd[k];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      uint32_t u = __funnelshift_r(w[k], w[k + 1], sh);
+      float2 f = __half22float2(*reinterpret_cast<__half2*>(&u));
+      sv[q * 16 + 2 * k] += f.x;
+      sv[q * 16 + 2 * k + 1] += f.y;
+    }
+  }
+}
+
+// Byte offset of 16-byte chunk `chunk` (0..7) of row `a` inside a [128 x 64] 16-bit tile stored in
+// the UMMA 128B-swizzled layout (rows of 128 B, chunk index XOR-ed with row & 7).
+__device__ __forceinline__ int swz_chunk(int a, int chunk) { return a * 128 + ((chunk ^ (a & 7)) << 4); }
+// Byte offset of 32-bit word `win` (0..31) of row `a` in such a tile.
+__device__ __forceinline__ int swz_word(int a, int win) {
+  return a * 128 + ((((win >> 2) ^ (a & 7)) << 4) | ((win & 3) << 2));
+}
+
+}  // namespace rga
+}  // namespace mt

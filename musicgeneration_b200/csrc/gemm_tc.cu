@@ -99,8 +99,8 @@ template <int A_MN, int B_MN>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcGemmParams p, const int fmt) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((tc::smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * TILE_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * TILE_BYTES);

@@ -52,8 +52,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmE,
                   const FwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // declared (and checked) 1024-byte aligned so that the compiler keeps the shared address space
+  // (LDS/STS instead of generic LD/ST) and the 128B-swizzle atoms line up
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((tc::smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* bar_q = bars + 0;
   uint64_t* kv_full = bars + 1;      // [2]

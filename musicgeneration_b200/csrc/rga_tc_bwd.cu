@@ -98,8 +98,8 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                   const __grid_constant__ CUtensorMap tmE, const BwdParams p) {
   using LY = Lay<MODE>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];      // shared address space kept: LDS/STS, not generic
+  if ((tc::smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LY::BAR);
   uint64_t* bar_res = bars + 0;
   uint64_t* ld_full = bars + 1;       // [2]
@@ -205,6 +205,16 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         if (MODE != MODE_DE) {
           tc::tma_load_2d(buf_elo(st), &tmE, &ld_full[st], 0, c0 - (TT - 1));
           tc::tma_load_2d(buf_ehi(st), &tmE, &ld_full[st], 0, c0 + 1);
+        }
+        if (LY::NST == 1 && n + 1 < nsteps) {
+          // single-buffered roles: pull the next step's tiles into L2 while this step computes
+          const StepInfo t = step_info<MODE>(p, n + 1, bh0);
+          if (MODE == MODE_DE) {
+            tc::tma_prefetch_4d(&tmQ, 0, t.hh, t.it * TT, t.b);
+            tc::tma_prefetch_4d(&tmDO, 0, t.hh, t.it * TT, t.b);
+          }
+          tc::tma_prefetch_4d(&tmK, 0, t.hh, t.jt * TT, t.b);
+          tc::tma_prefetch_4d(&tmV, 0, t.hh, t.jt * TT, t.b);
         }
       }
     }

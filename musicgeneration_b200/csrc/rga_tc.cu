@@ -172,6 +172,14 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t lane_base = (uint32_t)(w4 * 32) << 16;
     uint32_t* scr = reinterpret_cast<uint32_t*>(smem + OFF_SCR) + threadIdx.x * SCR_WORDS;
     const uint8_t* padrow = p.pad ? p.pad + (int64_t)b * L : nullptr;
+    if (padrow) {
+      // training batches carry no pad tokens: decide once per CTA whether any key this CTA visits
+      // is padded, and drop to the unmasked path if none is
+      bool mine = false;
+      const int jend = min(L, n_kt * TT);
+      for (int j = threadIdx.x; j < jend; j += SM_THREADS) mine |= (padrow[j] != 0);
+      if (!tc::named_bar_red_or(1, SM_THREADS, mine)) padrow = nullptr;
+    }
     float m_run = -INFINITY, l_part = 0.f;             // l_part: this thread's half of the row sum
 
     for (int jt = 0; jt < n_kt; ++jt) {

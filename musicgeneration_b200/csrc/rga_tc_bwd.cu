@@ -305,6 +305,16 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc::fence_proxy_async();
       tc::named_bar_sync(1, SM_THREADS);
     }
+    // training batches carry no pad tokens: decide once per CTA whether any key of the sequences
+    // this CTA touches is padded; if none is, the unmasked fast path is used for every step
+    const uint8_t* pad = p.pad;
+    if (pad) {
+      const StepInfo sf = step_info<MODE>(p, 0, bh0), sl = step_info<MODE>(p, nsteps - 1, bh0);
+      bool mine = false;
+      for (int64_t x = (int64_t)sf.b * p.L + threadIdx.x; x < (int64_t)(sl.b + 1) * p.L; x += SM_THREADS)
+        mine |= (pad[x] != 0);
+      if (!tc::named_bar_red_or(1, SM_THREADS, mine)) pad = nullptr;
+    }
     const int base_w = ((127 - a) >> 1) + 32 * wg;   // first 32-bit word of this thread's band run in dG
     const bool odd = (a & 1) != 0;
 
@@ -318,9 +328,9 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const int64_t rowidx = ((int64_t)s.b * p.h + s.hh) * p.L + i;
       const float lse2 = row_ok ? p.lse[rowidx] * LOG2E : 0.f;
       const float Dv = row_ok ? p.delta[rowidx] : 0.f;
-      if (p.pad) {
+      if (pad) {
         tc::named_bar_sync(1, SM_THREADS);
-        if (wg == 0) spad[a] = (j0 + a < p.L) ? p.pad[(int64_t)s.b * p.L + j0 + a] : 1;
+        if (wg == 0) spad[a] = (j0 + a < p.L) ? pad[(int64_t)s.b * p.L + j0 + a] : 1;
         tc::named_bar_sync(1, SM_THREADS);
       }
       if (MODE == MODE_DKV)      // scratch = the E_lo/E_hi buffers of this stage (dead once G is computed)
@@ -346,14 +356,14 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const bool tail = (j0 + TT > p.L) || (i0 + TT > p.L);
 #pragma unroll
       for (int x = 0; x < 64; ++x) pv[x] = tc::fast_exp2(fmaf(pv[x], p.scale_log2, -lse2));
-      if (diag || tail || p.pad != nullptr) {
+      if (diag || tail || pad != nullptr) {
 #pragma unroll
         for (int x = 0; x < 64; ++x) {
           const int bcol = wg * 64 + x;
           bool ok = row_ok;
           if (diag) ok = ok && (bcol <= a);
           ok = ok && (j0 + bcol < p.L);
-          if (p.pad) ok = ok && (spad[bcol] == 0);
+          if (pad) ok = ok && (spad[bcol] == 0);
           if (!ok) pv[x] = 0.f;
         }
       }

@@ -117,7 +117,19 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-// arrive (count 1) on an mbarrier from an ordinary thread
+// named barrier + OR-reduction of a predicate over the participating threads
+__device__ __forceinline__ bool named_bar_red_or(int id, int nthreads, bool pred) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.u32 q, %3, 0;\n\t"
+      "bar.red.or.pred p, %1, %2, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r)
+      : "r"(id), "r"(nthreads), "r"((uint32_t)pred)
+      : "memory");
+  return r != 0;
+}
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -271,11 +271,31 @@ def run_ours(args):
         last = float(step(x, y).item())
     barrier()
     e2e_s = time.perf_counter() - t0
+    # ---- decode leg (BASELINE config D): KV-cached sampling, sequences sharded over ranks ------
+    dec = None
+    if not args.no_decode:
+        seqs, new_events = args.decode_seqs, min(args.decode_events, L - 1)
+        model.eval()
+        prior = torch.randint(0, pad, (seqs, 1), generator=g, dtype=torch.int64).to(dev)
+        with torch.no_grad():
+            model.generate(prior, length=8, temperature=1.0, top_k=32)          # warm-up
+            barrier()
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d0.record()
+            out = model.generate(prior, length=new_events, temperature=1.0, top_k=32)
+            d1.record()
+            barrier()
+        dec_ms = d0.elapsed_time(d1)
+        model.train()
+        assert out.shape == (seqs, 1 + new_events)
+        dec = {"ms": dec_ms, "seqs_per_gpu": seqs, "events": new_events}
     # max over ranks
     if world > 1:
-        t = torch.tensor([ms_total, e2e_s], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_total, e2e_s, dec["ms"] if dec else 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, e2e_s = float(t[0]), float(t[1])
+        if dec:
+            dec["ms"] = float(t[2])
     if rank == 0:
         pk = peaks()
         ms_step = ms_total / K
@@ -310,6 +330,19 @@ def run_ours(args):
             "step_model_tflops": step_flops / (ms_step / 1e3) / 1e12,
             "step_frac_of_peak": step_flops / (ms_step / 1e3) / 1e12 / pk["tf_sust"],
         }
+        if dec:
+            ev = dec["seqs_per_gpu"] * world * dec["events"] / (dec["ms"] / 1e3)
+            # HBM roofline of the decode step: per sequence-step the K and V rows of every
+            # layer are read once (mean context = events/2), plus the weights once per step
+            es = 2 if args.precision == "bf16" else 4
+            kv = layers * 2 * (dec["events"] / 2) * d * es * dec["seqs_per_gpu"]
+            wts = (layers * (4 * d * d + d * d) + d * V) * es
+            line["decode"] = {"metric": "decode_events_per_s", "value": ev, "unit": "events/s",
+                              "sequences": dec["seqs_per_gpu"] * world, "events_per_sequence": dec["events"],
+                              "top_k": 32, "ms_total": dec["ms"],
+                              "hbm_bytes_per_step": kv + wts,
+                              "hbm_frac": (kv + wts) * dec["events"] / (dec["ms"] / 1e3) / 1e9 / pk["hbm"],
+                              "scaling": "sequences sharded over ranks, no collective"}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_leg(args.config)
         print(json.dumps(line), flush=True)
@@ -328,6 +361,9 @@ def main():
     ap.add_argument("--dropout", type=float, default=0.2)
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--decode-seqs", type=int, default=32)
+    ap.add_argument("--decode-events", type=int, default=2047)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

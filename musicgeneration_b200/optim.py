@@ -67,11 +67,8 @@ class FlatAdam:
 
     def all_reduce_grads(self):
         """Data-parallel exchange: sum of the flat gradient over ranks (NCCL, one call)."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.pg) > 1:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
-            return dist.get_world_size(self.pg)
-        return 1
+        from .parallel import all_reduce_flat_
+        return all_reduce_flat_(self.flat_g, self.pg)
 
     def step(self):
         world = self.all_reduce_grads()

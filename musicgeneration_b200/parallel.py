@@ -1,0 +1,67 @@
+"""Data-parallel plumbing: one process per GPU with torch.distributed (NCCL over NVLink on the B200
+box, gloo in the CPU tests).  This takes the ROLE of the reference's vendored single-process
+DataParallelModel / DataParallelCriterion (MT/parallel.py:69-129 -- dead code upstream, the calls at
+MT/train.py:232-235 are commented out): identical replicas, each rank draws its own batch, ONE
+exchange step per optimizer step -- a sum all-reduce over the flat fp32 gradient buffer -- and an
+identical Adam update everywhere.  Batched sampling shards sequences across ranks with no
+communication."""
+from __future__ import annotations
+
+import os
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """Initialise the default process group from RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (the
+    torchrun contract).  Returns (rank, world, local_rank); a no-op for world == 1."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local
+
+
+def world_size(group=None) -> int:
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced split of n items (sequences to sample, batch rows): [lo, hi) of rank."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def all_reduce_flat_(flat: torch.Tensor, group=None) -> int:
+    """In-place SUM all-reduce of a flat gradient buffer; returns the world size (the caller folds
+    1/world into the optimizer's gradient scale, so no extra pass over the buffer is made)."""
+    w = world_size(group)
+    if w > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return w
+
+
+def broadcast_params_(model: torch.nn.Module, src: int = 0, group=None) -> None:
+    """Make every replica start from rank ``src``'s weights."""
+    if world_size(group) > 1:
+        for p in model.parameters():
+            dist.broadcast(p.data, src=src, group=group)
+
+
+def global_mean_loss(loss_sum: torch.Tensor, n_valid: torch.Tensor, group=None) -> torch.Tensor:
+    """Mean loss over ALL ranks' non-pad tokens (the reference divides by the global non-pad count,
+    MT/criterion.py:57-59): all-reduce (sum, count) and divide."""
+    t = torch.stack([loss_sum.reshape(()).float(), n_valid.reshape(()).float()])
+    if world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t[0] / t[1]

@@ -88,6 +88,10 @@ size_t mt_colsum_workspace_bytes(int64_t M, int64_t N);
 int mt_colsum(const void* X, int dtype, float* out, int64_t M, int64_t N, int64_t ldx,
               void* workspace, size_t workspace_bytes, void* stream);
 int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+/* dst[r, 0:ldd] = {src[r, 0:cols], 0...}: row-padded operand copy (leading dimension -> multiple
+ * of 8 elements, as the TMA-fed GEMM needs; e.g. dlogits [T, 390] -> [T, 392]) */
+int mt_cast2d(const void* src, int src_dtype, int64_t lds, void* dst, int dst_dtype, int64_t ldd,
+              int64_t rows, int64_t cols, void* stream);
 /* dst[c,r] = src[r,c] with dtype conversion (weight shadows for dgrad) */
 int mt_transpose_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t rows,
                       int64_t cols, void* stream);

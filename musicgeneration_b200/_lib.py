@@ -39,6 +39,7 @@ SIGNATURES = {
     "mt_colsum_workspace_bytes": (_sz, [_i64, _i64]),
     "mt_colsum": (_int, [_p, _int, _p, _i64, _i64, _i64, _p, _sz, _p]),
     "mt_cast": (_int, [_p, _int, _p, _int, _i64, _p]),
+    "mt_cast2d": (_int, [_p, _int, _i64, _p, _int, _i64, _i64, _i64, _p]),
     "mt_transpose_cast": (_int, [_p, _int, _p, _int, _i64, _i64, _p]),
     "mt_rga_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _p]),
     "mt_rga_weights": (_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _int, _p]),

@@ -25,6 +25,8 @@ constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 2;          // 16 KB per operand tile
 constexpr int TC_THREADS = 192;
 constexpr int TMEM_COLS = 128;
+constexpr int EPI_PITCH = 132;          // floats per staged row (== 4 mod 32: conflict-free 128-bit stores)
+static_assert(BM * EPI_PITCH * 4 <= 2 * STAGES * TILE_BYTES, "epilogue staging aliases the operand ring");
 constexpr size_t SMEM_BYTES = 2 * STAGES * TILE_BYTES + 256 + 1024;
 
 struct TcGemmParams {
@@ -39,58 +41,57 @@ struct TcGemmParams {
   float* part;
 };
 
-__device__ __forceinline__ void epilogue_row(const TcGemmParams& p, int64_t row, int64_t n, const float (&v)[32]) {
-  // v[j] = accumulator at (row, n + j)
-  if (p.splits > 1) {
+// One quad (row, n .. n+3) of the output tile: bias / residual add / ReLU / ReLU-mask, then store.
+__device__ __forceinline__ void epilogue_quad(const TcGemmParams& p, int64_t row, int64_t n, float (&o)[4]) {
+  if (p.splits > 1) {                     // raw partial sums; the fold kernel applies the epilogue
     float* dst = p.part + ((int64_t)blockIdx.z * p.M + row) * p.N + n;
+    if (n + 3 < p.N && (p.N & 3) == 0) {
+      *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (n + j < p.N) dst[j] = v[j];
+      for (int t = 0; t < 4; ++t)
+        if (n + t < p.N) dst[t] = o[t];
+    }
     return;
   }
   const int64_t off = row * p.ldc + n;
+  if (n + 3 < p.N && p.vec_ok) {
+    if (p.epi & MT_EPI_BIAS) {
+      float4 b = *reinterpret_cast<const float4*>(p.bias + n);
+      o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
+    }
+    if (p.epi & MT_EPI_ADD) {
+      float4 a = *reinterpret_cast<const float4*>(p.addend + off);
+      o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
+    }
+    if (p.epi & MT_EPI_RELU) {
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    float o[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
-    const bool full = (n + j + 3 < p.N);
-    if (full && p.vec_ok) {
-      if (p.epi & MT_EPI_BIAS) {
-        float4 b = *reinterpret_cast<const float4*>(p.bias + n + j);
-        o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
-      }
-      if (p.epi & MT_EPI_ADD) {
-        float4 a = *reinterpret_cast<const float4*>(p.addend + off + j);
-        o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
-      }
-      if (p.epi & MT_EPI_RELU) {
+      for (int t = 0; t < 4; ++t) o[t] = fmaxf(o[t], 0.f);
+    }
+    if (p.epi & MT_EPI_RELU_MASK) {
+      float4 m = load4<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + off);
+      if (!(m.x > 0.f)) o[0] = 0.f;
+      if (!(m.y > 0.f)) o[1] = 0.f;
+      if (!(m.z > 0.f)) o[2] = 0.f;
+      if (!(m.w > 0.f)) o[3] = 0.f;
+    }
+    float4 r = make_float4(o[0], o[1], o[2], o[3]);
+    if (p.out_bf16) store4<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.C) + off, r);
+    else store4<float>(reinterpret_cast<float*>(p.C) + off, r);
+  } else {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) o[t] = fmaxf(o[t], 0.f);
-      }
+    for (int t = 0; t < 4; ++t) {
+      const int64_t nn = n + t;
+      if (nn >= p.N) continue;
+      float x = o[t];
+      if (p.epi & MT_EPI_BIAS) x += p.bias[nn];
+      if (p.epi & MT_EPI_ADD) x += p.addend[off + t];
+      if (p.epi & MT_EPI_RELU) x = fmaxf(x, 0.f);
       if (p.epi & MT_EPI_RELU_MASK) {
-        float4 m = load4<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + off + j);
-        if (!(m.x > 0.f)) o[0] = 0.f;
-        if (!(m.y > 0.f)) o[1] = 0.f;
-        if (!(m.z > 0.f)) o[2] = 0.f;
-        if (!(m.w > 0.f)) o[3] = 0.f;
+        if (!(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.aux)[off + t]) > 0.f)) x = 0.f;
       }
-      float4 r = make_float4(o[0], o[1], o[2], o[3]);
-      if (p.out_bf16) store4<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.C) + off + j, r);
-      else store4<float>(reinterpret_cast<float*>(p.C) + off + j, r);
-    } else {
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int64_t nn = n + j + t;
-        if (nn >= p.N) continue;
-        float x = o[t];
-        if (p.epi & MT_EPI_BIAS) x += p.bias[nn];
-        if (p.epi & MT_EPI_ADD) x += p.addend[off + j + t];
-        if (p.epi & MT_EPI_RELU) x = fmaxf(x, 0.f);
-        if (p.epi & MT_EPI_RELU_MASK) {
-          if (!(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.aux)[off + j + t]) > 0.f)) x = 0.f;
-        }
-        if (p.out_bf16) reinterpret_cast<__nv_bfloat16*>(p.C)[off + j + t] = __float2bfloat16_rn(x);
-        else reinterpret_cast<float*>(p.C)[off + j + t] = x;
-      }
+      if (p.out_bf16) reinterpret_cast<__nv_bfloat16*>(p.C)[off + t] = __float2bfloat16_rn(x);
+      else reinterpret_cast<float*>(p.C)[off + t] = x;
     }
   }
 }
@@ -180,23 +181,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc::umma_commit(tmem_full);
     }
   } else {
+    // Epilogue.  TMEM gives each thread one ROW of the tile, which would make every global access
+    // a 32-way strided one.  So: (1) park the fp32 accumulators in shared memory (the operand ring
+    // is dead by now: every TMA load has landed and every MMA has retired before tmem_full fires),
+    // (2) re-read them row-contiguously so that bias / addend / aux loads and the C stores are
+    // fully coalesced 128-bit accesses.
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     tc::mbar_wait(tmem_full, 0);
     tc::tc_fence_after();
-    const int64_t row = (int64_t)m0 + q * 32 + lane;
+    float* stage = reinterpret_cast<float*>(smem);            // [128][EPI_PITCH]
+    {
+      float* srow = stage + (q * 32 + lane) * EPI_PITCH;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-      tc::tmem_ld_wait();
-      if (row < p.M && n0 + c * 32 < p.N) {
-        float v[32];
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+        tc::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        epilogue_row(p, row, (int64_t)n0 + c * 32, v);
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(srow + c * 32 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
       }
     }
     tc::tc_fence_before();
+    tc::named_bar_sync(1, 128);
+    const int et = threadIdx.x - 64;              // 0..127
+    const int col = (et & 31) * 4;                // 4 consecutive columns of the tile
+    const int64_t n = (int64_t)n0 + col;
+#pragma unroll 4
+    for (int r = et >> 5; r < BM; r += 4) {
+      const int64_t row = (int64_t)m0 + r;
+      if (row >= p.M || n >= p.N) continue;
+      const float4 acc = *reinterpret_cast<const float4*>(stage + r * EPI_PITCH + col);
+      float o[4] = {acc.x, acc.y, acc.z, acc.w};
+      epilogue_quad(p, row, n, o);
+    }
   }
   __syncthreads();
   if (warp == 1) {

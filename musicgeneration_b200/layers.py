@@ -419,10 +419,19 @@ class _LinearFunction(torch.autograd.Function):
     def backward(ctx, d_out):
         cfg, xa, Wa = ctx.cfg, ctx.xa, ctx.Wa
         N, K = Wa.shape
-        dy = _act_copy(_as_f32_2d(d_out, N), cfg.act)
+        d2 = _as_f32_2d(d_out, N)
+        T = d2.shape[0]
+        if cfg.act != torch.float32 and N % 8 != 0:
+            # the TMA-fed GEMM needs a 16-byte row pitch: copy dY into a zero-padded [T, ld] buffer
+            ld = (N + 7) // 8 * 8
+            dy_buf = torch.empty((T, ld), dtype=cfg.act, device=d2.device)
+            ops.cast2d(d2, N, dy_buf, ld, T, N)
+            dy = dy_buf[:, :N]
+        else:
+            dy = _act_copy(d2, cfg.act)
         dW = torch.empty((N, K), dtype=torch.float32, device=dy.device)
         db = torch.empty((N,), dtype=torch.float32, device=dy.device)
         engine.linear_wgrad(dy, xa, dW, db, cfg)
-        dx = torch.empty((dy.shape[0], K), dtype=torch.float32, device=dy.device)
+        dx = torch.empty((T, K), dtype=torch.float32, device=dy.device)
         engine.linear_dgrad(dy, Wa, dx, cfg)
         return None, dx.view(ctx.shape), dW, db

@@ -127,6 +127,12 @@ def cast(src, dst, n=None):
     L.check(L.load().mt_cast(_ptr(src), dt(src), _ptr(dst), dt(dst), n, _stream()), "cast")
 
 
+def cast2d(src, lds, dst, ldd, rows, cols):
+    _need_cuda(src, dst)
+    L.check(L.load().mt_cast2d(_ptr(src), dt(src), lds, _ptr(dst), dt(dst), ldd, rows, cols, _stream()),
+            "cast2d")
+
+
 def transpose_cast(src, dst, rows, cols):
     _need_cuda(src, dst)
     L.check(L.load().mt_transpose_cast(_ptr(src), dt(src), _ptr(dst), dt(dst), rows, cols, _stream()),

@@ -69,8 +69,10 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   float* xch = reinterpret_cast<float*>(smem + OFF_XCH);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z, hh = blockIdx.y;
-  const int i0 = (gridDim.x - 1 - blockIdx.x) * TT;          // longest rows first
+  // grid = (h, B, nT): the query-tile index is the slowest dimension, so over the whole launch the
+  // CTAs with the most key tiles are dispatched first
+  const int b = blockIdx.y, hh = blockIdx.x;
+  const int i0 = (gridDim.z - 1 - blockIdx.z) * TT;
   const int L = p.L;
   const int n_kt = p.causal ? (i0 / TT + 1) : (L + TT - 1) / TT;
 
@@ -340,7 +342,7 @@ int rga_fwd_tc(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
     if (e != cudaSuccess) { set_error("rga_fwd_tc: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_done = true;
   }
-  dim3 grid((a.L + TT - 1) / TT, a.h, a.B);
+  dim3 grid(a.h, a.B, (a.L + TT - 1) / TT);
   rga_fwd_tc_kernel<<<grid, NTHREADS, FWD_SMEM, st>>>(tmQ, tmK, tmV, tmE, p);
   return check_launch("rga_fwd_tc");
 }

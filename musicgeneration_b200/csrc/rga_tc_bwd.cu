@@ -47,12 +47,12 @@ template <> struct Lay<MODE_DQ> {        // Q,dO resident; {K,V,E_lo,E_hi} per s
   static constexpr int DS = STAGE0 + STAGE_BYTES, DG = DS + 2 * TILE, SCR = DG + 4 * TILE, BAR = SCR + SCR_BYTES;
   static constexpr int RES_TILES = 2, STAGE_TILES = 4;
 };
-template <> struct Lay<MODE_DE> {        // E_lo,E_hi resident; {Q,dO,K,V} per step
+template <> struct Lay<MODE_DE> {        // E_lo,E_hi resident; Q double buffered; {dO,K,V} per step, released early
   static constexpr int NST = 1;
-  static constexpr int ELO = 0, EHI = TILE, STAGE0 = 2 * TILE, STAGE_BYTES = 4 * TILE;
-  static constexpr int sQ = 0, sDO = TILE, sK = 2 * TILE, sV = 3 * TILE;
+  static constexpr int ELO = 0, EHI = TILE, Q0 = 2 * TILE, STAGE0 = 4 * TILE, STAGE_BYTES = 3 * TILE;
+  static constexpr int sDO = 0, sK = TILE, sV = 2 * TILE;
   static constexpr int DG = STAGE0 + STAGE_BYTES, SCR = DG + 4 * TILE, BAR = SCR + SCR_BYTES;
-  static constexpr int RES_TILES = 2, STAGE_TILES = 4;
+  static constexpr int RES_TILES = 2, STAGE_TILES = 3;
 };
 template <int MODE> constexpr int smem_bytes() { return Lay<MODE>::BAR + 256 + 1024; }
 static_assert(SCR_BYTES <= 2 * TILE, "DKV role parks the skew scratch in the stage's E_lo/E_hi buffers");
@@ -72,22 +72,24 @@ struct StepInfo { int it, jt, b, hh; };
 
 template <int MODE>
 __device__ __forceinline__ int num_steps(const BwdParams& p, int& bh0) {
+  // grid = (h, B, nT) [DKV, DQ] or (slices, 1, nT) [DE]: the tile / diagonal index is the SLOWEST
+  // grid dimension, so CTAs are dispatched longest-first over the whole launch
   bh0 = 0;
-  if (MODE == MODE_DKV) return p.nT - (int)blockIdx.x;
-  if (MODE == MODE_DQ) return p.nT - (int)blockIdx.x;          // it = nT-1-blockIdx.x  -> it+1 steps
-  bh0 = (int)blockIdx.y * p.bh_per_cta;
+  if (MODE == MODE_DKV) return p.nT - (int)blockIdx.z;
+  if (MODE == MODE_DQ) return p.nT - (int)blockIdx.z;          // it = nT-1-blockIdx.z  -> it+1 steps
+  bh0 = (int)blockIdx.x * p.bh_per_cta;
   int nbh = min(p.bh_per_cta, p.B * p.h - bh0);
-  return nbh > 0 ? nbh * (p.nT - (int)blockIdx.x) : 0;
+  return nbh > 0 ? nbh * (p.nT - (int)blockIdx.z) : 0;
 }
 template <int MODE>
 __device__ __forceinline__ StepInfo step_info(const BwdParams& p, int n, int bh0) {
   StepInfo s;
-  if (MODE == MODE_DKV) { s.jt = blockIdx.x; s.it = s.jt + n; s.hh = blockIdx.y; s.b = blockIdx.z; }
-  else if (MODE == MODE_DQ) { s.it = p.nT - 1 - (int)blockIdx.x; s.jt = n; s.hh = blockIdx.y; s.b = blockIdx.z; }
+  if (MODE == MODE_DKV) { s.jt = blockIdx.z; s.it = s.jt + n; s.hh = blockIdx.x; s.b = blockIdx.y; }
+  else if (MODE == MODE_DQ) { s.it = p.nT - 1 - (int)blockIdx.z; s.jt = n; s.hh = blockIdx.x; s.b = blockIdx.y; }
   else {
-    const int per = p.nT - (int)blockIdx.x;
+    const int per = p.nT - (int)blockIdx.z;
     const int bh = bh0 + n / per, k = n % per;
-    s.it = (int)blockIdx.x + k; s.jt = k; s.b = bh / p.h; s.hh = bh % p.h;
+    s.it = (int)blockIdx.z + k; s.jt = k; s.b = bh / p.h; s.hh = bh % p.h;
   }
   return s;
 }
@@ -110,7 +112,9 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* ds_ready = bars + 8;
   uint64_t* step_done = bars + 9;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-  uint8_t* spad = reinterpret_cast<uint8_t*>(bars + 11);      // [128]
+  uint64_t* q_full = bars + 11;       // [2]  (DE role: double-buffered Q)
+  uint64_t* q_empty = bars + 13;      // [2]
+  uint8_t* spad = reinterpret_cast<uint8_t*>(bars + 16);      // [128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int bh0;
@@ -120,7 +124,10 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     tc::tma_prefetch_desc(&tmQ); tc::tma_prefetch_desc(&tmK); tc::tma_prefetch_desc(&tmV);
     tc::tma_prefetch_desc(&tmDO); tc::tma_prefetch_desc(&tmE);
     tc::mbar_init(bar_res, 1);
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&ld_full[s], 1); tc::mbar_init(&ld_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&ld_full[s], 1); tc::mbar_init(&ld_empty[s], 1);
+      tc::mbar_init(&q_full[s], 1); tc::mbar_init(&q_empty[s], 1);
+    }
     tc::mbar_init(sg_full, 1);
     tc::mbar_init(sg_consumed, SM_THREADS);
     tc::mbar_init(dp_full, 1);
@@ -143,7 +150,7 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   auto buf_q = [&](int st) -> uint8_t* {
     if (MODE == MODE_DKV) return smem + Lay<MODE_DKV>::STAGE0 + st * Lay<MODE_DKV>::STAGE_BYTES + Lay<MODE_DKV>::sQ;
     if (MODE == MODE_DQ) return smem + Lay<MODE_DQ>::Q;
-    return smem + Lay<MODE_DE>::STAGE0 + Lay<MODE_DE>::sQ;
+    return smem + Lay<MODE_DE>::Q0 + st * TILE;          // DE: st = step parity (Q is double buffered)
   };
   auto buf_do = [&](int st) -> uint8_t* {
     if (MODE == MODE_DKV) return smem + Lay<MODE_DKV>::STAGE0 + st * Lay<MODE_DKV>::STAGE_BYTES + Lay<MODE_DKV>::sDO;
@@ -183,7 +190,7 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tc::tma_load_4d(buf_q(0), &tmQ, bar_res, 0, s0.hh, s0.it * TT, s0.b);
         tc::tma_load_4d(buf_do(0), &tmDO, bar_res, 0, s0.hh, s0.it * TT, s0.b);
       } else {
-        const int c0 = p.max_seq - 1 - (int)blockIdx.x * TT;
+        const int c0 = p.max_seq - 1 - (int)blockIdx.z * TT;
         tc::tma_load_2d(buf_elo(0), &tmE, bar_res, 0, c0 - (TT - 1));
         tc::tma_load_2d(buf_ehi(0), &tmE, bar_res, 0, c0 + 1);
       }
@@ -191,13 +198,17 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const StepInfo s = step_info<MODE>(p, n, bh0);
         const int st = (LY::NST == 2) ? (n & 1) : 0;
         const uint32_t ph = (LY::NST == 2) ? ((n >> 1) & 1) : (n & 1);
+        if (MODE == MODE_DE && n == 0) {
+          // Q lives until the end of the step (dE = dG^T Q), so it gets its own double buffer and
+          // is fetched one step ahead; {dO, K, V} are released as soon as S, G and dP are computed
+          tc::mbar_arrive_expect_tx(&q_full[0], TILE);
+          tc::tma_load_4d(buf_q(0), &tmQ, &q_full[0], 0, s.hh, s.it * TT, s.b);
+        }
         tc::mbar_wait(&ld_empty[st], ph ^ 1);
         tc::mbar_arrive_expect_tx(&ld_full[st], LY::STAGE_TILES * TILE);
         const int c0 = p.max_seq - 1 - (s.it - s.jt) * TT;
-        if (MODE != MODE_DQ) {
-          tc::tma_load_4d(buf_q(st), &tmQ, &ld_full[st], 0, s.hh, s.it * TT, s.b);
-          tc::tma_load_4d(buf_do(st), &tmDO, &ld_full[st], 0, s.hh, s.it * TT, s.b);
-        }
+        if (MODE == MODE_DKV) tc::tma_load_4d(buf_q(st), &tmQ, &ld_full[st], 0, s.hh, s.it * TT, s.b);
+        if (MODE != MODE_DQ) tc::tma_load_4d(buf_do(st), &tmDO, &ld_full[st], 0, s.hh, s.it * TT, s.b);
         if (MODE != MODE_DKV) {
           tc::tma_load_4d(buf_k(st), &tmK, &ld_full[st], 0, s.hh, s.jt * TT, s.b);
           tc::tma_load_4d(buf_v(st), &tmV, &ld_full[st], 0, s.hh, s.jt * TT, s.b);
@@ -210,7 +221,10 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           // single-buffered roles: pull the next step's tiles into L2 while this step computes
           const StepInfo t = step_info<MODE>(p, n + 1, bh0);
           if (MODE == MODE_DE) {
-            tc::tma_prefetch_4d(&tmQ, 0, t.hh, t.it * TT, t.b);
+            const int nb = (n + 1) & 1;
+            tc::mbar_wait(&q_empty[nb], (((n + 1) >> 1) & 1) ^ 1);
+            tc::mbar_arrive_expect_tx(&q_full[nb], TILE);
+            tc::tma_load_4d(buf_q(nb), &tmQ, &q_full[nb], 0, t.hh, t.it * TT, t.b);
             tc::tma_prefetch_4d(&tmDO, 0, t.hh, t.it * TT, t.b);
           }
           tc::tma_prefetch_4d(&tmK, 0, t.hh, t.jt * TT, t.b);
@@ -230,8 +244,9 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const uint32_t ph = (LY::NST == 2) ? ((n >> 1) & 1) : (n & 1);
         const uint32_t par = n & 1;
         tc::mbar_wait(&ld_full[st], ph);
+        if (MODE == MODE_DE) tc::mbar_wait(&q_full[n & 1], (n >> 1) & 1);
         tc::tc_fence_after();
-        const uint32_t qb = tc::smem_u32(buf_q(st)), dob = tc::smem_u32(buf_do(st));
+        const uint32_t qb = tc::smem_u32(buf_q(MODE == MODE_DE ? (n & 1) : st)), dob = tc::smem_u32(buf_do(st));
         const uint32_t kb = tc::smem_u32(buf_k(st)), vb = tc::smem_u32(buf_v(st));
         const uint32_t elo = tc::smem_u32(buf_elo(st)), ehi = tc::smem_u32(buf_ehi(st));
         // ---- phase A: S = Q K^T, G_lo = Q E_lo^T, G_hi = Q E_hi^T
@@ -251,6 +266,7 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           tc::umma_f16(tmem + TM_DP, tc::make_sdesc(dob + k4 * 32, 16, 1024),
                        tc::make_sdesc(vb + k4 * 32, 16, 1024), id_kk, k4 != 0);
         tc::umma_commit(dp_full);
+        if (MODE == MODE_DE) tc::umma_commit(&ld_empty[st]);     // dO, K, V are dead from here on
         // ---- phase E: role MMAs on the P / dS / dG operands written by the math warps
         tc::mbar_wait(ds_ready, par);
         tc::tc_fence_after();
@@ -283,7 +299,8 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                          (n | k16) != 0);
           }
         }
-        tc::umma_commit(&ld_empty[st]);
+        if (MODE == MODE_DE) tc::umma_commit(&q_empty[n & 1]);
+        else tc::umma_commit(&ld_empty[st]);
         tc::umma_commit(step_done);
       }
     }
@@ -425,7 +442,7 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     tc::mbar_wait(step_done, (nsteps - 1) & 1);
     tc::tc_fence_after();
     if (MODE == MODE_DE) {
-      const int c0 = p.max_seq - 1 - (int)blockIdx.x * TT;
+      const int c0 = p.max_seq - 1 - (int)blockIdx.z * TT;
 #pragma unroll
       for (int blk = 0; blk < 2; ++blk) {
         const int erow = (blk == 0 ? c0 - (TT - 1) : c0 + 1) + a;
@@ -508,7 +525,7 @@ int rga_bwd_tc(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
   p.scale = 1.f / a.inv_scale_div;
   p.scale_log2 = LOG2E / a.inv_scale_div;
   p.bh_per_cta = 1;
-  dim3 grid(p.nT, a.h, a.B);
+  dim3 grid(a.h, a.B, p.nT);
   if ((rc = launch_mode<MODE_DKV>(tmQ, tmK, tmV, tmDO, tmE, p, grid, st))) return rc;
   if ((rc = launch_mode<MODE_DQ>(tmQ, tmK, tmV, tmDO, tmE, p, grid, st))) return rc;
   // dE: one CTA per (tile diagonal, slice of (b,h)); about two CTAs per SM's worth of slices
@@ -518,7 +535,7 @@ int rga_bwd_tc(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
   if (slices < 1) slices = 1;
   p.bh_per_cta = (bh + slices - 1) / slices;
   slices = (bh + p.bh_per_cta - 1) / p.bh_per_cta;
-  dim3 grid_e(p.nT, slices, 1);
+  dim3 grid_e(slices, 1, p.nT);
   return launch_mode<MODE_DE>(tmQ, tmK, tmV, tmDO, tmE, p, grid_e, st);
 }
 

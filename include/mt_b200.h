@@ -155,6 +155,28 @@ int mt_kv_append(const void* qkv, void* kcache, void* vcache, int64_t B, int64_t
 int mt_sample(const float* logits, const float* u, int32_t* ids_out, int64_t B, int64_t V,
               float temperature, int32_t top_k, int greedy, void* stream);
 
+/* ---- decode with a DEVICE-RESIDENT step index ------------------------------------------------
+ * Same arithmetic as the ops above, but the current position t is read from *t_dev, so ONE CUDA
+ * graph of a whole decode step (embed -> per layer: QKV GEMM, append, attend, fc, LN, FFN, LN ->
+ * vocabulary GEMM -> sample -> advance) can be replayed for every generated event without any
+ * host work in between (MT/network.py:52-77 is a Python loop of full-stack recomputes).
+ * ids [B, ld_ids] int32 holds prior + generated tokens; pad_bits [B, max_seq]. */
+int mt_decode_embed(const int32_t* ids, int64_t ld_ids, const int32_t* t_dev, const float* emb,
+                    const float* pe, float* out_f32, void* out_lp, int lp_dtype, int64_t B, int64_t d,
+                    int64_t V, float scale, void* stream);
+int mt_decode_kv_append(const void* qkv, void* kcache, void* vcache, const int32_t* ids, int64_t ld_ids,
+                        int32_t pad_token, uint8_t* pad_bits, const int32_t* t_dev, int64_t B, int64_t h,
+                        int64_t dh, int64_t max_seq, int dtype, void* stream);
+int mt_decode_attend(const void* q, int64_t q_stride_b, const void* kcache, const void* vcache, const void* E,
+                     const uint8_t* pad_bits, void* out, const int32_t* t_dev, int64_t B, int64_t h, int64_t dh,
+                     int64_t max_seq, int dtype, void* stream);
+/* writes the sampled id to ids[b, t+1] unless t+1 < prior_len (prior tokens are kept); u holds one
+ * row of B uniforms per generated event (row t+1-prior_len) */
+int mt_decode_sample(const float* logits, const float* u, int32_t* ids, int64_t ld_ids, const int32_t* t_dev,
+                     int32_t prior_len, int64_t B, int64_t V, float temperature, int32_t top_k, int greedy,
+                     void* stream);
+int mt_decode_advance(int32_t* t_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

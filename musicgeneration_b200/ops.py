@@ -202,3 +202,35 @@ def sample(logits, u, ids_out, temperature, top_k, greedy):
     B, V = logits.shape
     L.check(L.load().mt_sample(_ptr(logits), _ptr(u), _ptr(ids_out), B, V, temperature, top_k,
                                int(greedy), _stream()), "sample")
+
+
+# ---- decode with a device-resident step index (CUDA-graph replayable) ----------------------
+def decode_embed(ids, t_dev, emb, pe, out_f32, out_lp, scale):
+    B, ld = ids.shape
+    V, d = emb.shape
+    L.check(L.load().mt_decode_embed(_ptr(ids), ld, _ptr(t_dev), _ptr(emb), _ptr(pe), _ptr(out_f32),
+                                     _ptr(out_lp), dt(out_lp) if out_lp is not None else L.MT_F32, B, d, V,
+                                     scale, _stream()), "decode_embed")
+
+
+def decode_kv_append(qkv, kcache, vcache, ids, pad_token, pad_bits, t_dev, B, h, dh, max_seq):
+    L.check(L.load().mt_decode_kv_append(_ptr(qkv), _ptr(kcache), _ptr(vcache), _ptr(ids), ids.shape[1],
+                                         pad_token, _ptr(pad_bits), _ptr(t_dev), B, h, dh, max_seq, dt(qkv),
+                                         _stream()), "decode_kv_append")
+
+
+def decode_attend(q, q_stride_b, kcache, vcache, E, pad_bits, out, t_dev, B, h, dh, max_seq):
+    L.check(L.load().mt_decode_attend(_ptr(q), q_stride_b, _ptr(kcache), _ptr(vcache), _ptr(E),
+                                      _ptr(pad_bits), _ptr(out), _ptr(t_dev), B, h, dh, max_seq, dt(q),
+                                      _stream()), "decode_attend")
+
+
+def decode_sample(logits, u, ids, t_dev, prior_len, temperature, top_k, greedy):
+    B, V = logits.shape
+    L.check(L.load().mt_decode_sample(_ptr(logits), _ptr(u), _ptr(ids), ids.shape[1], _ptr(t_dev),
+                                      prior_len, B, V, temperature, top_k, int(greedy), _stream()),
+            "decode_sample")
+
+
+def decode_advance(t_dev):
+    L.check(L.load().mt_decode_advance(_ptr(t_dev), _stream()), "decode_advance")

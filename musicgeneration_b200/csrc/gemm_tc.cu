@@ -159,23 +159,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc(BM, BN, fmt, fmt, A_MN, B_MN);
+      const uint64_t ad_k = tc::make_sdesc(tc::smem_u32(sA), 16, 1024), ad_mn = tc::make_sdesc(tc::smem_u32(sA), TILE_BYTES / 2, 1024);
+      const uint64_t bd_k = tc::make_sdesc(tc::smem_u32(sB), 16, 1024), bd_mn = tc::make_sdesc(tc::smem_u32(sB), TILE_BYTES / 2, 1024);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         tc::mbar_wait(&full[s], ph);
         tc::tc_fence_after();
-        const uint32_t a_base = tc::smem_u32(sA + s * TILE_BYTES);
-        const uint32_t b_base = tc::smem_u32(sB + s * TILE_BYTES);
+        // K-major: 16 elements = 32 B inside the 128 B swizzle row; 8-row groups 1024 B apart.
+        // MN-major: 16 k-rows of 128 B = 2048 B; the two 64-wide MN halves are 8192 B apart.
+        // One descriptor per operand and stage; a k-step is an add on its 16-byte address field.
+        const uint64_t ad0 = (A_MN ? ad_mn : ad_k) + (uint64_t)s * (TILE_BYTES >> 4);
+        const uint64_t bd0 = (B_MN ? bd_mn : bd_k) + (uint64_t)s * (TILE_BYTES >> 4);
 #pragma unroll
-        for (int k4 = 0; k4 < BK / 16; ++k4) {
-          // K-major: 16 elements = 32 B inside the 128 B swizzle row; 8-row groups 1024 B apart.
-          // MN-major: 16 k-rows of 128 B = 2048 B; the two 64-wide MN halves are 8192 B apart.
-          const uint64_t ad = A_MN ? tc::make_sdesc(a_base + k4 * 2048, TILE_BYTES / 2, 1024)
-                                   : tc::make_sdesc(a_base + k4 * 32, 16, 1024);
-          const uint64_t bd = B_MN ? tc::make_sdesc(b_base + k4 * 2048, TILE_BYTES / 2, 1024)
-                                   : tc::make_sdesc(b_base + k4 * 32, 16, 1024);
-          tc::umma_f16(tmem_base, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
-        }
+        for (int k4 = 0; k4 < BK / 16; ++k4)
+          tc::umma_f16(tmem_base, ad0 + (A_MN ? 128 : 2) * k4, bd0 + (B_MN ? 128 : 2) * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
         tc::umma_commit(&empty[s]);
       }
       tc::umma_commit(tmem_full);

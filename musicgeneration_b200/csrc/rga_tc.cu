@@ -14,8 +14,8 @@
 // zero-filled by TMA, which realises the reference's _qe_masking.  Online softmax in fp32 with
 // exp2; LSE saved for the backward.
 //
-// Warps 0-7: softmax / correction / epilogue (row a = 32*(w&3)+lane, key columns 64*(w>>2)..+63),
-// warp 8: TMA producer, warp 9: TMEM allocator + MMA issuer.
+// Warps 0-15: softmax / correction / epilogue (row a = 32*(w&3)+lane, key columns 32*(w>>2)..+31),
+// warp 16: TMA producer, warp 17: TMEM allocator + MMA issuer.
 #include "ops.cuh"
 #include "rga_tc_common.cuh"
 
@@ -25,20 +25,34 @@ using namespace rga;
 
 namespace {
 
+// 16 softmax warps: warp w works on TMEM lanes 32*(w&3)..+31 (query row a = 32*(w&3)+lane) and on
+// the key-column quarter qt = w>>2, i.e. 32 logits per thread and step.  Four warps per scheduler
+// hide each other's TMEM / shared-memory / MUFU latency; the per-thread state stays below the
+// 112-register budget of a 576-thread CTA.
+constexpr int FW_MATH_WARPS = 16;
+constexpr int FW_MATH_THREADS = FW_MATH_WARPS * 32;
+constexpr int FW_THREADS = FW_MATH_THREADS + 64;     // + TMA producer warp + MMA issuer warp
+constexpr int FW_SCR_BYTES = FW_MATH_THREADS * SCR32_WORDS * 4;
+
 // shared memory map (offsets from the 1024-aligned base)
 constexpr int OFF_Q = 0;
 constexpr int OFF_K = OFF_Q + TILE;            // 2 stages
 constexpr int OFF_V = OFF_K + 2 * TILE;        // 2 stages
 constexpr int OFF_E = OFF_V + 2 * TILE;        // 2 stages: the new "hi" block of each step
-constexpr int OFF_ELO = OFF_E + 2 * TILE;      // "lo" block of the first step only
-constexpr int OFF_P = OFF_ELO + TILE;          // 2 K-subtiles of [128 x 64] 16-bit
+constexpr int OFF_P = OFF_E + 2 * TILE;        // 2 K-subtiles of [128 x 64] 16-bit
+constexpr int OFF_ELO = OFF_P;                 // "lo" block of the first step: dead before the first P is written
 constexpr int OFF_SCR = OFF_P + 2 * TILE;
-constexpr int OFF_XCH = OFF_SCR + SCR_BYTES;   // [2 parities][2 halves][128] floats: row max / row sum exchange
-constexpr int OFF_BAR = OFF_XCH + 4 * TT * 4;
+constexpr int OFF_XCH = OFF_SCR + FW_SCR_BYTES;   // [2 parities][4 quarters][128] floats: row max / row sum exchange
+constexpr int OFF_BAR = OFF_XCH + 2 * 4 * TT * 4;
 constexpr int FWD_SMEM = OFF_BAR + 256 + 1024;
+static_assert(FWD_SMEM <= 232448, "forward kernel exceeds the 227 KB shared-memory limit");
 
 // TMEM columns
 constexpr uint32_t TM_S = 0, TM_G0 = 128, TM_G1 = 256, TM_O = 384;
+
+// O is rescaled only when the running row maximum grows by more than 2^RESCALE_LOG2: P stays
+// below 2^8 (exact in the fp32 row sums, same relative precision in the 16-bit operand)
+constexpr float RESCALE_LOG2 = 8.f;
 
 struct FwdParams {
   void* O; int64_t ob, ol, oh;
@@ -48,7 +62,7 @@ struct FwdParams {
   float scale_log2;     // log2(e) / sqrt(dh)
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(FW_THREADS, 1)
 rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmE,
                   const FwdParams p) {
@@ -76,7 +90,7 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const int L = p.L;
   const int n_kt = p.causal ? (i0 / TT + 1) : (L + TT - 1) / TT;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == FW_MATH_WARPS && lane == 0) {
     tc::tma_prefetch_desc(&tmQ);
     tc::tma_prefetch_desc(&tmK);
     tc::tma_prefetch_desc(&tmV);
@@ -87,18 +101,18 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc::mbar_init(&kv_empty[s], 1);
     }
     tc::mbar_init(s_full, 1);
-    tc::mbar_init(s_consumed, SM_THREADS);
-    tc::mbar_init(p_full, SM_THREADS);
+    tc::mbar_init(s_consumed, FW_MATH_THREADS);
+    tc::mbar_init(p_full, FW_MATH_THREADS);
     tc::mbar_init(o_done, 1);
     tc::fence_barrier_init();
   }
-  if (warp == 9) tc::tmem_alloc(tmem_slot, 512);
+  if (warp == FW_MATH_WARPS + 1) tc::tmem_alloc(tmem_slot, 512);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == FW_MATH_WARPS) {
     // ================================ TMA producer ==========================================
     if (lane == 0) {
       tc::mbar_arrive_expect_tx(bar_q, TILE);
@@ -110,34 +124,35 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tc::mbar_wait(&kv_empty[s], ((jt >> 1) & 1) ^ 1);
         tc::mbar_arrive_expect_tx(&kv_full[s], (jt == 0 ? 4 : 3) * TILE);
         tc::tma_load_4d(smem + OFF_K + s * TILE, &tmK, &kv_full[s], 0, hh, j0, b);
-        tc::tma_load_4d(smem + OFF_V + s * TILE, &tmV, &kv_full[s], 0, hh, j0, b);
         tc::tma_load_2d(smem + OFF_E + s * TILE, &tmE, &kv_full[s], 0, c0 + 1);
         if (jt == 0) tc::tma_load_2d(smem + OFF_ELO, &tmE, &kv_full[s], 0, c0 - (TT - 1));
+        tc::tma_load_4d(smem + OFF_V + s * TILE, &tmV, &kv_full[s], 0, hh, j0, b);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == FW_MATH_WARPS + 1) {
     // ================================ MMA issuer ============================================
     if (lane == 0) {
       const uint32_t idesc_s = tc::make_idesc(TT, TT, p.fmt, p.fmt, 0, 0);     // S, G: K-major x K-major
       const uint32_t idesc_o = tc::make_idesc(TT, DHC, p.fmt, p.fmt, 0, 1);    // O: P K-major, V MN-major
-      const uint32_t q_base = tc::smem_u32(smem + OFF_Q);
+      // descriptors are built once; a k-step inside the loops is an add on the 16-byte address field
+      const uint64_t qd0 = tc::make_sdesc(tc::smem_u32(smem + OFF_Q), 16, 1024);
+      const uint64_t kd0 = tc::make_sdesc(tc::smem_u32(smem + OFF_K), 16, 1024);
+      const uint64_t ed0 = tc::make_sdesc(tc::smem_u32(smem + OFF_E), 16, 1024);
+      const uint64_t elod = tc::make_sdesc(tc::smem_u32(smem + OFF_ELO), 16, 1024);
+      const uint64_t pd0 = tc::make_sdesc(tc::smem_u32(smem + OFF_P), 16, 1024);
+      const uint64_t vd0 = tc::make_sdesc(tc::smem_u32(smem + OFF_V), 1024, 1024);
       auto issue_s = [&](int jt) {
-        const int s = jt & 1;
-        const uint32_t k_base = tc::smem_u32(smem + OFF_K + s * TILE);
-        const uint32_t e_base = tc::smem_u32(smem + OFF_E + s * TILE);
+        const uint64_t so = (uint64_t)(jt & 1) * (TILE >> 4);
         const uint32_t g_hi = tmem + (((jt + 1) & 1) ? TM_G1 : TM_G0);
 #pragma unroll
         for (int k4 = 0; k4 < DHC / 16; ++k4) {
-          const uint64_t qd = tc::make_sdesc(q_base + k4 * 32, 16, 1024);
-          tc::umma_f16(tmem + TM_S, qd, tc::make_sdesc(k_base + k4 * 32, 16, 1024), idesc_s, k4 != 0);
-          tc::umma_f16(g_hi, qd, tc::make_sdesc(e_base + k4 * 32, 16, 1024), idesc_s, k4 != 0);
+          tc::umma_f16(tmem + TM_S, qd0 + 2 * k4, kd0 + so + 2 * k4, idesc_s, k4 != 0);
+          tc::umma_f16(g_hi, qd0 + 2 * k4, ed0 + so + 2 * k4, idesc_s, k4 != 0);
         }
         if (jt == 0) {
-          const uint32_t elo = tc::smem_u32(smem + OFF_ELO);
 #pragma unroll
           for (int k4 = 0; k4 < DHC / 16; ++k4)
-            tc::umma_f16(tmem + TM_G0, tc::make_sdesc(q_base + k4 * 32, 16, 1024),
-                         tc::make_sdesc(elo + k4 * 32, 16, 1024), idesc_s, k4 != 0);
+            tc::umma_f16(tmem + TM_G0, qd0 + 2 * k4, elod + 2 * k4, idesc_s, k4 != 0);
         }
         tc::umma_commit(s_full);
       };
@@ -154,69 +169,68 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         tc::mbar_wait(p_full, jt & 1);
         tc::tc_fence_after();
-        const uint32_t p_base = tc::smem_u32(smem + OFF_P);
-        const uint32_t v_base = tc::smem_u32(smem + OFF_V + (jt & 1) * TILE);
+        const uint64_t vd = vd0 + (uint64_t)(jt & 1) * (TILE >> 4);
 #pragma unroll
-        for (int k8 = 0; k8 < TT / 16; ++k8) {
-          const uint64_t pd = tc::make_sdesc(p_base + (k8 >> 2) * TILE + (k8 & 3) * 32, 16, 1024);
-          const uint64_t vd = tc::make_sdesc(v_base + k8 * 2048, 1024, 1024);
-          tc::umma_f16(tmem + TM_O, pd, vd, idesc_o, (jt | k8) != 0);
-        }
+        for (int k8 = 0; k8 < TT / 16; ++k8)     // P sub-tile k8>>2, 16 keys = 32 B inside its rows; V: 16 key rows = 2048 B
+          tc::umma_f16(tmem + TM_O, pd0 + (k8 >> 2) * (TILE >> 4) + 2 * (k8 & 3), vd + 128 * k8, idesc_o, (jt | k8) != 0);
         tc::umma_commit(&kv_empty[jt & 1]);
         tc::umma_commit(o_done);
       }
     }
   } else {
     // ================================ softmax warps =========================================
-    const int w4 = warp & 3, wg = warp >> 2;
+    const int w4 = warp & 3, qt = warp >> 2;
     const int a = w4 * 32 + lane;                      // query row within the tile == TMEM lane
     const int i = i0 + a;
     const uint32_t lane_base = (uint32_t)(w4 * 32) << 16;
-    uint32_t* scr = reinterpret_cast<uint32_t*>(smem + OFF_SCR) + threadIdx.x * SCR_WORDS;
+    uint32_t* scr = reinterpret_cast<uint32_t*>(smem + OFF_SCR) + threadIdx.x * SCR32_WORDS;
+    const int w0 = 96 - 32 * w4 + 32 * qt;             // first band column of the warp's window
+    const int rowbar = 2 + w4;                         // named barrier of the four warps sharing these rows
     const uint8_t* padrow = p.pad ? p.pad + (int64_t)b * L : nullptr;
     if (padrow) {
       // training batches carry no pad tokens: decide once per CTA whether any key this CTA visits
       // is padded, and drop to the unmasked path if none is
       bool mine = false;
       const int jend = min(L, n_kt * TT);
-      for (int j = threadIdx.x; j < jend; j += SM_THREADS) mine |= (padrow[j] != 0);
-      if (!tc::named_bar_red_or(1, SM_THREADS, mine)) padrow = nullptr;
+      for (int j = threadIdx.x; j < jend; j += FW_MATH_THREADS) mine |= (padrow[j] != 0);
+      if (!tc::named_bar_red_or(1, FW_MATH_THREADS, mine)) padrow = nullptr;
     }
-    float m_run = -INFINITY, l_part = 0.f;             // l_part: this thread's half of the row sum
+    float m_run = -INFINITY, l_part = 0.f;             // l_part: this thread's quarter of the row sum
 
     for (int jt = 0; jt < n_kt; ++jt) {
       const int j0 = jt * TT;
       if (padrow) {          // stage the key tile's pad flags (overlaps the MMA)
-        tc::named_bar_sync(1, SM_THREADS);
-        if (wg == 0) spad[a] = (j0 + a < L) ? padrow[j0 + a] : 1;
-        tc::named_bar_sync(1, SM_THREADS);
+        tc::named_bar_sync(1, FW_MATH_THREADS);
+        if (qt == 0) spad[a] = (j0 + a < L) ? padrow[j0 + a] : 1;
+        tc::named_bar_sync(1, FW_MATH_THREADS);
       }
       tc::mbar_wait(s_full, jt & 1);
       tc::tc_fence_after();
       const uint32_t g_lo = tmem + ((jt & 1) ? TM_G1 : TM_G0);
       const uint32_t g_hi = tmem + (((jt + 1) & 1) ? TM_G1 : TM_G0);
 
-      float sv[64];
+      // band window -> scratch, then S; the skewed read of the scratch overlaps the S load
+      skew_park_64(g_lo, g_hi, lane_base, w0, scr);
+      float sv[32];
       {
-        uint32_t r0[32], r1[32];
-        tc::tmem_ld_32x32(tmem + TM_S + lane_base + wg * 64, r0);
-        tc::tmem_ld_32x32(tmem + TM_S + lane_base + wg * 64 + 32, r1);
+        uint32_t r[32];
+        tc::tmem_ld_32x32(tmem + TM_S + lane_base + qt * 32, r);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int x = 0; x < 32; ++x) { sv[x] = __uint_as_float(r0[x]); sv[32 + x] = __uint_as_float(r1[x]); }
+        for (int x = 0; x < 32; ++x) sv[x] = __uint_as_float(r[x]);
       }
-      skew_add_64(sv, g_lo, g_hi, lane_base, w4, wg, lane, scr);
       // S / G fully read: the MMA warp may overwrite them with the next key tile
       tc::tc_fence_before();
       tc::mbar_arrive(s_consumed);
+      skew_fetch_add_32(sv, scr, lane);
 
       // ---- mask (only on the diagonal / ragged / padded tiles) + online softmax (log2 domain)
       const bool diag = p.causal && (j0 == i0);
       const bool tail = (j0 + TT > L);
       if (diag || tail || padrow != nullptr) {
 #pragma unroll
-        for (int x = 0; x < 64; ++x) {
-          const int bcol = wg * 64 + x;
+        for (int x = 0; x < 32; ++x) {
+          const int bcol = qt * 32 + x;
           bool ok = true;
           if (diag) ok = (bcol <= a);
           if (tail) ok = ok && (j0 + bcol < L);
@@ -224,86 +238,95 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           if (!ok) sv[x] = -INFINITY;
         }
       }
-      float mx = sv[0];
+      float mx0 = fmaxf(sv[0], sv[1]), mx1 = fmaxf(sv[2], sv[3]);
 #pragma unroll
-      for (int x = 1; x < 64; ++x) mx = fmaxf(mx, sv[x]);
-      // exchange the half-row maxima with the partner thread (other warpgroup, same row); the slots
-      // alternate with the step parity, so a slot is rewritten only after its reader passed the
-      // following step's barrier
-      float* xs = xch + (jt & 1) * 2 * TT;
-      xs[wg * TT + a] = mx;
-      tc::named_bar_sync(2, SM_THREADS);
-      mx = fmaxf(mx, xs[(wg ^ 1) * TT + a]) * p.scale_log2;      // scale > 0: max commutes
-      const float m_new = fmaxf(m_run, mx);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = tc::fast_exp2(m_run - m_use);      // m_run = -inf -> 0
-      float sum = 0.f;
-#pragma unroll
-      for (int x = 0; x < 64; ++x) {
-        sv[x] = tc::fast_exp2(fmaf(sv[x], p.scale_log2, -m_use));
-        sum += sv[x];
+      for (int x = 4; x < 32; x += 4) {
+        mx0 = fmaxf(mx0, fmaxf(sv[x], sv[x + 1]));
+        mx1 = fmaxf(mx1, fmaxf(sv[x + 2], sv[x + 3]));
       }
-      l_part = l_part * alpha + sum;
-      m_run = m_new;
+      float mx = fmaxf(mx0, mx1);
+      // exchange the quarter-row maxima with the three partner threads (other quarters, same row);
+      // the slots alternate with the step parity, so a slot is rewritten only after its readers
+      // passed the following step's barrier
+      float* xs = xch + (jt & 1) * 4 * TT;
+      xs[qt * TT + a] = mx;
+      tc::named_bar_sync(rowbar, 128);
+      mx = fmaxf(fmaxf(xs[a], xs[TT + a]), fmaxf(xs[2 * TT + a], xs[3 * TT + a])) * p.scale_log2;   // scale > 0
+      float alpha = 1.f;
+      if (mx > m_run + RESCALE_LOG2) {          // also the first tile (m_run = -inf) unless fully masked
+        alpha = tc::fast_exp2(m_run - mx);      // m_run = -inf -> 0
+        m_run = mx;
+        l_part *= alpha;
+      }
+      const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+#pragma unroll
+      for (int x = 0; x < 32; x += 4) {
+        sv[x] = tc::fast_exp2(fmaf(sv[x], p.scale_log2, -m_use));
+        sv[x + 1] = tc::fast_exp2(fmaf(sv[x + 1], p.scale_log2, -m_use));
+        sv[x + 2] = tc::fast_exp2(fmaf(sv[x + 2], p.scale_log2, -m_use));
+        sv[x + 3] = tc::fast_exp2(fmaf(sv[x + 3], p.scale_log2, -m_use));
+        sum0 += sv[x]; sum1 += sv[x + 1]; sum2 += sv[x + 2]; sum3 += sv[x + 3];
+      }
+      l_part += (sum0 + sum1) + (sum2 + sum3);
+      uint32_t pk[16];
+#pragma unroll
+      for (int x = 0; x < 16; ++x) pk[x] = pack16(sv[2 * x], sv[2 * x + 1], p.fmt);
 
       // ---- previous P.V must be complete before O is rescaled and P overwritten
       if (jt > 0) {
         tc::mbar_wait(o_done, (jt - 1) & 1);
         tc::tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha != 1.f)) {
-          uint32_t r[32];
-          tc::tmem_ld_32x32(tmem + TM_O + lane_base + wg * 32, r);
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {       // each quarter rescales 16 of O's 64 columns
+          uint32_t r[16];
+          tc::tmem_ld_32x16(tmem + TM_O + lane_base + qt * 16, r);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int x = 0; x < 32; ++x) r[x] = __float_as_uint(__uint_as_float(r[x]) * alpha);
-          tc::tmem_st_32x32(tmem + TM_O + lane_base + wg * 32, r);
+          for (int x = 0; x < 16; ++x) r[x] = __float_as_uint(__uint_as_float(r[x]) * alpha);
+          tc::tmem_st_32x16(tmem + TM_O + lane_base + qt * 16, r);
           tc::tmem_st_wait();
         }
       }
-      // ---- P (16-bit) into the K-major 128B-swizzled operand layout (sub-tile wg of the row)
-      uint8_t* ptile = smem + OFF_P + wg * TILE;
+      // ---- P (16-bit) into the K-major 128B-swizzled operand layout: sub-tile qt>>1, chunks 4*(qt&1)..+3
+      uint8_t* ptile = smem + OFF_P + (qt >> 1) * TILE;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float* v = sv + c * 8;
-        *reinterpret_cast<uint4*>(ptile + swz_chunk(a, c)) =
-            make_uint4(pack16(v[0], v[1], p.fmt), pack16(v[2], v[3], p.fmt), pack16(v[4], v[5], p.fmt),
-                       pack16(v[6], v[7], p.fmt));
-      }
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(ptile + swz_chunk(a, (qt & 1) * 4 + c)) =
+            make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
       tc::fence_proxy_async();
       tc::tc_fence_before();
       tc::mbar_arrive(p_full);
     }
     // ---- epilogue: O / l, LSE
-    float* xs = xch + (n_kt & 1) * 2 * TT;
-    xs[wg * TT + a] = l_part;
-    tc::named_bar_sync(2, SM_THREADS);
-    const float l_run = l_part + xs[(wg ^ 1) * TT + a];
+    float* xs = xch + (n_kt & 1) * 4 * TT;
+    xs[qt * TT + a] = l_part;
+    tc::named_bar_sync(rowbar, 128);
+    const float l_run = (xs[a] + xs[TT + a]) + (xs[2 * TT + a] + xs[3 * TT + a]);
     tc::mbar_wait(o_done, (n_kt - 1) & 1);
     tc::tc_fence_after();
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-    uint32_t packed[16];
+    uint32_t packed[8];
     {
-      uint32_t r[32];
-      tc::tmem_ld_32x32(tmem + TM_O + lane_base + wg * 32, r);
+      uint32_t r[16];
+      tc::tmem_ld_32x16(tmem + TM_O + lane_base + qt * 16, r);
       tc::tmem_ld_wait();
 #pragma unroll
-      for (int x = 0; x < 32; x += 2)
+      for (int x = 0; x < 16; x += 2)
         packed[x / 2] = pack16(__uint_as_float(r[x]) * inv, __uint_as_float(r[x + 1]) * inv, p.fmt);
     }
     if (i < L) {
       uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.O) + (int64_t)b * p.ob + (int64_t)i * p.ol +
-                                            (int64_t)hh * p.oh + wg * 32);
-#pragma unroll
-      for (int x = 0; x < 4; ++x)
-        dst[x] = make_uint4(packed[4 * x], packed[4 * x + 1], packed[4 * x + 2], packed[4 * x + 3]);
+                                            (int64_t)hh * p.oh + qt * 16);
+      dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
       // natural-log LSE of the scaled logits (what the backward and rga_weights consume)
-      if (wg == 0)
+      if (qt == 0)
         p.lse[((int64_t)b * p.h + hh) * L + i] = l_run > 0.f ? (m_run + log2f(l_run)) * 0.6931471805599453f : 0.f;
     }
     tc::tc_fence_before();
   }
   __syncthreads();
-  if (warp == 9) {
+  if (warp == FW_MATH_WARPS + 1) {
     tc::tc_fence_after();
     tc::tmem_dealloc(tmem, 512);
   }
@@ -343,7 +366,7 @@ int rga_fwd_tc(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
     attr_done = true;
   }
   dim3 grid(a.h, a.B, (a.L + TT - 1) / TT);
-  rga_fwd_tc_kernel<<<grid, NTHREADS, FWD_SMEM, st>>>(tmQ, tmK, tmV, tmE, p);
+  rga_fwd_tc_kernel<<<grid, FW_THREADS, FWD_SMEM, st>>>(tmQ, tmK, tmV, tmE, p);
   return check_launch("rga_fwd_tc");
 }
 

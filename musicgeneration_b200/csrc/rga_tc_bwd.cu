@@ -246,16 +246,24 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tc::mbar_wait(&ld_full[st], ph);
         if (MODE == MODE_DE) tc::mbar_wait(&q_full[n & 1], (n >> 1) & 1);
         tc::tc_fence_after();
-        const uint32_t qb = tc::smem_u32(buf_q(MODE == MODE_DE ? (n & 1) : st)), dob = tc::smem_u32(buf_do(st));
-        const uint32_t kb = tc::smem_u32(buf_k(st)), vb = tc::smem_u32(buf_v(st));
-        const uint32_t elo = tc::smem_u32(buf_elo(st)), ehi = tc::smem_u32(buf_ehi(st));
+        // descriptors: built per step from the buffer addresses, k-steps are adds on the address field
+        const uint64_t qk = tc::make_sdesc(tc::smem_u32(buf_q(MODE == MODE_DE ? (n & 1) : st)), 16, 1024);
+        const uint64_t qmn = tc::make_sdesc(tc::smem_u32(buf_q(MODE == MODE_DE ? (n & 1) : st)), 1024, 1024);
+        const uint64_t dok = tc::make_sdesc(tc::smem_u32(buf_do(st)), 16, 1024);
+        const uint64_t domn = tc::make_sdesc(tc::smem_u32(buf_do(st)), 1024, 1024);
+        const uint64_t kk = tc::make_sdesc(tc::smem_u32(buf_k(st)), 16, 1024);
+        const uint64_t kmn = tc::make_sdesc(tc::smem_u32(buf_k(st)), 1024, 1024);
+        const uint64_t vk = tc::make_sdesc(tc::smem_u32(buf_v(st)), 16, 1024);
+        const uint64_t elok = tc::make_sdesc(tc::smem_u32(buf_elo(st)), 16, 1024);
+        const uint64_t ehik = tc::make_sdesc(tc::smem_u32(buf_ehi(st)), 16, 1024);
+        const uint64_t elomn = tc::make_sdesc(tc::smem_u32(buf_elo(st)), 1024, 1024);
+        const uint64_t ehimn = tc::make_sdesc(tc::smem_u32(buf_ehi(st)), 1024, 1024);
         // ---- phase A: S = Q K^T, G_lo = Q E_lo^T, G_hi = Q E_hi^T
 #pragma unroll
         for (int k4 = 0; k4 < DHC / 16; ++k4) {
-          const uint64_t qd = tc::make_sdesc(qb + k4 * 32, 16, 1024);
-          tc::umma_f16(tmem + TM_S, qd, tc::make_sdesc(kb + k4 * 32, 16, 1024), id_kk, k4 != 0);
-          tc::umma_f16(tmem + TM_GLO, qd, tc::make_sdesc(elo + k4 * 32, 16, 1024), id_kk, k4 != 0);
-          tc::umma_f16(tmem + TM_GHI, qd, tc::make_sdesc(ehi + k4 * 32, 16, 1024), id_kk, k4 != 0);
+          tc::umma_f16(tmem + TM_S, qk + 2 * k4, kk + 2 * k4, id_kk, k4 != 0);
+          tc::umma_f16(tmem + TM_GLO, qk + 2 * k4, elok + 2 * k4, id_kk, k4 != 0);
+          tc::umma_f16(tmem + TM_GHI, qk + 2 * k4, ehik + 2 * k4, id_kk, k4 != 0);
         }
         tc::umma_commit(sg_full);
         // ---- phase C: dP = dO V^T into the G_lo columns (after the math warps read S / G)
@@ -263,40 +271,36 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tc::tc_fence_after();
 #pragma unroll
         for (int k4 = 0; k4 < DHC / 16; ++k4)
-          tc::umma_f16(tmem + TM_DP, tc::make_sdesc(dob + k4 * 32, 16, 1024),
-                       tc::make_sdesc(vb + k4 * 32, 16, 1024), id_kk, k4 != 0);
+          tc::umma_f16(tmem + TM_DP, dok + 2 * k4, vk + 2 * k4, id_kk, k4 != 0);
         tc::umma_commit(dp_full);
         if (MODE == MODE_DE) tc::umma_commit(&ld_empty[st]);     // dO, K, V are dead from here on
         // ---- phase E: role MMAs on the P / dS / dG operands written by the math warps
         tc::mbar_wait(ds_ready, par);
         tc::tc_fence_after();
         if (MODE == MODE_DKV) {
-          const uint32_t pb = tc::smem_u32(smem + Lay<MODE_DKV>::P), dsb = tc::smem_u32(smem + Lay<MODE_DKV>::DS);
+          const uint64_t pd = tc::make_sdesc(tc::smem_u32(smem + Lay<MODE_DKV>::P), TILE, 1024);
+          const uint64_t dsd = tc::make_sdesc(tc::smem_u32(smem + Lay<MODE_DKV>::DS), TILE, 1024);
 #pragma unroll
           for (int k16 = 0; k16 < TT / 16; ++k16) {      // contraction over the 128 query rows
-            const uint64_t dod = tc::make_sdesc(dob + k16 * 2048, 1024, 1024);
-            const uint64_t qd = tc::make_sdesc(qb + k16 * 2048, 1024, 1024);
-            tc::umma_f16(tmem + TM_ACC1, tc::make_sdesc(pb + k16 * 2048, TILE, 1024), dod, id_mnmn, (n | k16) != 0);
-            tc::umma_f16(tmem + TM_ACC0, tc::make_sdesc(dsb + k16 * 2048, TILE, 1024), qd, id_mnmn, (n | k16) != 0);
+            tc::umma_f16(tmem + TM_ACC1, pd + 128 * k16, domn + 128 * k16, id_mnmn, (n | k16) != 0);
+            tc::umma_f16(tmem + TM_ACC0, dsd + 128 * k16, qmn + 128 * k16, id_mnmn, (n | k16) != 0);
           }
         } else if (MODE == MODE_DQ) {
-          const uint32_t dsb = tc::smem_u32(smem + Lay<MODE_DQ>::DS), dgb = tc::smem_u32(smem + Lay<MODE_DQ>::DG);
+          const uint64_t dsd = tc::make_sdesc(tc::smem_u32(smem + Lay<MODE_DQ>::DS), 16, 1024);
+          const uint64_t dgd = tc::make_sdesc(tc::smem_u32(smem + Lay<MODE_DQ>::DG), 16, 1024);
 #pragma unroll
           for (int k16 = 0; k16 < TT / 16; ++k16)         // dS . K_j (contraction over the 128 keys)
-            tc::umma_f16(tmem + TM_ACC0, tc::make_sdesc(dsb + (k16 >> 2) * TILE + (k16 & 3) * 32, 16, 1024),
-                         tc::make_sdesc(kb + k16 * 2048, 1024, 1024), id_kmn, (n | k16) != 0);
+            tc::umma_f16(tmem + TM_ACC0, dsd + (k16 >> 2) * (TILE >> 4) + 2 * (k16 & 3), kmn + 128 * k16, id_kmn, (n | k16) != 0);
 #pragma unroll
           for (int k16 = 0; k16 < 2 * TT / 16; ++k16)     // dG . [E_lo; E_hi] (contraction over the band)
-            tc::umma_f16(tmem + TM_ACC0, tc::make_sdesc(dgb + (k16 >> 2) * TILE + (k16 & 3) * 32, 16, 1024),
-                         tc::make_sdesc((k16 < 8 ? elo + k16 * 2048 : ehi + (k16 - 8) * 2048), 1024, 1024), id_kmn, 1);
+            tc::umma_f16(tmem + TM_ACC0, dgd + (k16 >> 2) * (TILE >> 4) + 2 * (k16 & 3),
+                         (k16 < 8 ? elomn + 128 * k16 : ehimn + 128 * (k16 - 8)), id_kmn, 1);
         } else {
-          const uint32_t dgb = tc::smem_u32(smem + Lay<MODE_DE>::DG);
+          const uint64_t dgd = tc::make_sdesc(tc::smem_u32(smem + Lay<MODE_DE>::DG), TILE, 1024);
 #pragma unroll
           for (int k16 = 0; k16 < TT / 16; ++k16) {       // dG_blk^T . Q (contraction over the query rows)
-            const uint64_t qd = tc::make_sdesc(qb + k16 * 2048, 1024, 1024);
-            tc::umma_f16(tmem + TM_ACC0, tc::make_sdesc(dgb + k16 * 2048, TILE, 1024), qd, id_mnmn, (n | k16) != 0);
-            tc::umma_f16(tmem + TM_ACC1, tc::make_sdesc(dgb + 2 * TILE + k16 * 2048, TILE, 1024), qd, id_mnmn,
-                         (n | k16) != 0);
+            tc::umma_f16(tmem + TM_ACC0, dgd + 128 * k16, qmn + 128 * k16, id_mnmn, (n | k16) != 0);
+            tc::umma_f16(tmem + TM_ACC1, dgd + 2 * (TILE >> 4) + 128 * k16, qmn + 128 * k16, id_mnmn, (n | k16) != 0);
           }
         }
         if (MODE == MODE_DE) tc::umma_commit(&q_empty[n & 1]);
@@ -333,7 +337,6 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (!tc::named_bar_red_or(1, SM_THREADS, mine)) pad = nullptr;
     }
     const int base_w = ((127 - a) >> 1) + 32 * wg;   // first 32-bit word of this thread's band run in dG
-    const bool odd = (a & 1) != 0;
 
     for (int n = 0; n < nsteps; ++n) {
       const StepInfo s = step_info<MODE>(p, n, bh0);
@@ -420,18 +423,7 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           *reinterpret_cast<uint4*>(dstile + swz_chunk(a, c)) = make_uint4(A[4 * c], A[4 * c + 1], A[4 * c + 2], A[4 * c + 3]);
       }
       if (MODE != MODE_DKV) {           // band dG: this thread's 64 values start at band column 127-a+64*wg
-        auto word_ptr = [&](int wd) -> uint8_t* { return dg_base + (wd >> 5) * TILE + swz_word(a, wd & 31); };
-        if (odd) {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) *reinterpret_cast<uint32_t*>(word_ptr(base_w + k)) = A[k];
-        } else {
-          // run starts at an odd column: first / last element share a word with the neighbour run
-          *reinterpret_cast<uint16_t*>(word_ptr(base_w) + 2) = (uint16_t)(A[0] & 0xffffu);
-#pragma unroll
-          for (int k = 1; k < 32; ++k)
-            *reinterpret_cast<uint32_t*>(word_ptr(base_w + k)) = __byte_perm(A[k - 1], A[k], 0x5432);
-          *reinterpret_cast<uint16_t*>(word_ptr(base_w + 32)) = (uint16_t)(A[31] >> 16);
-        }
+        band_store(dg_base, a, base_w, A);
       }
       tc::fence_proxy_async();
       tc::tc_fence_before();
@@ -499,6 +491,11 @@ int launch_mode(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMa
 
 }  // namespace
 
+int rga_bwd2_dkv(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                 const CUtensorMap& tmDO, const CUtensorMap& tmE, cudaStream_t st);      // rga_tc_bwd2.cu
+int rga_bwd2_de(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                const CUtensorMap& tmDO, const CUtensorMap& tmE, cudaStream_t st);
+
 bool rga_bwd_tc_supported(const RgaArgs& a, int dh, int dtype) {
   if (dh != DHC || dtype != MT_BF16 || !a.causal) return false;
   if (a.sl % 8 || a.sh % 8 || a.sb % 8 || a.ol % 8 || a.oh % 8 || a.ob % 8) return false;
@@ -526,17 +523,10 @@ int rga_bwd_tc(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
   p.scale_log2 = LOG2E / a.inv_scale_div;
   p.bh_per_cta = 1;
   dim3 grid(a.h, a.B, p.nT);
-  if ((rc = launch_mode<MODE_DKV>(tmQ, tmK, tmV, tmDO, tmE, p, grid, st))) return rc;
+  // dK/dV and dE: second-generation two-group pipeline (rga_tc_bwd2.cu); dQ: the role kernel above
+  if ((rc = rga_bwd2_dkv(a, tmQ, tmK, tmV, tmDO, tmE, st))) return rc;
   if ((rc = launch_mode<MODE_DQ>(tmQ, tmK, tmV, tmDO, tmE, p, grid, st))) return rc;
-  // dE: one CTA per (tile diagonal, slice of (b,h)); about two CTAs per SM's worth of slices
-  const int bh = a.B * a.h;
-  int slices = (2 * sm_count() + p.nT - 1) / p.nT;
-  if (slices > bh) slices = bh;
-  if (slices < 1) slices = 1;
-  p.bh_per_cta = (bh + slices - 1) / slices;
-  slices = (bh + p.bh_per_cta - 1) / p.bh_per_cta;
-  dim3 grid_e(slices, 1, p.nT);
-  return launch_mode<MODE_DE>(tmQ, tmK, tmV, tmDO, tmE, p, grid_e, st);
+  return rga_bwd2_de(a, tmQ, tmK, tmV, tmDO, tmE, st);
 }
 
 }  // namespace mt

@@ -1,0 +1,623 @@
+// Backward of the fused relative global attention, second generation: the dK/dV role and the dE
+// role as a two-group software pipeline (K2).  Math as in rga_tc_bwd.cu:
+//     P = exp(S - lse),  S = (Q K^T + skew(Q E_band^T)) / sqrt(dh)
+//     dP = dO V^T ;  dS = P o (dP - D) / sqrt(dh) ;  dV = P^T dO ;  dK = dS^T Q ;  dE_band = dG^T Q
+// with dG = dS in band coordinates (dG[a][127-a+b] = dS[a][b]).
+//
+// What changed against the first generation: the 8 math warps did everything of a step in lock
+// step (skew -> exp -> dS), so the LSU phase, the MUFU phase and the FMA phase of all warps
+// coincided and every tensor-core phase was exposed.  Here the work of a step is split by FUNCTION:
+//   * group A (warps 0-7)  : S + skew -> P = exp(S - lse) -> P (bf16, swizzled) to shared memory;
+//   * group B (warps 8-15) : dP out of TMEM, P out of shared memory -> dS (and dG) operands;
+//   * warp 16 TMA producer, warp 17 MMA issuer.
+// A works on step n+1 while B works on step n, so the shared-memory/MUFU-heavy half and the
+// FMA/TMEM-heavy half of the math overlap, and the MMAs of step n+1 (S, G_lo, G_hi) are issued as
+// soon as A has read S/G of step n and B has read dP of step n (dP reuses the S columns).
+// Row a = 32*(w&3)+lane, key columns 64*((w>>2)&1)..+63 for both groups.
+#include "ops.cuh"
+#include "rga_tc_common.cuh"
+
+#include <stdlib.h>
+
+namespace mt {
+
+using namespace rga;
+
+namespace {
+
+enum { R_DKV = 0, R_DE = 2 };
+
+constexpr int B2_GROUP = 256;                       // threads of one math group
+constexpr int B2_THREADS = 2 * B2_GROUP + 64;       // A, B, TMA warp, MMA warp
+constexpr int SCRB_WORDS = 34;                      // skew scratch pitch (8-byte stores conflict-free)
+constexpr int B2_SCR_BYTES = B2_GROUP * SCRB_WORDS * 4;
+
+// TMEM columns: dP reuses the S columns once group A has read S
+constexpr uint32_t TM_S = 0, TM_GLO = 128, TM_GHI = 256, TM_ACC0 = 384, TM_ACC1 = 448;
+
+template <int ROLE> struct Lay2;
+template <> struct Lay2<R_DKV> {     // K,V resident; stage = {Q, dO, E_lo} x 2 (E_hi of a step = E_lo of the previous one)
+  static constexpr int K = 0, V = TILE, ST0 = 2 * TILE, ST_BYTES = 3 * TILE;
+  static constexpr int sQ = 0, sDO = TILE, sE = 2 * TILE;
+  static constexpr int P = ST0 + 2 * ST_BYTES, DS = P + 2 * TILE, SCR = DS + 2 * TILE, BAR = SCR + B2_SCR_BYTES;
+};
+template <> struct Lay2<R_DE> {      // E_lo,E_hi resident; Q x 2; K; {dO, V} (doubles as the P hand-off); dG
+  static constexpr int ELO = 0, EHI = TILE, Q0 = 2 * TILE, K = 4 * TILE, DOV = 5 * TILE, DG = 7 * TILE;
+  static constexpr int SCR = 11 * TILE, BAR = SCR + B2_SCR_BYTES;
+};
+template <int ROLE> constexpr int smem2_bytes() { return Lay2<ROLE>::BAR + 512; }
+static_assert(smem2_bytes<R_DKV>() <= 232448 && smem2_bytes<R_DE>() <= 232448, "shared memory budget");
+
+// barrier slots (uint64 each)
+enum { BR_RES = 0, BR_QF = 1, BR_QE = 3, BR_KF = 5, BR_KE = 6, BR_VF = 7, BR_SFULL = 8, BR_SGFREE = 9,
+       BR_DPFULL = 10, BR_DPFREE = 11, BR_PREADY = 12, BR_DSREADY = 13, BR_STEPDONE = 14, BR_TMEM = 15, BR_SPAD = 16 };
+
+struct Bwd2Params {
+  void* dk; void* dv;                    // 16-bit, k/v addressing
+  int64_t sb, sl, sh;
+  float* dE;
+  const float* lse; const float* delta;
+  const uint8_t* pad;
+  int B, h, L, max_seq, nT;
+  int bh_per_cta;                        // DE role
+  float scale, scale_log2;
+  long long* trace;                      // MT_RGA_TRACE=1: clock64 stamps of CTA (0,0,0), [4 agents][32 steps][8 events]
+};
+
+// pipeline timeline of one CTA (debug aid, off unless the launcher passes a buffer)
+#define TRACE(agent, n, ev)                                                                         \
+  do {                                                                                              \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (n) < 32)               \
+      p.trace[((agent) * 32 + (n)) * 8 + (ev)] = clock64();                                         \
+  } while (0)
+
+struct Step2 { int it, jt, b, hh; };
+
+template <int ROLE>
+__device__ __forceinline__ int num_steps2(const Bwd2Params& p, int& bh0) {
+  // grid = (h, B, nT) [DKV] or (slices, 1, nT) [DE]: the tile / diagonal index is the SLOWEST grid
+  // dimension, so CTAs are dispatched longest-first over the whole launch
+  bh0 = 0;
+  if (ROLE == R_DKV) return p.nT - (int)blockIdx.z;
+  bh0 = (int)blockIdx.x * p.bh_per_cta;
+  int nbh = min(p.bh_per_cta, p.B * p.h - bh0);
+  return nbh > 0 ? nbh * (p.nT - (int)blockIdx.z) : 0;
+}
+template <int ROLE>
+__device__ __forceinline__ Step2 step2(const Bwd2Params& p, int n, int bh0) {
+  Step2 s;
+  if (ROLE == R_DKV) { s.jt = blockIdx.z; s.it = s.jt + n; s.hh = blockIdx.x; s.b = blockIdx.y; }
+  else {
+    const int per = p.nT - (int)blockIdx.z;
+    const int bh = bh0 + n / per, k = n % per;
+    s.it = (int)blockIdx.z + k; s.jt = k; s.b = bh / p.h; s.hh = bh % p.h;
+  }
+  return s;
+}
+
+// 64-column band window [w0, w0+64) of this warp's 32 rows -> private scratch as 32 f16 pairs
+// (pitch SCRB_WORDS: 8-byte stores)
+__device__ __forceinline__ void park64_st64(uint32_t g_lo, uint32_t g_hi, uint32_t lane_base, int w0, uint32_t* scr) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t r[32];
+    const int cc = w0 + 32 * c;
+    tc::tmem_ld_32x32((cc < 128 ? g_lo + cc : g_hi + (cc - 128)) + lane_base, r);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int x = 0; x < 32; x += 4)
+      *reinterpret_cast<uint2*>(scr + 16 * c + x / 2) =
+          make_uint2(pack_f16x2(__uint_as_float(r[x]), __uint_as_float(r[x + 1])),
+                     pack_f16x2(__uint_as_float(r[x + 2]), __uint_as_float(r[x + 3])));
+  }
+}
+
+__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+template <int ROLE>
+__global__ void __launch_bounds__(B2_THREADS, 1)
+rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                const __grid_constant__ CUtensorMap tmE, const Bwd2Params p) {
+  using LY = Lay2<ROLE>;
+  extern __shared__ __align__(1024) uint8_t smem[];      // shared address space kept: LDS/STS, not generic
+  if ((tc::smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LY::BAR);
+  uint64_t* bar_res = bars + BR_RES;
+  uint64_t* q_full = bars + BR_QF;        // [2]  DKV: stage {Q,dO,E_lo};  DE: Q ring
+  uint64_t* q_empty = bars + BR_QE;       // [2]
+  uint64_t* k_full = bars + BR_KF;        // DE: K
+  uint64_t* k_empty = bars + BR_KE;
+  uint64_t* v_full = bars + BR_VF;        // DE: {dO, V}
+  uint64_t* s_full = bars + BR_SFULL;     // MMA -> A : S, G_lo, G_hi of the step
+  uint64_t* sg_free = bars + BR_SGFREE;   // A -> MMA : S and G read
+  uint64_t* dp_full = bars + BR_DPFULL;   // MMA -> B (and A in the DE role)
+  uint64_t* dp_free = bars + BR_DPFREE;   // B -> MMA : dP read (the S columns may be overwritten)
+  uint64_t* p_ready = bars + BR_PREADY;   // A -> B (and MMA) : P stored
+  uint64_t* ds_ready = bars + BR_DSREADY; // B -> MMA (and TMA in the DE role)
+  uint64_t* step_done = bars + BR_STEPDONE;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BR_TMEM);
+  uint8_t* spad = reinterpret_cast<uint8_t*>(bars + BR_SPAD);      // [128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int bh0;
+  const int nsteps = num_steps2<ROLE>(p, bh0);
+
+  if (warp == 16 && lane == 0) {
+    tc::tma_prefetch_desc(&tmQ); tc::tma_prefetch_desc(&tmK); tc::tma_prefetch_desc(&tmV);
+    tc::tma_prefetch_desc(&tmDO); tc::tma_prefetch_desc(&tmE);
+    tc::mbar_init(bar_res, 1);
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&q_full[s], 1); tc::mbar_init(&q_empty[s], 1); }
+    tc::mbar_init(k_full, 1); tc::mbar_init(k_empty, 1); tc::mbar_init(v_full, 1);
+    tc::mbar_init(s_full, 1);
+    tc::mbar_init(sg_free, B2_GROUP);
+    tc::mbar_init(dp_full, 1);
+    tc::mbar_init(dp_free, B2_GROUP);
+    tc::mbar_init(p_ready, B2_GROUP);
+    tc::mbar_init(ds_ready, B2_GROUP);
+    tc::mbar_init(step_done, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 17) tc::tmem_alloc(tmem_slot, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (nsteps <= 0) {            // (DE role: empty slice) -- uniform for the whole CTA
+    __syncthreads();
+    if (warp == 17) tc::tmem_dealloc(tmem, 512);
+    return;
+  }
+
+  // buffers of step n
+  auto buf_q = [&](int n) -> uint8_t* {
+    if (ROLE == R_DKV) return smem + Lay2<R_DKV>::ST0 + (n & 1) * Lay2<R_DKV>::ST_BYTES + Lay2<R_DKV>::sQ;
+    return smem + Lay2<R_DE>::Q0 + (n & 1) * TILE;
+  };
+  auto buf_do = [&](int n) -> uint8_t* {
+    if (ROLE == R_DKV) return smem + Lay2<R_DKV>::ST0 + (n & 1) * Lay2<R_DKV>::ST_BYTES + Lay2<R_DKV>::sDO;
+    return smem + Lay2<R_DE>::DOV;
+  };
+  auto buf_k = [&]() -> uint8_t* { return smem + (ROLE == R_DKV ? Lay2<R_DKV>::K : Lay2<R_DE>::K); };
+  auto buf_v = [&]() -> uint8_t* { return smem + (ROLE == R_DKV ? Lay2<R_DKV>::V : Lay2<R_DE>::DOV + TILE); };
+  auto buf_elo = [&](int n) -> uint8_t* {
+    if (ROLE == R_DKV) return smem + Lay2<R_DKV>::ST0 + (n & 1) * Lay2<R_DKV>::ST_BYTES + Lay2<R_DKV>::sE;
+    return smem + Lay2<R_DE>::ELO;
+  };
+  auto buf_ehi = [&](int n) -> uint8_t* {       // DKV: the E_lo block of the previous step
+    if (ROLE == R_DKV) return smem + Lay2<R_DKV>::ST0 + ((n + 1) & 1) * Lay2<R_DKV>::ST_BYTES + Lay2<R_DKV>::sE;
+    return smem + Lay2<R_DE>::EHI;
+  };
+  // P hand-off A -> B: the P operand buffer (DKV) or the {dO, V} tiles, dead once dP is computed (DE)
+  uint8_t* const pbuf = smem + (ROLE == R_DKV ? Lay2<R_DKV>::P : Lay2<R_DE>::DOV);
+
+  if (warp == 16) {
+    // ================================ TMA producer ==========================================
+    if (lane == 0) {
+      if (ROLE == R_DKV) {
+        const Step2 s0 = step2<ROLE>(p, 0, bh0);
+        tc::mbar_arrive_expect_tx(bar_res, 2 * TILE);
+        tc::tma_load_4d(buf_k(), &tmK, bar_res, 0, s0.hh, s0.jt * TT, s0.b);
+        tc::tma_load_4d(buf_v(), &tmV, bar_res, 0, s0.hh, s0.jt * TT, s0.b);
+        for (int n = 0; n < nsteps; ++n) {
+          const Step2 s = step2<ROLE>(p, n, bh0);
+          const int st = n & 1;
+          const int c0 = p.max_seq - 1 - (s.it - s.jt) * TT;
+          tc::mbar_wait(&q_empty[st], ((n >> 1) & 1) ^ 1);
+          if (n == 1) tc::mbar_wait(s_full, 0);     // stage 1's E slot held E_hi of step 0 until G(0) was computed
+          tc::mbar_arrive_expect_tx(&q_full[st], (n == 0 ? 4 : 3) * TILE);
+          tc::tma_load_4d(buf_q(n), &tmQ, &q_full[st], 0, s.hh, s.it * TT, s.b);
+          tc::tma_load_2d(buf_elo(n), &tmE, &q_full[st], 0, c0 - (TT - 1));
+          if (n == 0) tc::tma_load_2d(buf_ehi(0), &tmE, &q_full[st], 0, c0 + 1);
+          tc::tma_load_4d(buf_do(n), &tmDO, &q_full[st], 0, s.hh, s.it * TT, s.b);
+          if (n + 2 < nsteps) {       // pull the tiles of step n+2 into L2
+            tc::tma_prefetch_4d(&tmQ, 0, s.hh, (s.it + 2) * TT, s.b);
+            tc::tma_prefetch_4d(&tmDO, 0, s.hh, (s.it + 2) * TT, s.b);
+          }
+        }
+      } else {
+        const int c0 = p.max_seq - 1 - (int)blockIdx.z * TT;
+        tc::mbar_arrive_expect_tx(bar_res, 2 * TILE);
+        tc::tma_load_2d(smem + Lay2<R_DE>::ELO, &tmE, bar_res, 0, c0 - (TT - 1));
+        tc::tma_load_2d(smem + Lay2<R_DE>::EHI, &tmE, bar_res, 0, c0 + 1);
+        for (int n = 0; n < nsteps; ++n) {
+          const Step2 s = step2<ROLE>(p, n, bh0);
+          tc::mbar_wait(k_empty, (n & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(k_full, TILE);
+          tc::tma_load_4d(buf_k(), &tmK, k_full, 0, s.hh, s.jt * TT, s.b);
+          tc::mbar_wait(&q_empty[n & 1], ((n >> 1) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(&q_full[n & 1], TILE);
+          tc::tma_load_4d(buf_q(n), &tmQ, &q_full[n & 1], 0, s.hh, s.it * TT, s.b);
+          if (n + 1 < nsteps) {       // pull the next step's tiles into L2 while waiting for the hand-off buffer
+            const Step2 t = step2<ROLE>(p, n + 1, bh0);
+            tc::tma_prefetch_4d(&tmK, 0, t.hh, t.jt * TT, t.b);
+            tc::tma_prefetch_4d(&tmQ, 0, t.hh, t.it * TT, t.b);
+            tc::tma_prefetch_4d(&tmDO, 0, t.hh, t.it * TT, t.b);
+            tc::tma_prefetch_4d(&tmV, 0, t.hh, t.jt * TT, t.b);
+          }
+          // {dO, V} region: group B must have finished reading P of the previous step out of it
+          if (n > 0) tc::mbar_wait(ds_ready, (n - 1) & 1);
+          tc::mbar_arrive_expect_tx(v_full, 2 * TILE);
+          tc::tma_load_4d(buf_do(n), &tmDO, v_full, 0, s.hh, s.it * TT, s.b);
+          tc::tma_load_4d(buf_v(), &tmV, v_full, 0, s.hh, s.jt * TT, s.b);
+        }
+      }
+    }
+  } else if (warp == 17) {
+    // ================================ MMA issuer ============================================
+    if (lane == 0) {
+      const uint32_t id_kk = tc::make_idesc(TT, TT, 1, 1, 0, 0);      // S, G, dP : K-major x K-major, N = 128
+      const uint32_t id_mnmn = tc::make_idesc(TT, DHC, 1, 1, 1, 1);   // dK/dV/dE: A MN-major, B MN-major, N = 64
+      // Shared-memory descriptors are built once; inside the loops a k-step is an add on the address
+      // field (16-byte units): +2 per 16 elements of a K-major operand, +128 per 16 rows of an MN-major one.
+      // (Building them per MMA cost the issuing thread ~100 cycles per instruction.)
+      const uint64_t kd = tc::make_sdesc(tc::smem_u32(buf_k()), 16, 1024);
+      const uint64_t vd = tc::make_sdesc(tc::smem_u32(buf_v()), 16, 1024);
+      // stage st of a double-buffered tile = stage 0 + st * stride (no indexed descriptor arrays:
+      // they would live in local memory)
+      constexpr uint64_t QSTR = (ROLE == R_DKV ? Lay2<R_DKV>::ST_BYTES : TILE) >> 4;          // Q: both roles x2
+      constexpr uint64_t SSTR = (ROLE == R_DKV ? Lay2<R_DKV>::ST_BYTES : 0) >> 4;             // dO, E_lo: DKV only
+      const uint64_t qd_k0 = tc::make_sdesc(tc::smem_u32(buf_q(0)), 16, 1024);
+      const uint64_t qd_mn0 = tc::make_sdesc(tc::smem_u32(buf_q(0)), 1024, 1024);
+      const uint64_t dod_k0 = tc::make_sdesc(tc::smem_u32(buf_do(0)), 16, 1024);
+      const uint64_t dod_mn0 = tc::make_sdesc(tc::smem_u32(buf_do(0)), 1024, 1024);
+      const uint64_t elod0 = tc::make_sdesc(tc::smem_u32(buf_elo(0)), 16, 1024);
+      const uint64_t ehid_de = tc::make_sdesc(tc::smem_u32(smem + Lay2<R_DE>::EHI), 16, 1024);
+      const uint64_t opd0 = tc::make_sdesc(tc::smem_u32(smem + (ROLE == R_DKV ? Lay2<R_DKV>::P : Lay2<R_DE>::DG)), TILE, 1024);
+      const uint64_t opd1 = tc::make_sdesc(tc::smem_u32(smem + (ROLE == R_DKV ? Lay2<R_DKV>::DS : Lay2<R_DE>::DG + 2 * TILE)), TILE, 1024);
+      auto issue_g = [&](int n) {
+        const uint64_t st = n & 1;
+        const uint64_t qd = qd_k0 + st * QSTR, lo = elod0 + st * SSTR;
+        const uint64_t hi = (ROLE == R_DKV) ? elod0 + (st ^ 1) * SSTR : ehid_de;      // DKV: E_lo of the previous step
+#pragma unroll
+        for (int k4 = 0; k4 < DHC / 16; ++k4) {
+          tc::umma_f16(tmem + TM_GLO, qd + 2 * k4, lo + 2 * k4, id_kk, k4 != 0);
+          tc::umma_f16(tmem + TM_GHI, qd + 2 * k4, hi + 2 * k4, id_kk, k4 != 0);
+        }
+      };
+      auto issue_s = [&](int n) {
+        const uint64_t qd = qd_k0 + (uint64_t)(n & 1) * QSTR;
+#pragma unroll
+        for (int k4 = 0; k4 < DHC / 16; ++k4)
+          tc::umma_f16(tmem + TM_S, qd + 2 * k4, kd + 2 * k4, id_kk, k4 != 0);
+        tc::umma_commit(s_full);
+        if (ROLE == R_DE) tc::umma_commit(k_empty);
+      };
+      tc::mbar_wait(bar_res, 0);
+      tc::mbar_wait(&q_full[0], 0);
+      if (ROLE == R_DE) tc::mbar_wait(k_full, 0);
+      tc::tc_fence_after();
+      issue_g(0);
+      issue_s(0);
+      for (int n = 0; n < nsteps; ++n) {
+        const uint32_t par = n & 1;
+        const uint64_t st = n & 1;
+        const uint64_t dod_k = dod_k0 + st * SSTR, dod_mn = dod_mn0 + st * SSTR, qd_mn = qd_mn0 + st * QSTR;
+        // ---- dP = dO V^T into the S columns (group A has read S and G)
+        tc::mbar_wait(sg_free, par);
+        TRACE(3, n, 0);
+        if (ROLE == R_DE) tc::mbar_wait(v_full, par);
+        tc::tc_fence_after();
+        TRACE(3, n, 1);
+#pragma unroll
+        for (int k4 = 0; k4 < DHC / 16; ++k4)
+          tc::umma_f16(tmem + TM_S, dod_k + 2 * k4, vd + 2 * k4, id_kk, k4 != 0);
+        tc::umma_commit(dp_full);
+        // ---- next step's G (needs only the G columns), then its S once group B has read dP
+        if (n + 1 < nsteps) {
+          tc::mbar_wait(&q_full[(n + 1) & 1], ((n + 1) >> 1) & 1);
+          tc::tc_fence_after();
+          TRACE(3, n, 2);
+          issue_g(n + 1);
+          if (ROLE == R_DE) tc::mbar_wait(k_full, (n + 1) & 1);
+          TRACE(3, n, 3);
+          tc::mbar_wait(dp_free, par);
+          tc::tc_fence_after();
+          TRACE(3, n, 4);
+          issue_s(n + 1);
+        }
+        // ---- role MMAs on the operands written by the math groups
+        tc::mbar_wait(p_ready, par);
+        TRACE(3, n, 5);
+        tc::mbar_wait(ds_ready, par);
+        tc::tc_fence_after();
+        TRACE(3, n, 6);
+        if (ROLE == R_DKV) {
+#pragma unroll
+          for (int k16 = 0; k16 < TT / 16; ++k16) {      // contraction over the 128 query rows
+            tc::umma_f16(tmem + TM_ACC1, opd0 + 128 * k16, dod_mn + 128 * k16, id_mnmn, (n | k16) != 0);   // dV += P^T dO
+            tc::umma_f16(tmem + TM_ACC0, opd1 + 128 * k16, qd_mn + 128 * k16, id_mnmn, (n | k16) != 0);    // dK += dS^T Q
+          }
+        } else {
+#pragma unroll
+          for (int k16 = 0; k16 < TT / 16; ++k16) {       // dG_blk^T . Q (contraction over the query rows)
+            tc::umma_f16(tmem + TM_ACC0, opd0 + 128 * k16, qd_mn + 128 * k16, id_mnmn, (n | k16) != 0);
+            tc::umma_f16(tmem + TM_ACC1, opd1 + 128 * k16, qd_mn + 128 * k16, id_mnmn, (n | k16) != 0);
+          }
+        }
+        tc::umma_commit(&q_empty[n & 1]);
+        tc::umma_commit(step_done);
+      }
+    }
+  } else {
+    const bool grpA = warp < 8;
+    const int w4 = warp & 3, half = (warp >> 2) & 1;
+    const int a = w4 * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(w4 * 32) << 16;
+
+    if (grpA) {
+      // ================================ group A: S + skew -> P ================================
+      uint32_t* scr = reinterpret_cast<uint32_t*>(smem + LY::SCR) + threadIdx.x * SCRB_WORDS;
+      // training batches carry no pad tokens: decide once per CTA whether any key of the sequences
+      // this CTA touches is padded; if none is, the unmasked fast path is used for every step
+      const uint8_t* pad = p.pad;
+      if (pad) {
+        const Step2 sf = step2<ROLE>(p, 0, bh0), sl = step2<ROLE>(p, nsteps - 1, bh0);
+        bool mine = false;
+        for (int64_t x = (int64_t)sf.b * p.L + threadIdx.x; x < (int64_t)(sl.b + 1) * p.L; x += B2_GROUP)
+          mine |= (pad[x] != 0);
+        if (!tc::named_bar_red_or(1, B2_GROUP, mine)) pad = nullptr;
+      }
+      // the per-row statistic of step n+1 is fetched during step n (a global load in the step's
+      // dependency chain cost ~600 cycles per step)
+      auto row_stat = [&](const float* src, int n) -> float {
+        const Step2 t = step2<ROLE>(p, n, bh0);
+        const int i = t.it * TT + a;
+        return i < p.L ? src[((int64_t)t.b * p.h + t.hh) * p.L + i] : 0.f;
+      };
+      float lse_next = row_stat(p.lse, 0);
+      for (int n = 0; n < nsteps; ++n) {
+        const Step2 s = step2<ROLE>(p, n, bh0);
+        const uint32_t par = n & 1;
+        const int i0 = s.it * TT, j0 = s.jt * TT;
+        const int i = i0 + a;
+        const bool row_ok = i < p.L;
+        const float lse2 = lse_next * LOG2E;
+        if (n + 1 < nsteps) lse_next = row_stat(p.lse, n + 1);
+        if (pad) {
+          tc::named_bar_sync(1, B2_GROUP);
+          if (half == 0) spad[a] = (j0 + a < p.L) ? pad[(int64_t)s.b * p.L + j0 + a] : 1;
+          tc::named_bar_sync(1, B2_GROUP);
+        }
+        const bool diag = (i0 == j0);
+        const bool need_mask = diag || (j0 + TT > p.L) || (i0 + TT > p.L) || pad != nullptr;
+
+        if (threadIdx.x == 0) TRACE(0, n, 0);
+        tc::mbar_wait(s_full, par);
+        tc::tc_fence_after();
+        if (threadIdx.x == 0) TRACE(0, n, 1);
+        uint32_t pk[32];
+#pragma unroll
+        for (int ps = 0; ps < 2; ++ps) {
+          const int cfirst = 64 * half + 32 * ps;
+          park64_st64(tmem + TM_GLO, tmem + TM_GHI, lane_base, 96 - 32 * w4 + cfirst, scr);
+          float sv[32];
+          {
+            uint32_t r[32];
+            tc::tmem_ld_32x32(tmem + TM_S + lane_base + cfirst, r);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int x = 0; x < 32; ++x) sv[x] = __uint_as_float(r[x]);
+          }
+          if (ps == 1) {        // S and both G blocks are in registers / scratch: release the TMEM columns
+            tc::tc_fence_before();
+            tc::mbar_arrive(sg_free);
+            if (threadIdx.x == 0) TRACE(0, n, 2);
+          }
+          skew_fetch_add_32(sv, scr, lane);
+          // P = exp(S - lse) with the reference's mask (causal on the diagonal tile, key padding, tails)
+#pragma unroll
+          for (int x = 0; x < 32; ++x) sv[x] = tc::fast_exp2(fmaf(sv[x], p.scale_log2, -lse2));
+          if (need_mask) {
+#pragma unroll
+            for (int x = 0; x < 32; ++x) {
+              const int bcol = cfirst + x;
+              bool ok = row_ok;
+              if (diag) ok = ok && (bcol <= a);
+              ok = ok && (j0 + bcol < p.L);
+              if (pad) ok = ok && (spad[bcol] == 0);
+              if (!ok) sv[x] = 0.f;
+            }
+          }
+#pragma unroll
+          for (int x = 0; x < 16; ++x) pk[16 * ps + x] = pack_bf16x2(sv[2 * x], sv[2 * x + 1]);
+        }
+        // the hand-off buffer must be free: DKV -- dV MMA of the previous step has read P;
+        // DE -- dP of THIS step has consumed the {dO, V} tiles it aliases
+        if (threadIdx.x == 0) TRACE(0, n, 3);
+        if (ROLE == R_DKV) { if (n > 0) tc::mbar_wait(step_done, (n - 1) & 1); }
+        else tc::mbar_wait(dp_full, par);
+        if (threadIdx.x == 0) TRACE(0, n, 4);
+        uint8_t* ptile = pbuf + half * TILE;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(ptile + swz_chunk(a, c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        tc::fence_proxy_async();
+        tc::mbar_arrive(p_ready);
+        if (threadIdx.x == 0) TRACE(0, n, 5);
+      }
+    } else {
+      // ================================ group B: dP, P -> dS / dG =============================
+      uint8_t* const dg_base = smem + Lay2<R_DE>::DG;
+      if (ROLE == R_DE) {
+        // dG is zero outside the 128 band columns each row owns; those positions never change
+        uint4* z = reinterpret_cast<uint4*>(dg_base);
+        for (int x = threadIdx.x - B2_GROUP; x < 4 * TILE / 16; x += B2_GROUP) z[x] = make_uint4(0, 0, 0, 0);
+        tc::fence_proxy_async();
+        tc::named_bar_sync(2, B2_GROUP);
+      }
+      const int base_w = ((127 - a) >> 1) + 32 * half;   // first 32-bit word of this thread's band run in dG
+      auto row_stat = [&](const float* src, int n) -> float {
+        const Step2 t = step2<ROLE>(p, n, bh0);
+        const int i = t.it * TT + a;
+        return i < p.L ? src[((int64_t)t.b * p.h + t.hh) * p.L + i] : 0.f;
+      };
+      float d_next = row_stat(p.delta, 0);
+      for (int n = 0; n < nsteps; ++n) {
+        const uint32_t par = n & 1;
+        const float Ds = d_next * p.scale;
+        if (n + 1 < nsteps) d_next = row_stat(p.delta, n + 1);
+        if (threadIdx.x == B2_GROUP) TRACE(1, n, 0);
+        tc::mbar_wait(dp_full, par);
+        tc::tc_fence_after();
+        if (threadIdx.x == B2_GROUP) TRACE(1, n, 1);
+        uint32_t dp[64];
+        {
+          uint32_t r0[32], r1[32];
+          tc::tmem_ld_32x32(tmem + TM_S + lane_base + half * 64, r0);
+          tc::tmem_ld_32x32(tmem + TM_S + lane_base + half * 64 + 32, r1);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int x = 0; x < 32; ++x) { dp[x] = r0[x]; dp[32 + x] = r1[x]; }
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive(dp_free);
+        if (threadIdx.x == B2_GROUP) TRACE(1, n, 2);
+        tc::mbar_wait(p_ready, par);
+        if (threadIdx.x == B2_GROUP) TRACE(1, n, 3);
+        // dS = P o (dP - D) / sqrt(dh)
+        uint32_t A[32];
+        const uint8_t* ptile = pbuf + half * TILE;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 pw = *reinterpret_cast<const uint4*>(ptile + swz_chunk(a, c));
+          const uint32_t w[4] = {pw.x, pw.y, pw.z, pw.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float d0 = fmaf(__uint_as_float(dp[8 * c + 2 * e]), p.scale, -Ds) * bf16lo(w[e]);
+            const float d1 = fmaf(__uint_as_float(dp[8 * c + 2 * e + 1]), p.scale, -Ds) * bf16hi(w[e]);
+            A[4 * c + e] = pack_bf16x2(d0, d1);
+          }
+        }
+        if (ROLE == R_DKV) {            // rectangular dS: sub-tile `half` of row a
+          uint8_t* dstile = smem + Lay2<R_DKV>::DS + half * TILE;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(dstile + swz_chunk(a, c)) = make_uint4(A[4 * c], A[4 * c + 1], A[4 * c + 2], A[4 * c + 3]);
+        } else {                        // band dG: this thread's 64 values start at band column 127-a+64*half
+          if (threadIdx.x == B2_GROUP) TRACE(1, n, 4);
+          if (n > 0) tc::mbar_wait(step_done, (n - 1) & 1);      // the previous step's dE MMAs have read dG
+          if (threadIdx.x == B2_GROUP) TRACE(1, n, 5);
+          band_store(dg_base, a, base_w, A);
+        }
+        tc::fence_proxy_async();
+        tc::mbar_arrive(ds_ready);
+        if (threadIdx.x == B2_GROUP) TRACE(1, n, 6);
+      }
+    }
+
+    // ---- epilogue: accumulators out of TMEM; group A takes ACC0, group B ACC1; each thread 32 of
+    // the 64 columns of its row
+    tc::mbar_wait(step_done, (nsteps - 1) & 1);
+    tc::tc_fence_after();
+    uint32_t r[32];
+    tc::tmem_ld_32x32(tmem + (grpA ? TM_ACC0 : TM_ACC1) + lane_base + half * 32, r);
+    tc::tmem_ld_wait();
+    if (ROLE == R_DE) {
+      const int c0 = p.max_seq - 1 - (int)blockIdx.z * TT;
+      const int erow = (grpA ? c0 - (TT - 1) : c0 + 1) + a;
+      if (erow >= 0 && erow < p.max_seq) {
+#pragma unroll
+        for (int x = 0; x < 32; ++x) atomicAdd(p.dE + (int64_t)erow * DHC + half * 32 + x, __uint_as_float(r[x]));
+      }
+    } else {
+      const Step2 s = step2<ROLE>(p, 0, bh0);
+      const int row = s.jt * TT + a;
+      uint32_t packed[16];
+#pragma unroll
+      for (int x = 0; x < 32; x += 2) packed[x / 2] = pack_bf16x2(__uint_as_float(r[x]), __uint_as_float(r[x + 1]));
+      if (row < p.L) {
+        void* base = grpA ? p.dk : p.dv;
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(base) + (int64_t)s.b * p.sb +
+                                              (int64_t)row * p.sl + (int64_t)s.hh * p.sh + half * 32);
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+          dst[x] = make_uint4(packed[4 * x], packed[4 * x + 1], packed[4 * x + 2], packed[4 * x + 3]);
+      }
+    }
+    tc::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 17) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem, 512);
+  }
+}
+
+template <int ROLE>
+int launch_role2(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmDO,
+                 const CUtensorMap& tmE, const Bwd2Params& p, dim3 grid, cudaStream_t st) {
+  auto kern = rga_bwd2_kernel<ROLE>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_bytes<ROLE>());
+    if (e != cudaSuccess) { set_error("rga_bwd2: smem attribute (%d B): %s", smem2_bytes<ROLE>(), cudaGetErrorString(e)); return (int)e; }
+    attr_done = true;
+  }
+  Bwd2Params q = p;
+  static const bool want_trace = getenv("MT_RGA_TRACE") != nullptr;
+  static long long* trace_dev = nullptr;
+  const size_t trace_n = 4 * 32 * 8;
+  if (want_trace) {
+    if (!trace_dev) cudaMalloc(&trace_dev, trace_n * sizeof(long long));
+    cudaMemsetAsync(trace_dev, 0, trace_n * sizeof(long long), st);
+    q.trace = trace_dev;
+  }
+  kern<<<grid, B2_THREADS, smem2_bytes<ROLE>(), st>>>(tmQ, tmK, tmV, tmDO, tmE, q);
+  if (want_trace) {
+    static long long host[4 * 32 * 8];
+    cudaMemcpyAsync(host, trace_dev, sizeof(host), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    long long t0 = 0;
+    for (size_t x = 0; x < trace_n; ++x) if (host[x] && (!t0 || host[x] < t0)) t0 = host[x];
+    static const char* agent[4] = {"A", "B", "-", "MMA"};
+    for (int ag = 0; ag < 4; ++ag)
+      for (int n = 0; n < 32; ++n) {
+        bool any = false;
+        for (int e = 0; e < 8; ++e) any |= host[(ag * 32 + n) * 8 + e] != 0;
+        if (!any) continue;
+        fprintf(stderr, "trace role %d %-3s step %2d:", ROLE, agent[ag], n);
+        for (int e = 0; e < 8; ++e) fprintf(stderr, " %8lld", host[(ag * 32 + n) * 8 + e] ? host[(ag * 32 + n) * 8 + e] - t0 : -1LL);
+        fprintf(stderr, "\n");
+      }
+  }
+  return check_launch("rga_bwd2");
+}
+
+Bwd2Params make_params2(const RgaArgs& a) {
+  Bwd2Params p;
+  p.dk = a.dk; p.dv = a.dv; p.sb = a.sb; p.sl = a.sl; p.sh = a.sh;
+  p.dE = a.dE; p.lse = a.lse; p.delta = a.delta; p.pad = a.pad;
+  p.B = a.B; p.h = a.h; p.L = a.L; p.max_seq = a.max_seq;
+  p.nT = (a.L + TT - 1) / TT;
+  p.scale = 1.f / a.inv_scale_div;
+  p.scale_log2 = LOG2E / a.inv_scale_div;
+  p.bh_per_cta = 1;
+  p.trace = nullptr;
+  return p;
+}
+
+}  // namespace
+
+// dK, dV (key-tile owner walks the query tiles at or below it)
+int rga_bwd2_dkv(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                 const CUtensorMap& tmDO, const CUtensorMap& tmE, cudaStream_t st) {
+  Bwd2Params p = make_params2(a);
+  return launch_role2<R_DKV>(tmQ, tmK, tmV, tmDO, tmE, p, dim3(a.h, a.B, p.nT), st);
+}
+
+// dE (tile-diagonal owner walks down the diagonal over a slice of (batch, head))
+int rga_bwd2_de(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                const CUtensorMap& tmDO, const CUtensorMap& tmE, cudaStream_t st) {
+  Bwd2Params p = make_params2(a);
+  const int bh = a.B * a.h;
+  int slices = (2 * sm_count() + p.nT - 1) / p.nT;       // about two CTAs per SM's worth of slices
+  if (slices > bh) slices = bh;
+  if (slices < 1) slices = 1;
+  p.bh_per_cta = (bh + slices - 1) / slices;
+  slices = (bh + p.bh_per_cta - 1) / p.bh_per_cta;
+  return launch_role2<R_DE>(tmQ, tmK, tmV, tmDO, tmE, p, dim3(slices, 1, p.nT), st);
+}
+
+}  // namespace mt

@@ -76,12 +76,94 @@ __device__ __forceinline__ void skew_add_64(float (&sv)[64], uint32_t g_lo, uint
   }
 }
 
+// ---- 32-column unit of the skew (used by the 16-warp forward and the P-producer warps of the
+// backward).  A thread owns row a = 32*w4 + lane and the 32 key columns [c_first, c_first+32) with
+// c_first a multiple of 32.  Its band columns are 127 - a + c_first + x = w0 + o + x with the
+// warp-uniform w0 = 96 - 32*w4 + c_first (a multiple of 32, so each 32-column TMEM load lies in
+// G_lo or in G_hi) and the per-lane o = 31 - lane.  skew_park_64 parks the 64-column window
+// [w0, w0+64) as 32 f16 pairs in the thread's private scratch (SCR32_WORDS apart: 16-byte stores
+// conflict-free); skew_fetch_32 reads it back at offset o (odd o = 16-bit funnel shift).
+constexpr int SCR32_WORDS = 36;
+__device__ __forceinline__ void skew_park_64(uint32_t g_lo, uint32_t g_hi, uint32_t lane_base, int w0,
+                                             uint32_t* scr) {
+  uint32_t r0[32], r1[32];
+  const int c0 = w0, c1 = w0 + 32;
+  tc::tmem_ld_32x32((c0 < 128 ? g_lo + c0 : g_hi + (c0 - 128)) + lane_base, r0);
+  tc::tmem_ld_32x32((c1 < 128 ? g_lo + c1 : g_hi + (c1 - 128)) + lane_base, r1);
+  tc::tmem_ld_wait();
+#pragma unroll
+  for (int x = 0; x < 32; x += 8)
+    *reinterpret_cast<uint4*>(scr + x / 2) =
+        make_uint4(pack_f16x2(__uint_as_float(r0[x]), __uint_as_float(r0[x + 1])),
+                   pack_f16x2(__uint_as_float(r0[x + 2]), __uint_as_float(r0[x + 3])),
+                   pack_f16x2(__uint_as_float(r0[x + 4]), __uint_as_float(r0[x + 5])),
+                   pack_f16x2(__uint_as_float(r0[x + 6]), __uint_as_float(r0[x + 7])));
+#pragma unroll
+  for (int x = 0; x < 32; x += 8)
+    *reinterpret_cast<uint4*>(scr + 16 + x / 2) =
+        make_uint4(pack_f16x2(__uint_as_float(r1[x]), __uint_as_float(r1[x + 1])),
+                   pack_f16x2(__uint_as_float(r1[x + 2]), __uint_as_float(r1[x + 3])),
+                   pack_f16x2(__uint_as_float(r1[x + 4]), __uint_as_float(r1[x + 5])),
+                   pack_f16x2(__uint_as_float(r1[x + 6]), __uint_as_float(r1[x + 7])));
+}
+// sv[x] += window[o + x], x in [0, 32)
+__device__ __forceinline__ void skew_fetch_add_32(float (&sv)[32], const uint32_t* scr, int lane) {
+  const int o = 31 - lane;
+  const uint32_t sh = (uint32_t)(o & 1) * 16u;
+  const uint32_t* rd = scr + (o >> 1);
+  uint32_t w[17];
+#pragma unroll
+  for (int k = 0; k < 17; ++k) w[k] = rd[k];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    uint32_t u = __funnelshift_r(w[k], w[k + 1], sh);
+    float2 f = __half22float2(*reinterpret_cast<__half2*>(&u));
+    sv[2 * k] += f.x;
+    sv[2 * k + 1] += f.y;
+  }
+}
+
 // Byte offset of 16-byte chunk `chunk` (0..7) of row `a` inside a [128 x 64] 16-bit tile stored in
 // the UMMA 128B-swizzled layout (rows of 128 B, chunk index XOR-ed with row & 7).
 __device__ __forceinline__ int swz_chunk(int a, int chunk) { return a * 128 + ((chunk ^ (a & 7)) << 4); }
 // Byte offset of 32-bit word `win` (0..31) of row `a` in such a tile.
 __device__ __forceinline__ int swz_word(int a, int win) {
   return a * 128 + ((((win >> 2) ^ (a & 7)) << 4) | ((win & 3) << 2));
+}
+
+// dG band store.  A thread holds the 64 dS values of row a / key columns [64*half, +64) as 32 packed
+// bf16 words A[]; in band coordinates they are columns 127-a+64*half .. +63 of the [128 x 256] dG
+// operand (4 sub-tiles of 64 columns, 128B-swizzled rows).  base_w = ((127-a)>>1) + 32*half is the
+// first 32-bit word of the run; for even a the run starts at an odd column, so every word takes a
+// half from two neighbours and the first / last element are 16-bit stores.  The word addresses are
+// chunk address (9 per thread, 16-byte granules) + one of 4 in-chunk offsets: two integer ops per
+// store instead of the full swizzle arithmetic.
+__device__ __forceinline__ void band_store(uint8_t* dg_base, int a, int base_w, const uint32_t (&A)[32]) {
+  const int cb = base_w >> 2, r0 = base_w & 3, a7 = a & 7;
+  uint8_t* const rowbase = dg_base + a * 128;
+  uint8_t* ca[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) {
+    const int c = cb + q;
+    ca[q] = rowbase + (c >> 3) * TILE + (((c & 7) ^ a7) << 4);
+  }
+  int offs[4];
+  bool carry[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { carry[j] = (r0 + j) >= 4; offs[j] = ((r0 + j) & 3) * 4; }
+  auto wp = [&](int k) -> uint8_t* {
+    const int j = k & 3, q = k >> 2;
+    return ((q < 8 && carry[j]) ? ca[q + 1 < 9 ? q + 1 : 8] : ca[q]) + offs[j];
+  };
+  if (a & 1) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) *reinterpret_cast<uint32_t*>(wp(k)) = A[k];
+  } else {
+    *reinterpret_cast<uint16_t*>(wp(0) + 2) = (uint16_t)(A[0] & 0xffffu);
+#pragma unroll
+    for (int k = 1; k < 32; ++k) *reinterpret_cast<uint32_t*>(wp(k)) = __byte_perm(A[k - 1], A[k], 0x5432);
+    *reinterpret_cast<uint16_t*>(wp(32)) = (uint16_t)(A[31] >> 16);
+  }
 }
 
 }  // namespace rga

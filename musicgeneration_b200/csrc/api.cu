@@ -30,6 +30,9 @@ int mt_gemm(const void* A, const void* B, void* C, const float* bias, const floa
     set_error("gemm: tcgen05 path does not take this problem (M=%ld N=%ld K=%ld tA=%d tB=%d in=%d out=%d)", (long)M, (long)N, (long)K, transA, transB, in_dtype, out_dtype);
     return MT_E_UNSUPPORTED;
   }
+  // decode-sized problems (a few dozen activation rows): weight-streaming strip kernel
+  if (path == 0 && gemm_skinny_supported(M, N, K, lda, ldb, transA, transB, in_dtype, out_dtype, epilogue, A, B))
+    return gemm_skinny(A, B, C, bias, M, N, K, lda, ldb, ldc, out_dtype, epilogue, as_stream(stream));
   if (path == 2 || (path == 0 && tc_ok))
     return gemm_tc(A, B, C, bias, addend, aux, M, N, K, lda, ldb, ldc, transA, transB, in_dtype, out_dtype, epilogue, workspace, workspace_bytes, as_stream(stream));
   return gemm_simt(A, B, C, bias, addend, aux, M, N, K, lda, ldb, ldc, transA, transB, in_dtype, out_dtype, epilogue, workspace, workspace_bytes, as_stream(stream));

@@ -81,8 +81,18 @@ class MusicTransformer(torch.nn.Module, _PrecisionMixin):
             raise RuntimeError(f"prior ({P}) + length ({length}) - 1 exceeds max_seq ({self.max_seq}); "
                                "KV-cached decode does not slide the window")
         dec = _DecodeSession(self, B)
-        ids = torch.empty((B, P + length), dtype=torch.int32, device=prior.device)
+        ids = torch.zeros((B, P + length), dtype=torch.int32, device=prior.device)
         ids[:, :P] = prior.to(torch.int32)
+        if not return_logits and P + length - 1 >= 4:
+            # one CUDA graph of a whole decode step (device-resident step index), replayed per event
+            if greedy:
+                u = None
+            elif uniforms is not None:
+                u = uniforms[:length].to(torch.float32).contiguous()
+            else:
+                u = torch.rand((length, B), dtype=torch.float32, device=prior.device)
+            dec.run_graph(ids, P, P + length - 1, u, float(temperature), int(top_k), bool(greedy))
+            return ids.to(torch.int64)
         step_logits = []
         logits = None
         for t in range(P + length - 1):
@@ -161,6 +171,68 @@ class _DecodeSession:
         # pad bit per cached position: a generated/prior pad token is masked as a key, exactly as
         # the look-ahead mask of MT/utils.py:73 does in the reference's recompute
         self.pad_bits = torch.zeros((B, cfg.max_seq), dtype=torch.uint8, device=dev)
+
+    # ---- graph mode: every buffer preallocated, the position read from device memory ----------
+    def _alloc_step_buffers(self):
+        cfg, B = self.cfg, self.B
+        d = cfg.d
+        dev = self.emb.device
+        lp = cfg.act != torch.float32
+        f32 = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)
+        act = lambda *sh: torch.empty(sh, dtype=cfg.act, device=dev)
+        nl = len(self.Ws)
+        self.g_x = [f32(B, d) for _ in range(nl + 1)]
+        self.g_xlp = [act(B, d) if lp else None for _ in range(nl + 1)]
+        self.g_qkv, self.g_o, self.g_a = act(B, 3 * d), act(B, d), f32(B, d)
+        self.g_out1, self.g_out1lp = f32(B, d), (act(B, d) if lp else None)
+        self.g_hmid, self.g_f = act(B, d // 2), f32(B, d)
+        self.g_mean, self.g_rstd = f32(B), f32(B)
+        self.g_logits = f32(B, self.V)
+        self.t_dev = torch.zeros((1,), dtype=torch.int32, device=dev)
+
+    def _graph_step(self, ids, prior_len, u, temperature, top_k, greedy):
+        """Enqueue one decode step at position *t_dev (embed -> layers -> vocabulary GEMM -> sample ->
+        advance); the same launches serve every position, so they are captured once."""
+        cfg, B = self.cfg, self.B
+        d, h, dh = cfg.d, cfg.h, cfg.dh
+        lp = cfg.act != torch.float32
+        ops.decode_embed(ids, self.t_dev, self.emb, self.pe, self.g_x[0], self.g_xlp[0], math.sqrt(d))
+        for li, W in enumerate(self.Ws):
+            x, xl = self.g_x[li], (self.g_xlp[li] if lp else self.g_x[li])
+            engine.linear_fwd(xl, W.Wqkv, W.bqkv, self.g_qkv, cfg)
+            ops.decode_kv_append(self.g_qkv, self.kc[li], self.vc[li], ids, config.pad_token,
+                                 self.pad_bits if li == 0 else None, self.t_dev, B, h, dh, cfg.max_seq)
+            ops.decode_attend(self.g_qkv, 3 * d, self.kc[li], self.vc[li], W.E, self.pad_bits, self.g_o,
+                              self.t_dev, B, h, dh, cfg.max_seq)
+            engine.linear_fwd(self.g_o, W.Wfc, W.bfc, self.g_a, cfg)
+            ops.add_ln_fwd(self.g_a, x, W.g1, W.b1, self.g_out1, self.g_out1lp, self.g_mean, self.g_rstd,
+                           1e-6, 0.0, 0, 0)
+            o1 = self.g_out1lp if lp else self.g_out1
+            engine.linear_fwd(o1, W.Wpre, W.bpre, self.g_hmid, cfg, relu=True)
+            engine.linear_fwd(self.g_hmid, W.Wsuf, W.bsuf, self.g_f, cfg)
+            ops.add_ln_fwd(self.g_f, self.g_out1, W.g2, W.b2, self.g_x[li + 1], self.g_xlp[li + 1],
+                           self.g_mean, self.g_rstd, 1e-6, 0.0, 0, 0)
+        nl = len(self.Ws)
+        engine.linear_fwd(self.g_xlp[nl] if lp else self.g_x[nl], self.Wv, self.bv, self.g_logits, cfg)
+        ops.decode_sample(self.g_logits, u, ids, self.t_dev, prior_len, temperature, top_k, greedy)
+        ops.decode_advance(self.t_dev)
+
+    def run_graph(self, ids, prior_len, n_steps, u, temperature, top_k, greedy):
+        """Positions 0 .. n_steps-1 of ``ids`` [B, >= n_steps+1] (prior tokens kept, later ones sampled)."""
+        self._alloc_step_buffers()
+        args = (ids, prior_len, u, temperature, top_k, greedy)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._graph_step(*args)          # warm-up outside capture: function attributes, workspaces
+            self.t_dev.zero_()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            self._graph_step(*args)
+        self.t_dev.zero_()
+        for _ in range(n_steps):
+            graph.replay()
 
     def step(self, tok: torch.Tensor, t: int) -> torch.Tensor:
         """tok int32 [B] at position t -> logits fp32 [B, V] for position t+1."""

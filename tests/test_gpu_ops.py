@@ -327,3 +327,26 @@ def test_gemm_tc_split_k_weight_gradient_shape(dev):
     dW2 = torch.empty(N, K, dtype=torch.float32, device=dev)
     ops.gemm(dY.to(dev), X.to(dev), dW2, N, K, T, N, K, K, True, False, path=2)
     assert torch.equal(dW, dW2)                 # deterministic split-K
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", [(32, 1536, 512), (1, 390, 512), (17, 512, 256), (64, 256, 512), (33, 390, 64),
+                                   (48, 8, 1024)])
+@pytest.mark.parametrize("out_bf16", [False, True])
+def test_gemm_skinny_decode_shapes(dev, M, N, K, out_bf16):
+    """Decode-sized x . W^T (+bias, ReLU): the auto path takes the mma.sync strip kernel; compared with
+    an fp64 product of the same bf16 operands."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(M * 5 + N + K)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    W = torch.randn(N, K, generator=g).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g)
+    ref = A.double() @ W.double().t() + bias.double()
+    Ad, Wd = A.to(dev), W.to(dev)
+    odt = torch.bfloat16 if out_bf16 else torch.float32
+    C = torch.full((M, N), 7.0, dtype=odt, device=dev)
+    ops.gemm(Ad, Wd, C, M, N, K, K, K, N, False, True, bias=bias.to(dev))
+    assert rel(C.float().cpu(), ref) < (4e-3 if out_bf16 else 2e-6)
+    C2 = torch.empty((M, N), dtype=odt, device=dev)
+    ops.gemm(Ad, Wd, C2, M, N, K, K, K, N, False, True, bias=bias.to(dev), relu=True)
+    assert rel(C2.float().cpu(), torch.relu(ref)) < (4e-3 if out_bf16 else 2e-6)

@@ -27,6 +27,11 @@ struct SkinnyParams {
   int mtiles;                       // ceil(M / 16)
 };
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gmem_src)
+               : "memory");
+}
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -50,18 +55,23 @@ gemm_skinny_kernel(const SkinnyParams p) {
   const int n0 = blockIdx.x * SK_BN;
   const int kv = p.K / 8;                                           // 16-byte vectors per row
 
-  // ---- stage A (rows >= M zero-filled) and the 8 weight rows (rows >= N clamped: their columns are never stored)
+  // ---- stage A (rows >= M zero-filled) and the 8 weight rows (rows >= N clamped: their columns are
+  // never stored) with cp.async: every 16-byte vector of the panel is in flight at once (a
+  // load-then-store loop serialised ~16 L2 round trips per thread)
+  const int kvs = 31 - __clz(kv);                                   // shift instead of a division when kv is a power of two
+  const bool pow2 = (kv & (kv - 1)) == 0;
   for (int v = tid; v < MT * 16 * kv; v += SK_THREADS) {
-    const int r = v / kv, c = v - r * kv;
-    uint4 x = make_uint4(0, 0, 0, 0);
-    if (r < p.M) x = *reinterpret_cast<const uint4*>(p.A + (int64_t)r * p.lda + c * 8);
-    *reinterpret_cast<uint4*>(sA + r * pitch + c * 8) = x;
+    const int r = pow2 ? (v >> kvs) : v / kv, c = v - r * kv;
+    __nv_bfloat16* dst = sA + r * pitch + c * 8;
+    if (r < p.M) cp_async16(dst, p.A + (int64_t)r * p.lda + c * 8);
+    else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
   }
   for (int v = tid; v < SK_BN * kv; v += SK_THREADS) {
-    const int r = v / kv, c = v - r * kv;
+    const int r = pow2 ? (v >> kvs) : v / kv, c = v - r * kv;
     const int n = min(n0 + r, p.N - 1);
-    *reinterpret_cast<uint4*>(sW + r * pitch + c * 8) = *reinterpret_cast<const uint4*>(p.W + (int64_t)n * p.ldw + c * 8);
+    cp_async16(sW + r * pitch + c * 8, p.W + (int64_t)n * p.ldw + c * 8);
   }
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   // ---- this warp's quarter of K

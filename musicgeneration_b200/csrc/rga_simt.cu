@@ -218,7 +218,34 @@ __global__ void __launch_bounds__(RTHREADS) rga_weights_kernel(RgaArgs p) {
 // =======================================================================================
 // backward
 // =======================================================================================
-// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]; one warp per (b,h,i)
+// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d].  dh/8 lanes per (b,i,h) row, 16-byte loads (a
+// warp reads 512 contiguous bytes of O and of dO when the heads of a position are adjacent),
+// shuffle reduction inside the lane group; dh in {32, 64, 128} (other head sizes: one warp per row).
+template <typename T, int LPR>         // LPR = lanes per row = dh / 8
+__global__ void __launch_bounds__(256) rga_delta_vec_kernel(RgaArgs p) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t row = t / LPR;                    // (b, i, h) flattened, h fastest
+  const int sub = (int)(t % LPR);
+  const int64_t n = (int64_t)p.B * p.L * p.h;
+  float s = 0.f;
+  int hh = 0, i = 0, b = 0;
+  if (row < n) {
+    hh = (int)(row % p.h);
+    i = (int)((row / p.h) % p.L);
+    b = (int)(row / ((int64_t)p.h * p.L));
+    const int64_t off = (int64_t)b * p.ob + (int64_t)hh * p.oh + (int64_t)i * p.ol + sub * 8;
+    const uint4 o = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.O) + off);
+    const uint4 g = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.dO) + off);
+    const T* ov = reinterpret_cast<const T*>(&o);
+    const T* gv = reinterpret_cast<const T*>(&g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += to_f<T>(ov[e]) * to_f<T>(gv[e]);
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (row < n && sub == 0) p.delta[((int64_t)b * p.h + hh) * p.L + i] = s;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) rga_delta_kernel(RgaArgs p, int dh) {
   int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -497,8 +524,24 @@ int rga_weights_simt(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
 }
 
 int rga_delta_launch(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
+  const int64_t rows = (int64_t)a.B * a.h * a.L;
+  const bool vec = (dtype == MT_BF16 || dtype == MT_F16) && (dh == 32 || dh == 64 || dh == 128) &&
+                   a.ob % 8 == 0 && a.oh % 8 == 0 && a.ol % 8 == 0 && aligned(a.O, 16) && aligned(a.dO, 16);
+  if (vec) {
+    const int lpr = dh / 8;
+    const unsigned grid = (unsigned)((rows * lpr + 255) / 256);
+    if (dtype == MT_BF16) {
+      if (lpr == 4) rga_delta_vec_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(a);
+      else if (lpr == 8) rga_delta_vec_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>(a);
+      else rga_delta_vec_kernel<__nv_bfloat16, 16><<<grid, 256, 0, st>>>(a);
+    } else {
+      if (lpr == 4) rga_delta_vec_kernel<__half, 4><<<grid, 256, 0, st>>>(a);
+      else if (lpr == 8) rga_delta_vec_kernel<__half, 8><<<grid, 256, 0, st>>>(a);
+      else rga_delta_vec_kernel<__half, 16><<<grid, 256, 0, st>>>(a);
+    }
+    return check_launch("rga_delta");
+  }
   MT_DISPATCH_DTYPE(dtype, T, {
-    int64_t rows = (int64_t)a.B * a.h * a.L;
     rga_delta_kernel<T><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(a, dh);
   });
   return check_launch("rga_delta");

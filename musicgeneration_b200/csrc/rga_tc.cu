@@ -228,14 +228,21 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const bool diag = p.causal && (j0 == i0);
       const bool tail = (j0 + TT > L);
       if (diag || tail || padrow != nullptr) {
+        // branch-free: columns x > lim are masked (causal limit on the diagonal tile, ragged tail),
+        // then the key-padding bytes, four per shared-memory word
+        int lim = 31;
+        if (diag) lim = min(lim, a - qt * 32);
+        lim = min(lim, L - 1 - j0 - qt * 32);
 #pragma unroll
-        for (int x = 0; x < 32; ++x) {
-          const int bcol = qt * 32 + x;
-          bool ok = true;
-          if (diag) ok = (bcol <= a);
-          if (tail) ok = ok && (j0 + bcol < L);
-          if (padrow) ok = ok && (spad[bcol] == 0);
-          if (!ok) sv[x] = -INFINITY;
+        for (int x = 0; x < 32; ++x) sv[x] = (x > lim) ? -INFINITY : sv[x];
+        if (padrow) {
+          const uint32_t* sp = reinterpret_cast<const uint32_t*>(spad + qt * 32);
+#pragma unroll
+          for (int x4 = 0; x4 < 8; ++x4) {
+            const uint32_t w = sp[x4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) sv[4 * x4 + e] = ((w >> (8 * e)) & 0xffu) ? -INFINITY : sv[4 * x4 + e];
+          }
         }
       }
       float mx0 = fmaxf(sv[0], sv[1]), mx1 = fmaxf(sv[2], sv[3]);

@@ -377,14 +377,22 @@ rga_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
       for (int x = 0; x < 64; ++x) pv[x] = tc::fast_exp2(fmaf(pv[x], p.scale_log2, -lse2));
       if (diag || tail || pad != nullptr) {
+        // branch-free: columns x > lim are masked (causal limit on the diagonal tile, ragged tail,
+        // rows beyond L), then the key-padding bytes, four per shared-memory word
+        int lim = 63;
+        if (diag) lim = min(lim, a - wg * 64);
+        lim = min(lim, p.L - 1 - j0 - wg * 64);
+        if (!row_ok) lim = -1;
 #pragma unroll
-        for (int x = 0; x < 64; ++x) {
-          const int bcol = wg * 64 + x;
-          bool ok = row_ok;
-          if (diag) ok = ok && (bcol <= a);
-          ok = ok && (j0 + bcol < p.L);
-          if (pad) ok = ok && (spad[bcol] == 0);
-          if (!ok) pv[x] = 0.f;
+        for (int x = 0; x < 64; ++x) pv[x] = (x > lim) ? 0.f : pv[x];
+        if (pad) {
+          const uint32_t* sp = reinterpret_cast<const uint32_t*>(spad + wg * 64);
+#pragma unroll
+          for (int x4 = 0; x4 < 16; ++x4) {
+            const uint32_t w = sp[x4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pv[4 * x4 + e] = ((w >> (8 * e)) & 0xffu) ? 0.f : pv[4 * x4 + e];
+          }
         }
       }
       // the previous step's role MMAs read P / dS / dG: they must be done before we overwrite

@@ -61,13 +61,14 @@ struct Bwd2Params {
   int B, h, L, max_seq, nT;
   int bh_per_cta;                        // DE role
   float scale, scale_log2;
-  long long* trace;                      // MT_RGA_TRACE=1: clock64 stamps of CTA (0,0,0), [4 agents][32 steps][8 events]
+  long long* trace;                      // MT_RGA_TRACE=z: clock64 stamps of CTA (0,0,z), [4 agents][32 steps][8 events]
+  int trace_z;
 };
 
 // pipeline timeline of one CTA (debug aid, off unless the launcher passes a buffer)
 #define TRACE(agent, n, ev)                                                                         \
   do {                                                                                              \
-    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (n) < 32)               \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (int)blockIdx.z == p.trace_z && (n) < 32)               \
       p.trace[((agent) * 32 + (n)) * 8 + (ev)] = clock64();                                         \
   } while (0)
 
@@ -93,6 +94,15 @@ __device__ __forceinline__ Step2 step2(const Bwd2Params& p, int n, int bh0) {
     s.it = (int)blockIdx.z + k; s.jt = k; s.b = bh / p.h; s.hh = bh % p.h;
   }
   return s;
+}
+
+// step n+1 from step n without the integer divisions of step2 (they sat in every agent's per-step chain)
+template <int ROLE>
+__device__ __forceinline__ void step_advance(const Bwd2Params& p, Step2& s) {
+  if (ROLE == R_DKV) { ++s.it; return; }
+  if (s.it + 1 < p.nT) { ++s.it; ++s.jt; return; }       // next tile down the diagonal
+  s.it = (int)blockIdx.z; s.jt = 0;                      // next (batch, head) of the slice
+  if (++s.hh == p.h) { s.hh = 0; ++s.b; }
 }
 
 // 64-column band window [w0, w0+64) of this warp's 32 rows -> private scratch as 32 f16 pairs
@@ -200,8 +210,8 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc::mbar_arrive_expect_tx(bar_res, 2 * TILE);
         tc::tma_load_4d(buf_k(), &tmK, bar_res, 0, s0.hh, s0.jt * TT, s0.b);
         tc::tma_load_4d(buf_v(), &tmV, bar_res, 0, s0.hh, s0.jt * TT, s0.b);
-        for (int n = 0; n < nsteps; ++n) {
-          const Step2 s = step2<ROLE>(p, n, bh0);
+        Step2 s = s0;
+        for (int n = 0; n < nsteps; ++n, step_advance<ROLE>(p, s)) {
           const int st = n & 1;
           const int c0 = p.max_seq - 1 - (s.it - s.jt) * TT;
           tc::mbar_wait(&q_empty[st], ((n >> 1) & 1) ^ 1);
@@ -221,8 +231,8 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc::mbar_arrive_expect_tx(bar_res, 2 * TILE);
         tc::tma_load_2d(smem + Lay2<R_DE>::ELO, &tmE, bar_res, 0, c0 - (TT - 1));
         tc::tma_load_2d(smem + Lay2<R_DE>::EHI, &tmE, bar_res, 0, c0 + 1);
-        for (int n = 0; n < nsteps; ++n) {
-          const Step2 s = step2<ROLE>(p, n, bh0);
+        Step2 s = step2<ROLE>(p, 0, bh0);
+        for (int n = 0; n < nsteps; ++n, step_advance<ROLE>(p, s)) {
           tc::mbar_wait(k_empty, (n & 1) ^ 1);
           tc::mbar_arrive_expect_tx(k_full, TILE);
           tc::tma_load_4d(buf_k(), &tmK, k_full, 0, s.hh, s.jt * TT, s.b);
@@ -230,7 +240,8 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tc::mbar_arrive_expect_tx(&q_full[n & 1], TILE);
           tc::tma_load_4d(buf_q(n), &tmQ, &q_full[n & 1], 0, s.hh, s.it * TT, s.b);
           if (n + 1 < nsteps) {       // pull the next step's tiles into L2 while waiting for the hand-off buffer
-            const Step2 t = step2<ROLE>(p, n + 1, bh0);
+            Step2 t = s;
+            step_advance<ROLE>(p, t);
             tc::tma_prefetch_4d(&tmK, 0, t.hh, t.jt * TT, t.b);
             tc::tma_prefetch_4d(&tmQ, 0, t.hh, t.it * TT, t.b);
             tc::tma_prefetch_4d(&tmDO, 0, t.hh, t.it * TT, t.b);
@@ -361,20 +372,20 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       // the per-row statistic of step n+1 is fetched during step n (a global load in the step's
       // dependency chain cost ~600 cycles per step)
-      auto row_stat = [&](const float* src, int n) -> float {
-        const Step2 t = step2<ROLE>(p, n, bh0);
+      auto row_stat = [&](const float* src, const Step2& t) -> float {
         const int i = t.it * TT + a;
         return i < p.L ? src[((int64_t)t.b * p.h + t.hh) * p.L + i] : 0.f;
       };
-      float lse_next = row_stat(p.lse, 0);
-      for (int n = 0; n < nsteps; ++n) {
-        const Step2 s = step2<ROLE>(p, n, bh0);
+      Step2 s = step2<ROLE>(p, 0, bh0), snext = s;
+      float lse_next = row_stat(p.lse, s);
+      for (int n = 0; n < nsteps; ++n, s = snext) {
         const uint32_t par = n & 1;
         const int i0 = s.it * TT, j0 = s.jt * TT;
         const int i = i0 + a;
         const bool row_ok = i < p.L;
         const float lse2 = lse_next * LOG2E;
-        if (n + 1 < nsteps) lse_next = row_stat(p.lse, n + 1);
+        step_advance<ROLE>(p, snext);
+        if (n + 1 < nsteps) lse_next = row_stat(p.lse, snext);
         if (pad) {
           tc::named_bar_sync(1, B2_GROUP);
           if (half == 0) spad[a] = (j0 + a < p.L) ? pad[(int64_t)s.b * p.L + j0 + a] : 1;
@@ -410,14 +421,22 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
           for (int x = 0; x < 32; ++x) sv[x] = tc::fast_exp2(fmaf(sv[x], p.scale_log2, -lse2));
           if (need_mask) {
+            // branch-free: columns x > lim are masked (causal limit on the diagonal tile, ragged tail,
+            // rows beyond L), then the key-padding bytes, four per shared-memory word
+            int lim = 31;
+            if (diag) lim = min(lim, a - cfirst);
+            lim = min(lim, p.L - 1 - j0 - cfirst);
+            if (!row_ok) lim = -1;
 #pragma unroll
-            for (int x = 0; x < 32; ++x) {
-              const int bcol = cfirst + x;
-              bool ok = row_ok;
-              if (diag) ok = ok && (bcol <= a);
-              ok = ok && (j0 + bcol < p.L);
-              if (pad) ok = ok && (spad[bcol] == 0);
-              if (!ok) sv[x] = 0.f;
+            for (int x = 0; x < 32; ++x) sv[x] = (x > lim) ? 0.f : sv[x];
+            if (pad) {
+              const uint32_t* sp = reinterpret_cast<const uint32_t*>(spad + cfirst);
+#pragma unroll
+              for (int x4 = 0; x4 < 8; ++x4) {
+                const uint32_t w = sp[x4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sv[4 * x4 + e] = ((w >> (8 * e)) & 0xffu) ? 0.f : sv[4 * x4 + e];
+              }
             }
           }
 #pragma unroll
@@ -448,16 +467,17 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc::named_bar_sync(2, B2_GROUP);
       }
       const int base_w = ((127 - a) >> 1) + 32 * half;   // first 32-bit word of this thread's band run in dG
-      auto row_stat = [&](const float* src, int n) -> float {
-        const Step2 t = step2<ROLE>(p, n, bh0);
+      auto row_stat = [&](const float* src, const Step2& t) -> float {
         const int i = t.it * TT + a;
         return i < p.L ? src[((int64_t)t.b * p.h + t.hh) * p.L + i] : 0.f;
       };
-      float d_next = row_stat(p.delta, 0);
+      Step2 snext = step2<ROLE>(p, 0, bh0);
+      float d_next = row_stat(p.delta, snext);
       for (int n = 0; n < nsteps; ++n) {
         const uint32_t par = n & 1;
         const float Ds = d_next * p.scale;
-        if (n + 1 < nsteps) d_next = row_stat(p.delta, n + 1);
+        step_advance<ROLE>(p, snext);
+        if (n + 1 < nsteps) d_next = row_stat(p.delta, snext);
         if (threadIdx.x == B2_GROUP) TRACE(1, n, 0);
         tc::mbar_wait(dp_full, par);
         tc::tc_fence_after();
@@ -563,6 +583,7 @@ int launch_role2(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorM
     if (!trace_dev) cudaMalloc(&trace_dev, trace_n * sizeof(long long));
     cudaMemsetAsync(trace_dev, 0, trace_n * sizeof(long long), st);
     q.trace = trace_dev;
+    q.trace_z = atoi(getenv("MT_RGA_TRACE"));
   }
   kern<<<grid, B2_THREADS, smem2_bytes<ROLE>(), st>>>(tmQ, tmK, tmV, tmDO, tmE, q);
   if (want_trace) {
@@ -595,6 +616,7 @@ Bwd2Params make_params2(const RgaArgs& a) {
   p.scale_log2 = LOG2E / a.inv_scale_div;
   p.bh_per_cta = 1;
   p.trace = nullptr;
+  p.trace_z = 0;
   return p;
 }
 

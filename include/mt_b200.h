@@ -64,15 +64,17 @@ int mt_add_ln_fwd(const void* a, int a_dtype, const float* resid, const float* g
                   float* rstd, int64_t T, int64_t d, float eps, float p_drop, uint64_t seed,
                   uint64_t site, void* stream);
 /* dz (fp32, may alias dout) = grad wrt (dropout(a)+resid); da (da_dtype) = dropmask * dz;
- * part[2, nparts, d] receives per-block partial sums of dgamma / dbeta, reduced by
- * mt_ln_param_grad.  nparts = mt_add_ln_bwd_parts(T). */
+ * part[3, nparts, d] receives per-block partial sums of dgamma / dbeta / colsum(da) -- the last is
+ * the bias gradient of the linear layer that produced `a` (MT/layers.py:153,158: fc, FFN_suf), so
+ * no second pass over da is needed -- reduced by mt_ln_param_grad (dbias may be NULL).
+ * nparts = mt_add_ln_bwd_parts(T). */
 int64_t mt_add_ln_bwd_parts(int64_t T);
 int mt_add_ln_bwd(const float* dout, const void* a, int a_dtype, const float* resid,
                   const float* gamma, const float* mean, const float* rstd, float* dz,
                   void* da, int da_dtype, float* part, int64_t T, int64_t d, float p_drop,
                   uint64_t seed, uint64_t site, void* stream);
-int mt_ln_param_grad(const float* part, float* dgamma, float* dbeta, int64_t nparts, int64_t d,
-                     void* stream);
+int mt_ln_param_grad(const float* part, float* dgamma, float* dbeta, float* dbias, int64_t nparts,
+                     int64_t d, void* stream);
 
 /* ---- K5: C = epi(op(A)[M,K] . op(B)[K,N])  (nn.Linear fwd/dgrad/wgrad on the path) ------- */
 /* transA: A stored [K,M] (lda = row pitch of the stored matrix); transB: B stored [N,K].

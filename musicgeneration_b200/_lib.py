@@ -33,7 +33,7 @@ SIGNATURES = {
     "mt_add_ln_fwd": (_int, [_p, _int, _p, _p, _p, _p, _p, _int, _p, _p, _i64, _i64, _f, _f, _u64, _u64, _p]),
     "mt_add_ln_bwd_parts": (_i64, [_i64]),
     "mt_add_ln_bwd": (_int, [_p, _p, _int, _p, _p, _p, _p, _p, _p, _int, _p, _i64, _i64, _f, _u64, _u64, _p]),
-    "mt_ln_param_grad": (_int, [_p, _p, _p, _i64, _i64, _p]),
+    "mt_ln_param_grad": (_int, [_p, _p, _p, _p, _i64, _i64, _p]),
     "mt_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64, _int, _int]),
     "mt_gemm": (_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _int, _int, _p, _sz, _p]),
     "mt_colsum_workspace_bytes": (_sz, [_i64, _i64]),

@@ -161,18 +161,18 @@ add_ln_fwd_kernel(const TA* __restrict__ a, const float* __restrict__ resid,
 // Each warp keeps running dgamma/dbeta partial sums for its columns over the rows it owns and
 // the block folds its 8 warps through shared memory into part[0/1][block][d].
 template <typename TA, typename TD, int NV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (NV <= 4 ? 2 : 1))       // two CTAs per SM (<= 128 registers) up to d = 512
 add_ln_bwd_kernel(const float* dout /* may alias dz_out */, const TA* __restrict__ a,
                   const float* __restrict__ resid, const float* __restrict__ gamma,
                   const float* __restrict__ mean, const float* __restrict__ rstd, float* dz_out,
                   TD* __restrict__ da, float* __restrict__ part, int64_t T, int d, float p,
                   float inv_keep, uint64_t seed, uint64_t site) {
-  extern __shared__ float sh[];  // [2][8][d]
+  extern __shared__ float sh[];  // [3][8][d]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d4 = d >> 2;
-  float4 dg[NV], db[NV];
+  float4 dg[NV], db[NV], dc[NV];      // dc: column sums of da = bias gradient of the linear that produced `a`
 #pragma unroll
-  for (int i = 0; i < NV; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i) dg[i] = db[i] = dc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   int64_t row = blockIdx.x * 8 + warp;
   const int64_t stride = (int64_t)gridDim.x * 8;
   for (; row < T; row += stride) {
@@ -214,6 +214,9 @@ add_ln_bwd_kernel(const float* dout /* may alias dz_out */, const TA* __restrict
         *reinterpret_cast<float4*>(dz_out + e4 * 4) = o;
         o.x *= msk[i].x; o.y *= msk[i].y; o.z *= msk[i].z; o.w *= msk[i].w;
         store4<TD>(da + e4 * 4, o);
+        // sum what the weight-gradient GEMM will read (the rounded value)
+        dc[i].x += to_f<TD>(from_f<TD>(o.x)); dc[i].y += to_f<TD>(from_f<TD>(o.y));
+        dc[i].z += to_f<TD>(from_f<TD>(o.z)); dc[i].w += to_f<TD>(from_f<TD>(o.w));
       }
     }
   }
@@ -224,10 +227,11 @@ add_ln_bwd_kernel(const float* dout /* may alias dz_out */, const TA* __restrict
     if (c4 < d4) {
       *reinterpret_cast<float4*>(sh + (0 * 8 + warp) * d + c4 * 4) = dg[i];
       *reinterpret_cast<float4*>(sh + (1 * 8 + warp) * d + c4 * 4) = db[i];
+      *reinterpret_cast<float4*>(sh + (2 * 8 + warp) * d + c4 * 4) = dc[i];
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) {
+  for (int c = threadIdx.x; c < 3 * d; c += blockDim.x) {
     int which = c / d, col = c - which * d;
     float s = 0.f;
 #pragma unroll
@@ -236,15 +240,20 @@ add_ln_bwd_kernel(const float* dout /* may alias dz_out */, const TA* __restrict
   }
 }
 
-__global__ void ln_param_grad_kernel(const float* __restrict__ part, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta, int64_t nparts, int d) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * d) return;
-  int which = c / d, col = c - which * d;
+// one warp per (which, column): the nparts partials are strided by d, lanes take every 32nd
+__global__ void __launch_bounds__(256)
+ln_param_grad_kernel(const float* __restrict__ part, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     float* __restrict__ dbias, int64_t nparts, int d) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= 3 * d) return;
+  const int which = c / d, col = c - which * d;
+  float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dbias);
+  if (!dst) return;
   const float* src = part + (int64_t)which * nparts * d + col;
   float s = 0.f;
-  for (int64_t i = 0; i < nparts; ++i) s += src[i * d];
-  (which == 0 ? dgamma : dbeta)[col] = s;
+  for (int64_t i = lane; i < nparts; i += 32) s += src[i * d];
+  s = warp_sum(s);
+  if (lane == 0) dst[col] = s;
 }
 
 // =======================================================================================
@@ -607,7 +616,7 @@ int mt_add_ln_bwd(const float* dout, const void* a, int a_dtype, const float* re
   float inv_keep = 1.f / (1.f - p_drop);
   int grid = (int)mt_add_ln_bwd_parts(T);
   int d4 = (int)(d / 4);
-  size_t smem = 2 * 8 * d * sizeof(float);
+  size_t smem = 3 * 8 * d * sizeof(float);
   MT_REQUIRE(smem <= 48 * 1024 || d <= 1024, "add_ln_bwd: d too large");
   cudaError_t attr_err = cudaSuccess;
   MT_DISPATCH_F32_BF16(a_dtype, TA, MT_DISPATCH_F32_BF16(da_dtype, TD, MT_LN_NV_DISPATCH(d4, NVC, {
@@ -619,12 +628,11 @@ int mt_add_ln_bwd(const float* dout, const void* a, int a_dtype, const float* re
   return check_launch("add_ln_bwd");
 }
 
-int mt_ln_param_grad(const float* part, float* dgamma, float* dbeta, int64_t nparts, int64_t d,
+int mt_ln_param_grad(const float* part, float* dgamma, float* dbeta, float* dbias, int64_t nparts, int64_t d,
                      void* stream) {
   MT_REQUIRE(part && dgamma && dbeta && nparts > 0 && d > 0, "ln_param_grad: bad args");
-  int threads = 128;
-  int grid = (int)((2 * d + threads - 1) / threads);
-  ln_param_grad_kernel<<<grid, threads, 0, as_stream(stream)>>>(part, dgamma, dbeta, nparts, (int)d);
+  const int64_t warps = 3 * d;
+  ln_param_grad_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(part, dgamma, dbeta, dbias, nparts, (int)d);
   return check_launch("ln_param_grad");
 }
 

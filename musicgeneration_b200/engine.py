@@ -135,8 +135,17 @@ def rga_block_fwd(xq, xk, xv, W: LayerWeights, cfg: StackCfg, B: int, Lq: int, m
     return a, saved, P
 
 
+def _gbuf(dst, name, shape, like, zero=False):
+    """Gradient destination: the caller's buffer (a zeroed view of the flat gradient buffer) or a temporary."""
+    if dst is not None and name in dst:
+        return dst[name]
+    if zero:
+        return torch.zeros(shape, dtype=torch.float32, device=like.device)
+    return _empty(shape, torch.float32, like)
+
+
 def rga_block_bwd(d_a, s, W: LayerWeights, cfg: StackCfg, g: Dict[str, torch.Tensor],
-                  dx_addend: Optional[torch.Tensor]):
+                  dx_addend: Optional[torch.Tensor], dst: Optional[Dict[str, torch.Tensor]] = None):
     """d_a [T,d] act dtype = grad wrt fc output.  Fills g[...] (fp32 grads) and returns
     (dxq, dxk, dxv) fp32 [T,d]; for self-attention the three are one tensor that already
     includes ``dx_addend`` (the residual-path gradient)."""
@@ -144,21 +153,23 @@ def rga_block_bwd(d_a, s, W: LayerWeights, cfg: StackCfg, g: Dict[str, torch.Ten
     B, Lq = s["B"], s["L"]
     T = B * Lq
     dev = d_a
-    g["Wfc"] = _empty((d, d), torch.float32, dev)
-    g["bfc"] = _empty((d,), torch.float32, dev)
-    linear_wgrad(d_a, s["O"], g["Wfc"], g["bfc"], cfg)
+    g["Wfc"] = _gbuf(dst, "Wfc", (d, d), dev)
+    have_bfc = "bfc" in g                              # already produced by the LayerNorm backward
+    if not have_bfc:
+        g["bfc"] = _gbuf(dst, "bfc", (d,), dev)
+    linear_wgrad(d_a, s["O"], g["Wfc"], None if have_bfc else g["bfc"], cfg)
     dO = _empty((T, d), cfg.act, dev)
     linear_dgrad(d_a, W.Wfc, dO, cfg)
     dqkv = _empty((T, 3 * d), cfg.act, dev)
     delta = _empty((B, h, Lq), torch.float32, dev)
-    g["E"] = torch.zeros((cfg.max_seq, dh), dtype=torch.float32, device=dev.device)
+    g["E"] = _gbuf(dst, "E", (cfg.max_seq, dh), dev, zero=True)
     qkv = s["qkv"]
     ops.rga_bwd(qkv[:, 0:d], qkv[:, d:2 * d], qkv[:, 2 * d:3 * d], s["strides"], W.E, s["pad"],
                 s["O"], dO, s["ostrides"], s["lse"], delta, dqkv[:, 0:d], dqkv[:, d:2 * d],
                 dqkv[:, 2 * d:3 * d], g["E"], B, h, Lq, dh, cfg.max_seq, s["causal"],
                 path=cfg.attn_path)
-    g["Wqkv"] = _empty((3 * d, d), torch.float32, dev)
-    g["bqkv"] = _empty((3 * d,), torch.float32, dev)
+    g["Wqkv"] = _gbuf(dst, "Wqkv", (3 * d, d), dev)
+    g["bqkv"] = _gbuf(dst, "bqkv", (3 * d,), dev)
     if s["same"]:
         linear_wgrad(dqkv, s["xq"], g["Wqkv"], g["bqkv"], cfg)
         dx = _empty((T, d), torch.float32, dev)
@@ -205,40 +216,43 @@ def layer_fwd(x_f32, x_lp, W: LayerWeights, cfg: StackCfg, B: int, Lq: int, mask
     return out2, (out2_lp if lp else out2), saved, P
 
 
-def layer_bwd(dout, s, W: LayerWeights, cfg: StackCfg) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
-    """dout [T,d] f32 (may be overwritten).  Returns (dx f32, grads dict keyed like LayerWeights)."""
+def layer_bwd(dout, s, W: LayerWeights, cfg: StackCfg,
+              dst: Optional[Dict[str, torch.Tensor]] = None) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+    """dout [T,d] f32 (may be overwritten).  Returns (dx f32, grads dict keyed like LayerWeights).
+    ``dst``: zeroed gradient buffers (keys of the grads dict) to write into instead of temporaries."""
     d = cfg.d
     T = dout.shape[0]
     g: Dict[str, torch.Tensor] = {}
     dev = dout
     p, seed, site0 = s["p"], s["seed"], s["site0"]
     # LN2
-    g["g2"] = _empty((d,), torch.float32, dev)
-    g["b2"] = _empty((d,), torch.float32, dev)
+    g["g2"] = _gbuf(dst, "g2", (d,), dev)
+    g["b2"] = _gbuf(dst, "b2", (d,), dev)
     d_f = _empty((T, d), cfg.act, dev)
+    g["bsuf"] = _gbuf(dst, "bsuf", (d,), dev)         # colsum(d_f) comes out of the LayerNorm backward
     ops.add_ln_bwd(dout, s["f"], s["out1"], W.g2, s["mean2"], s["rstd2"], dout, d_f, g["g2"], g["b2"],
-                   p, seed, site0 + 1)
+                   p, seed, site0 + 1, dbias=g["bsuf"])
     dz2 = dout
     # FFN_suf
-    g["Wsuf"] = _empty((d, d // 2), torch.float32, dev)
-    g["bsuf"] = _empty((d,), torch.float32, dev)
-    linear_wgrad(d_f, s["hmid"], g["Wsuf"], g["bsuf"], cfg)
+    g["Wsuf"] = _gbuf(dst, "Wsuf", (d, d // 2), dev)
+    linear_wgrad(d_f, s["hmid"], g["Wsuf"], None, cfg)
     dh_ = _empty((T, d // 2), cfg.act, dev)
     linear_dgrad(d_f, W.Wsuf, dh_, cfg, relu_mask_aux=s["hmid"])
     # FFN_pre
-    g["Wpre"] = _empty((d // 2, d), torch.float32, dev)
-    g["bpre"] = _empty((d // 2,), torch.float32, dev)
+    g["Wpre"] = _gbuf(dst, "Wpre", (d // 2, d), dev)
+    g["bpre"] = _gbuf(dst, "bpre", (d // 2,), dev)
     linear_wgrad(dh_, s["o1"], g["Wpre"], g["bpre"], cfg)
     linear_dgrad(dh_, W.Wpre, dz2, cfg, addend=dz2)          # d_out1 = dz2 + dh . Wpre (in place)
     d_out1 = dz2
     # LN1
-    g["g1"] = _empty((d,), torch.float32, dev)
-    g["b1"] = _empty((d,), torch.float32, dev)
+    g["g1"] = _gbuf(dst, "g1", (d,), dev)
+    g["b1"] = _gbuf(dst, "b1", (d,), dev)
     d_a = _empty((T, d), cfg.act, dev)
+    g["bfc"] = _gbuf(dst, "bfc", (d,), dev)           # colsum(d_a), likewise
     ops.add_ln_bwd(d_out1, s["a"], s["x"], W.g1, s["mean1"], s["rstd1"], d_out1, d_a, g["g1"], g["b1"],
-                   p, seed, site0)
+                   p, seed, site0, dbias=g["bfc"])
     dz1 = d_out1
-    dx, _, _ = rga_block_bwd(d_a, s["att"], W, cfg, g, dx_addend=dz1)
+    dx, _, _ = rga_block_bwd(d_a, s["att"], W, cfg, g, dx_addend=dz1, dst=dst)
     return dx, g
 
 
@@ -267,12 +281,17 @@ def encoder_fwd(ids: torch.Tensor, emb: torch.Tensor, pe: torch.Tensor, Ws: List
     return x, xl, saved, weights
 
 
-def encoder_bwd(dhid: torch.Tensor, saved, Ws: List[LayerWeights], cfg: StackCfg, V: int):
-    """dhid [T,d] f32 -> (demb [V,d] f32, [layer grad dicts])."""
+def encoder_bwd(dhid: torch.Tensor, saved, Ws: List[LayerWeights], cfg: StackCfg, V: int,
+                dsts: Optional[List[Optional[Dict[str, torch.Tensor]]]] = None,
+                demb_dst: Optional[torch.Tensor] = None):
+    """dhid [T,d] f32 -> (demb [V,d] f32, [layer grad dicts]).  ``dsts`` / ``demb_dst``: zeroed
+    gradient buffers to write into (see layer_bwd)."""
     dx = dhid
     layer_grads: List[Dict[str, torch.Tensor]] = [None] * len(Ws)
     for li in range(len(Ws) - 1, -1, -1):
-        dx, layer_grads[li] = layer_bwd(dx, saved["layers"][li], Ws[li], cfg)
-    demb = torch.zeros((V, cfg.d), dtype=torch.float32, device=dhid.device)
+        dx, layer_grads[li] = layer_bwd(dx, saved["layers"][li], Ws[li], cfg,
+                                        dst=dsts[li] if dsts is not None else None)
+    demb = demb_dst if demb_dst is not None else \
+        torch.zeros((V, cfg.d), dtype=torch.float32, device=dhid.device)
     ops.embed_pos_bwd(saved["ids"], dx, demb, math.sqrt(cfg.d), saved["p"], saved["seed"], 0)
     return demb, layer_grads

@@ -292,6 +292,57 @@ class EncoderLayer(torch.nn.Module, _PrecisionMixin):
         return out, w
 
 
+def _claim_direct(params) -> Optional[list]:
+    """Gradient views of ``params`` that a kernel may write in place: every parameter must belong
+    to a FlatAdam whose zero_grad() ran since the parameter's gradient was last written (so the view
+    is zero and plain assignment equals accumulation).  Claims them (a second backward before the
+    next zero_grad() goes through autograd's accumulation again)."""
+    for p in params:
+        opt = getattr(p, "_mt_opt", None)
+        if opt is None or p.grad is None or id(p) not in opt.fresh or p.grad.dtype != torch.float32 \
+                or not p.grad.is_contiguous():
+            return None
+    for p in params:
+        p._mt_opt.fresh.discard(id(p))
+    return [p.grad for p in params]
+
+
+def _adjacent_rows(ts) -> Optional[torch.Tensor]:
+    """One [sum rows, ...] view over tensors that sit back to back in one storage, else None."""
+    first = ts[0]
+    store = first.untyped_storage()
+    off = first.storage_offset()
+    for t in ts:
+        if t.untyped_storage().data_ptr() != store.data_ptr() or t.storage_offset() != off \
+                or t.shape[1:] != first.shape[1:] or not t.is_contiguous():
+            return None
+        off += t.numel()
+    rows = sum(t.shape[0] for t in ts)
+    return torch.empty(0, dtype=first.dtype, device=first.device).set_(
+        store, first.storage_offset(), (rows,) + tuple(first.shape[1:]))
+
+
+def layer_direct_dst(layer) -> Optional[dict]:
+    """Destination dict for engine.layer_bwd (keys of its grads dict) over the layer's parameter
+    gradients, or None when they cannot be written in place."""
+    ps = layer.params()
+    probe = [getattr(p, "_mt_opt", None) is not None and p.grad is not None for p in ps]
+    if not all(probe):
+        return None
+    wq, bq, wk, bk, wv, bv = ps[0], ps[1], ps[2], ps[3], ps[4], ps[5]
+    gw = _adjacent_rows([wq.grad, wk.grad, wv.grad])
+    gb = _adjacent_rows([bq.grad, bk.grad, bv.grad])
+    if gw is None or gb is None:
+        return None
+    grads = _claim_direct(ps)
+    if grads is None:
+        return None
+    names = ["Wfc", "bfc", "E", "Wpre", "bpre", "Wsuf", "bsuf", "g1", "b1", "g2", "b2"]
+    dst = {"Wqkv": gw, "bqkv": gb}
+    dst.update({n: grads[6 + i] for i, n in enumerate(names)})
+    return dst
+
+
 def layer_grads_in_param_order(g, d):
     """engine grad dict -> tuple ordered like EncoderLayer.params()."""
     gw, gb = g["Wqkv"], g["bqkv"]
@@ -377,7 +428,7 @@ class _EncoderFunction(torch.autograd.Function):
         pe = enc.pos_encoding.table(ids.device)
         hid, hid_lp, saved, weights = engine.encoder_fwd(ids32, enc.embedding.weight.data, pe, Ws, cfg,
                                                          mask, _next_seed(), enc.training, want_w)
-        ctx.cfg, ctx.Ws, ctx.saved = cfg, Ws, saved
+        ctx.cfg, ctx.Ws, ctx.saved, ctx.enc = cfg, Ws, saved, enc
         ctx.V = enc.embedding.weight.shape[0]
         ctx.shape = (B, Lq, cfg.d)
         ctx.n_w = len(weights) if want_w else 0
@@ -391,10 +442,16 @@ class _EncoderFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_hid, *_dw):
         B, Lq, d = ctx.shape
-        demb, lg = engine.encoder_bwd(_as_f32_2d(d_hid, d).clone(), ctx.saved, ctx.Ws, ctx.cfg, ctx.V)
-        grads = (demb,)
-        for g in lg:
-            grads += layer_grads_in_param_order(g, d)
+        enc = ctx.enc
+        # gradients go straight into the optimizer's flat buffer where that is allowed (FlatAdam,
+        # freshly zeroed); autograd then gets None for those parameters
+        dsts = [layer_direct_dst(l) for l in enc.enc_layers]
+        emb_dst = _claim_direct([enc.embedding.weight])
+        demb, lg = engine.encoder_bwd(_as_f32_2d(d_hid, d).clone(), ctx.saved, ctx.Ws, ctx.cfg, ctx.V,
+                                      dsts=dsts, demb_dst=emb_dst[0] if emb_dst else None)
+        grads = (None,) if emb_dst else (demb,)
+        for g, dst in zip(lg, dsts):
+            grads += (None,) * N_LAYER_PARAMS if dst is not None else layer_grads_in_param_order(g, d)
         return (None, None, None, None) + grads
 
 
@@ -413,6 +470,7 @@ class _LinearFunction(torch.autograd.Function):
         out = torch.empty((x2.shape[0], N), dtype=torch.float32, device=x.device)
         engine.linear_fwd(xa, Wa, bias.data, out, cfg)
         ctx.cfg, ctx.xa, ctx.Wa, ctx.shape = cfg, xa, Wa, shape
+        ctx.weight, ctx.bias = weight, bias
         return out.view(*shape[:-1], N)
 
     @staticmethod
@@ -429,9 +487,10 @@ class _LinearFunction(torch.autograd.Function):
             dy = dy_buf[:, :N]
         else:
             dy = _act_copy(d2, cfg.act)
-        dW = torch.empty((N, K), dtype=torch.float32, device=dy.device)
-        db = torch.empty((N,), dtype=torch.float32, device=dy.device)
+        direct = _claim_direct([ctx.weight, ctx.bias])
+        dW = direct[0] if direct else torch.empty((N, K), dtype=torch.float32, device=dy.device)
+        db = direct[1] if direct else torch.empty((N,), dtype=torch.float32, device=dy.device)
         engine.linear_wgrad(dy, xa, dW, db, cfg)
         dx = torch.empty((T, K), dtype=torch.float32, device=dy.device)
         engine.linear_dgrad(dy, Wa, dx, cfg)
-        return None, dx.view(ctx.shape), dW, db
+        return (None, dx.view(ctx.shape), None, None) if direct else (None, dx.view(ctx.shape), dW, db)

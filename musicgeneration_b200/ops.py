@@ -78,16 +78,17 @@ def add_ln_fwd(a, resid, gamma, beta, out_f32, out_lp, mean, rstd, eps, p_drop, 
                                    _ptr(rstd), T, d, eps, p_drop, seed, site, _stream()), "add_ln_fwd")
 
 
-def add_ln_bwd(dout, a, resid, gamma, mean, rstd, dz, da, dgamma, dbeta, p_drop, seed, site):
+def add_ln_bwd(dout, a, resid, gamma, mean, rstd, dz, da, dgamma, dbeta, p_drop, seed, site, dbias=None):
+    """``dbias`` (optional, [d] fp32) receives colsum(da): the bias gradient of the linear producing ``a``."""
     _need_cuda(dout, a, resid)
     T, d = resid.shape
     lib = L.load()
     nparts = lib.mt_add_ln_bwd_parts(T)
-    part = torch.empty((2, nparts, d), dtype=torch.float32, device=dout.device)
+    part = torch.empty((3, nparts, d), dtype=torch.float32, device=dout.device)
     L.check(lib.mt_add_ln_bwd(_ptr(dout), _ptr(a), dt(a), _ptr(resid), _ptr(gamma), _ptr(mean),
                               _ptr(rstd), _ptr(dz), _ptr(da), dt(da), _ptr(part), T, d, p_drop, seed,
                               site, _stream()), "add_ln_bwd")
-    L.check(lib.mt_ln_param_grad(_ptr(part), _ptr(dgamma), _ptr(dbeta), nparts, d, _stream()),
+    L.check(lib.mt_ln_param_grad(_ptr(part), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), nparts, d, _stream()),
             "ln_param_grad")
 
 

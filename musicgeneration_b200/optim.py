@@ -54,6 +54,12 @@ class FlatAdam:
             p.data = view
             p.grad = self.flat_g[off:off + p.numel()].view(p.shape)
             off += sz
+        # Kernels may write a gradient straight into its flat_g view (instead of handing a temporary
+        # to autograd, which then launches one `grad += tmp` per parameter) as long as that view is
+        # known to be zero: ``fresh`` holds the ids of the parameters not written since zero_grad().
+        self.fresh = set()
+        for p in order:
+            p._mt_opt = self
         self.lr, self.betas, self.eps = lr, betas, eps
         self.param_groups = [{"lr": lr, "params": order}]     # what CustomSchedule.step() touches
         self.step_count = 0
@@ -62,8 +68,7 @@ class FlatAdam:
 
     def zero_grad(self, set_to_none: bool = False):
         self.flat_g.zero_()
-        for p in self.params:           # autograd may have replaced .grad objects; re-point
-            pass
+        self.fresh = {id(p) for p in self.params}
 
     def all_reduce_grads(self):
         """Data-parallel exchange: sum of the flat gradient over ranks (NCCL, one call)."""

@@ -74,6 +74,37 @@ def test_train_small_fp32_logits_loss_grads():
     assert (crit.last_argmax.cpu().numpy() == z["bucket"]).all()
 
 
+def test_flat_adam_gradients_written_in_place_match_fixture():
+    """With FlatAdam the kernels write every gradient straight into the flat buffer (no autograd
+    accumulation launches).  Same fixture gradients; a second backward without zero_grad() must
+    still ACCUMULATE (it goes through autograd again)."""
+    import musicgeneration_b200 as mtb
+    from musicgeneration_b200.optim import FlatAdam
+    dev = torch.device("cuda:0")
+    z = load("train_small.npz")
+    m, (d, V, pad, layers, L) = build_model(z, dev)
+    x, y = torch.from_numpy(z["x"]).to(dev), torch.from_numpy(z["y"]).to(dev)
+    m.train()
+    opt = FlatAdam(m, lr=0.0)
+    crit = mtb.SmoothCrossEntropyLoss(0.1, V, pad)
+    opt.zero_grad()
+    assert len(opt.fresh) == len(opt.params)
+    crit(m(x), y).backward()
+    assert not opt.fresh                      # every parameter's gradient was claimed by a kernel
+    for k, p in m.named_parameters():
+        g = z["g:" + k]
+        assert p.grad.data_ptr() >= opt.flat_g.data_ptr() and \
+            p.grad.data_ptr() < opt.flat_g.data_ptr() + opt.flat_g.numel() * 4, k
+        err = np.abs(p.grad.cpu().numpy() - g).max()
+        assert err <= 2e-6 + 3e-4 * np.abs(g).max(), (k, err, np.abs(g).max())
+    once = opt.flat_g.clone()
+    crit(m(x), y).backward()                  # no zero_grad(): accumulates
+    assert rel(opt.flat_g.cpu(), (2 * once).cpu()) < 1e-6
+    opt.zero_grad()
+    crit(m(x), y).backward()
+    assert rel(opt.flat_g.cpu(), once.cpu()) < 1e-6
+
+
 def test_train_small_eval_returns_attention_weights():
     dev = torch.device("cuda:0")
     z = load("train_small.npz")

@@ -100,7 +100,10 @@ def test_add_ln_fwd_bwd(dev, d, lp):
     da = torch.empty(T, d, dtype=torch.bfloat16 if lp else torch.float32, device=dev)
     dgam = torch.empty(d, device=dev)
     dbet = torch.empty(d, device=dev)
-    ops.add_ln_bwd(dyd, ad, rd, gd, mean, rstd, dz, da, dgam, dbet, 0.0, 0, 0)
+    dbias = torch.empty(d, device=dev)
+    ops.add_ln_bwd(dyd, ad, rd, gd, mean, rstd, dz, da, dgam, dbet, 0.0, 0, 0, dbias=dbias)
+    # colsum(da) = bias gradient of the linear that produced `a` (sum of the stored, rounded values)
+    assert rel(dbias.cpu(), da.float().sum(0).cpu()) < 2e-5
     assert rel(dz.cpu(), r64.grad) < 5e-6
     assert rel(da.float().cpu(), a64.grad) < (4e-3 if lp else 5e-6)
     assert rel(dgam.cpu(), g64.grad) < 5e-6

@@ -163,15 +163,24 @@ int mt_sample(const float* logits, const float* u, int32_t* ids_out, int64_t B, 
  * vocabulary GEMM -> sample -> advance) can be replayed for every generated event without any
  * host work in between (MT/network.py:52-77 is a Python loop of full-stack recomputes).
  * ids [B, ld_ids] int32 holds prior + generated tokens; pad_bits [B, max_seq]. */
+/* pad_bits (optional): pad_bits[b, t] = (ids[b, t] == pad_token), the key mask of position t */
 int mt_decode_embed(const int32_t* ids, int64_t ld_ids, const int32_t* t_dev, const float* emb,
                     const float* pe, float* out_f32, void* out_lp, int lp_dtype, int64_t B, int64_t d,
-                    int64_t V, float scale, void* stream);
+                    int64_t V, float scale, int32_t pad_token, uint8_t* pad_bits, int64_t max_seq,
+                    void* stream);
 int mt_decode_kv_append(const void* qkv, void* kcache, void* vcache, const int32_t* ids, int64_t ld_ids,
                         int32_t pad_token, uint8_t* pad_bits, const int32_t* t_dev, int64_t B, int64_t h,
                         int64_t dh, int64_t max_seq, int dtype, void* stream);
-int mt_decode_attend(const void* q, int64_t q_stride_b, const void* kcache, const void* vcache, const void* E,
+/* split-context kernel: one CTA per (head, sequence, 256-key chunk); `workspace`
+ * (mt_decode_attend_workspace_bytes, 16-byte aligned) holds the per-chunk partials and one arrival
+ * counter per (sequence, head); the caller zeroes it ONCE, the kernel leaves the counters at zero. */
+size_t mt_decode_attend_workspace_bytes(int64_t B, int64_t h, int64_t dh, int64_t max_seq);
+/* append != 0: q is the fused projection row [3, h, dh] of the new token (q_stride_b apart); its
+ * K / V rows are read from there and stored into the caches at position t by this launch. */
+int mt_decode_attend(const void* q, int64_t q_stride_b, void* kcache, void* vcache, const void* E,
                      const uint8_t* pad_bits, void* out, const int32_t* t_dev, int64_t B, int64_t h, int64_t dh,
-                     int64_t max_seq, int dtype, void* stream);
+                     int64_t max_seq, int dtype, int append, void* workspace, size_t workspace_bytes,
+                     void* stream);
 /* writes the sampled id to ids[b, t+1] unless t+1 < prior_len (prior tokens are kept); u holds one
  * row of B uniforms per generated event (row t+1-prior_len) */
 int mt_decode_sample(const float* logits, const float* u, int32_t* ids, int64_t ld_ids, const int32_t* t_dev,

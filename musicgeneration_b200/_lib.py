@@ -50,9 +50,10 @@ SIGNATURES = {
     "mt_rga_decode": (_int, [_p, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _p]),
     "mt_kv_append": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _p]),
     "mt_sample": (_int, [_p, _p, _p, _i64, _i64, _f, _i32, _int, _p]),
-    "mt_decode_embed": (_int, [_p, _i64, _p, _p, _p, _p, _p, _int, _i64, _i64, _i64, _f, _p]),
+    "mt_decode_embed": (_int, [_p, _i64, _p, _p, _p, _p, _p, _int, _i64, _i64, _i64, _f, _i32, _p, _i64, _p]),
     "mt_decode_kv_append": (_int, [_p, _p, _p, _p, _i64, _i32, _p, _p, _i64, _i64, _i64, _i64, _int, _p]),
-    "mt_decode_attend": (_int, [_p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _int, _p]),
+    "mt_decode_attend_workspace_bytes": (C.c_size_t, [_i64, _i64, _i64, _i64]),
+    "mt_decode_attend": (_int, [_p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _int, _int, _p, C.c_size_t, _p]),
     "mt_decode_sample": (_int, [_p, _p, _p, _i64, _p, _i32, _i64, _i64, _f, _i32, _int, _p]),
     "mt_decode_advance": (_int, [_p, _p]),
 }

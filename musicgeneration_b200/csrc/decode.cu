@@ -77,6 +77,185 @@ rga_decode_kernel(const T* __restrict__ q, const T* __restrict__ kc, const T* __
   }
 }
 
+
+// ---- split-context variant (the decode hot path) ---------------------------------------------
+// One CTA per (head, sequence, 256-key chunk of the context): DH/8 lanes share a key row (16-byte
+// loads, a warp reads whole contiguous rows), partial (max, sum, o[DH]) per chunk goes to the
+// caller's workspace and the LAST chunk-CTA of a (sequence, head) to finish folds the partials
+// (arrival counter, reset for the next launch) -- no second launch.  The one-CTA-per-(sequence,
+// head) kernel above streams its whole context through 128 threads and reaches ~1.1 TB/s at
+// context 1000; splitting gives every SM several independent streams.
+constexpr int DEC_CHUNK = 256;
+
+// eight consecutive elements held raw (one or two 16-byte registers quads) until they are needed
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> {
+  uint4 r;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { r = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void zero() { r = make_uint4(0, 0, 0, 0); }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = r; }
+  __device__ __forceinline__ void to_float(float (&f)[8]) const {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void zero() { a = b = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = a; *reinterpret_cast<float4*>(p + 4) = b;
+  }
+  __device__ __forceinline__ void to_float(float (&f)[8]) const {
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+};
+template <typename T> __device__ __forceinline__ void load8f(const T* p, float (&f)[8]);
+template <> __device__ __forceinline__ void load8f<float>(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8f<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+
+template <typename T, int DH>
+__global__ void __launch_bounds__(128)
+rga_decode_split_kernel(const T* __restrict__ q, T* kc, T* vc,
+                        const T* __restrict__ E, const uint8_t* __restrict__ pad_keys, T* __restrict__ out,
+                        int64_t q_stride_b, int h, int max_seq, const int32_t* __restrict__ t_dev,
+                        float inv_sqrt_dh, int32_t* __restrict__ counters, float* __restrict__ part, int nsplit,
+                        int append) {
+  constexpr int LPK = DH / 8;            // lanes per key row
+  constexpr int KPI = 128 / LPK;         // keys per block iteration
+  constexpr int NIT = DEC_CHUNK / KPI;
+  __shared__ float red[KPI][DH + 1];
+  __shared__ float wred[8];
+  __shared__ uint8_t spad[DEC_CHUNK];
+  __shared__ int s_last;
+  const int t = *t_dev;
+  const int tid = threadIdx.x, hh = blockIdx.x, b = blockIdx.y, sp = blockIdx.z;
+  const int j0 = sp * DEC_CHUNK;
+  const int n = min(DEC_CHUNK, t + 1 - j0);
+  if (n <= 0) return;                                         // chunk beyond the context (uniform per CTA)
+  const int active = (t + DEC_CHUNK) / DEC_CHUNK;             // chunks that hold keys 0..t
+  const int64_t bh = (int64_t)b * h + hh;
+  const int sub = tid % LPK, grp = tid / LPK;
+  // shuffles stay inside a key group: its LPK lanes leave the key loop together, other groups of the warp may not
+  const uint32_t LMASK = (LPK == 32 ? 0xffffffffu : ((1u << LPK) - 1u)) << ((tid & 31) / LPK * LPK);
+  float q8[8];
+  load8f<T>(q + (int64_t)b * q_stride_b + (int64_t)hh * DH + sub * 8, q8);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) q8[e] *= inv_sqrt_dh;
+  const uint8_t* pad = pad_keys ? pad_keys + (int64_t)b * max_seq : nullptr;
+  if (pad) {                                                  // the chunk's pad flags, once
+    for (int x = tid; x < DEC_CHUNK; x += 128) spad[x] = (x < n) ? pad[j0 + x] : 1;
+    __syncthreads();
+  }
+  T* kb = kc + (bh * (int64_t)max_seq + j0) * DH + sub * 8;
+  T* vb = vc + (bh * (int64_t)max_seq + j0) * DH + sub * 8;
+  // append != 0: q is the fused projection row [3, h, DH] of the new token; its K / V rows (position t)
+  // are taken from there and stored into the caches by the chunk that owns key t (no separate append launch)
+  const T* knew = q + (int64_t)b * q_stride_b + (int64_t)(h + hh) * DH + sub * 8;
+  const T* vnew = q + (int64_t)b * q_stride_b + (int64_t)(2 * h + hh) * DH + sub * 8;
+  const T* eb = E + (int64_t)(max_seq - 1 - t + j0) * DH + sub * 8;      // row of key j0; key j0+jj is jj rows further
+  // ---- one pass: every key group (LPK lanes) walks its keys with a running (max, sum, o).  Keys are
+  // taken four at a time: the 12 row loads (K, E, V of four keys) are issued back to back BEFORE any
+  // of them is used (the compiler does not hoist them across the per-key branches by itself), so a
+  // thread keeps 12 independent 16/32-byte loads in flight.
+  float m_run = -INFINITY, l_run = 0.f, o8[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o8[e] = 0.f;
+#pragma unroll 1
+  for (int it0 = 0; it0 < NIT; it0 += 4) {
+    if (grp + it0 * KPI >= n) break;                // uniform per key group; later groups only feed zeros to the shuffles
+    Raw8<T> kr[4], er[4], vr[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int jj = grp + (it0 + u) * KPI;
+      if (jj < n) {
+        const bool is_new = append && (j0 + jj == t);
+        kr[u].load(is_new ? knew : kb + (int64_t)jj * DH);
+        er[u].load(eb + (int64_t)jj * DH);
+        vr[u].load(is_new ? vnew : vb + (int64_t)jj * DH);
+        if (is_new) { kr[u].store(kb + (int64_t)jj * DH); vr[u].store(vb + (int64_t)jj * DH); }
+      } else {
+        kr[u].zero(); er[u].zero(); vr[u].zero();
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int jj = grp + (it0 + u) * KPI;
+      float kf[8], ef[8], vf[8];
+      kr[u].to_float(kf); er[u].to_float(ef); vr[u].to_float(vf);
+      float acc = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc = fmaf(q8[e], kf[e] + ef[e], acc);
+#pragma unroll
+      for (int o = LPK / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(LMASK, acc, o);
+      const bool use = (jj < n) && !(pad && spad[jj]);
+      const float a2 = use ? acc : -INFINITY;
+      const float m_new = fmaxf(m_run, a2);
+      const float corr = (m_new == -INFINITY) ? 1.f : __expf(m_run - m_new);     // nothing seen yet: keep zeros
+      const float pj = use ? __expf(acc - m_new) : 0.f;
+      l_run = fmaf(l_run, corr, pj);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o8[e] = fmaf(o8[e], corr, pj * vf[e]);
+      m_run = m_new;
+    }
+  }
+  // ---- fold the key groups: M = max m_g, weights exp(m_g - M)
+  float mx = warp_max(m_run);
+  if ((tid & 31) == 0) wred[tid >> 5] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(wred[0], wred[1]), fmaxf(wred[2], wred[3]));
+  const float wg = (m_run == -INFINITY) ? 0.f : __expf(m_run - mx);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[grp][sub * 8 + e] = o8[e] * wg;
+  float sum = (sub == 0) ? l_run * wg : 0.f;
+  sum = warp_sum(sum);
+  if ((tid & 31) == 0) wred[4 + (tid >> 5)] = sum;
+  __syncthreads();
+  float* my = part + (bh * nsplit + sp) * (DH + 2);
+  if (tid < DH) {
+    float tot = 0.f;
+#pragma unroll 8
+    for (int g = 0; g < KPI; ++g) tot += red[g][tid];
+    my[2 + tid] = tot;
+  }
+  if (tid == 0) { my[0] = mx; my[1] = (wred[4] + wred[5]) + (wred[6] + wred[7]); }
+  // ---- the last chunk of this (sequence, head) to arrive folds the partials
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int prev = atomicAdd(&counters[bh], 1);
+    s_last = (prev == active - 1);
+    if (s_last) counters[bh] = 0;                  // ready for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid < DH) {
+    const float* base = part + bh * nsplit * (DH + 2);
+    float M = -INFINITY;
+    for (int s2 = 0; s2 < active; ++s2) M = fmaxf(M, __ldcg(base + s2 * (DH + 2)));
+    float L = 0.f, acc = 0.f;
+    for (int s2 = 0; s2 < active; ++s2) {
+      const float ms = __ldcg(base + s2 * (DH + 2));
+      const float w = (ms == -INFINITY) ? 0.f : __expf(ms - M);
+      L = fmaf(w, __ldcg(base + s2 * (DH + 2) + 1), L);
+      acc = fmaf(w, __ldcg(base + s2 * (DH + 2) + 2 + tid), acc);
+    }
+    out[bh * DH + tid] = from_f<T>(L > 0.f ? acc / L : 0.f);
+  }
+}
+
 // qkv row layout of the fused projection: [B, 3, h, dh] -> caches [B, h, max_seq, dh] at t
 template <typename T>
 __global__ void kv_append_kernel(const T* __restrict__ qkv, T* __restrict__ kc, T* __restrict__ vc,
@@ -101,12 +280,15 @@ template <typename TL>
 __global__ void __launch_bounds__(256)
 decode_embed_kernel(const int32_t* __restrict__ ids, int64_t ld_ids, const int32_t* __restrict__ t_dev,
                     const float* __restrict__ emb, const float* __restrict__ pe, float* __restrict__ out,
-                    TL* __restrict__ out_lp, int B, int d4, int V, float scale) {
+                    TL* __restrict__ out_lp, int B, int d4, int V, float scale, int32_t pad_token,
+                    uint8_t* __restrict__ pad_bits, int64_t max_seq) {
   const int e4 = blockIdx.x * blockDim.x + threadIdx.x;
   if (e4 >= B * d4) return;
   const int b = e4 / d4, c4 = e4 - b * d4;
   const int t = *t_dev;
   int32_t id = ids[(int64_t)b * ld_ids + t];
+  // the key at position t is masked later iff its token is the pad token (MT/utils.py:73)
+  if (pad_bits && c4 == 0) pad_bits[(int64_t)b * max_seq + t] = (id == pad_token) ? 1 : 0;
   id = id < 0 ? 0 : (id >= V ? V - 1 : id);
   const float4 w = *reinterpret_cast<const float4*>(emb + ((int64_t)id * d4 + c4) * 4);
   const float4 q = *reinterpret_cast<const float4*>(pe + ((int64_t)t * d4 + c4) * 4);
@@ -284,12 +466,12 @@ int mt_sample(const float* logits, const float* u, int32_t* ids_out, int64_t B, 
 // ---- device-resident step index: one CUDA graph of a decode step is replayed per event -------
 int mt_decode_embed(const int32_t* ids, int64_t ld_ids, const int32_t* t_dev, const float* emb,
                     const float* pe, float* out_f32, void* out_lp, int lp_dtype, int64_t B, int64_t d,
-                    int64_t V, float scale, void* stream) {
+                    int64_t V, float scale, int32_t pad_token, uint8_t* pad_bits, int64_t max_seq, void* stream) {
   MT_REQUIRE(ids && t_dev && emb && pe && out_f32 && B > 0 && d > 0 && d % 4 == 0 && V > 0, "decode_embed: bad args");
   if (!out_lp) lp_dtype = MT_F32;
   int64_t n4 = B * (d / 4);
   MT_DISPATCH_F32_BF16(lp_dtype, TL,
-      (decode_embed_kernel<TL><<<(unsigned)((n4 + 255) / 256), 256, 0, as_stream(stream)>>>(ids, ld_ids, t_dev, emb, pe, out_f32, (TL*)out_lp, (int)B, (int)(d / 4), (int)V, scale)));
+      (decode_embed_kernel<TL><<<(unsigned)((n4 + 255) / 256), 256, 0, as_stream(stream)>>>(ids, ld_ids, t_dev, emb, pe, out_f32, (TL*)out_lp, (int)B, (int)(d / 4), (int)V, scale, pad_token, pad_bits, max_seq)));
   return check_launch("decode_embed");
 }
 
@@ -300,11 +482,40 @@ int mt_decode_kv_append(const void* qkv, void* kcache, void* vcache, const int32
   return kv_append_impl(qkv, kcache, vcache, B, h, dh, max_seq, 0, t_dev, ids, ld_ids, pad_token, pad_bits, dtype, stream);
 }
 
-int mt_decode_attend(const void* q, int64_t q_stride_b, const void* kcache, const void* vcache, const void* E,
+size_t mt_decode_attend_workspace_bytes(int64_t B, int64_t h, int64_t dh, int64_t max_seq) {
+  const int64_t nsplit = (max_seq + DEC_CHUNK - 1) / DEC_CHUNK;
+  return (size_t)(B * h) * sizeof(int32_t) + (size_t)(B * h * nsplit * (dh + 2)) * sizeof(float);
+}
+
+int mt_decode_attend(const void* q, int64_t q_stride_b, void* kcache, void* vcache, const void* E,
                      const uint8_t* pad_bits, void* out, const int32_t* t_dev, int64_t B, int64_t h, int64_t dh,
-                     int64_t max_seq, int dtype, void* stream) {
+                     int64_t max_seq, int dtype, int append, void* workspace, size_t workspace_bytes, void* stream) {
   MT_REQUIRE(t_dev, "decode_attend: null step index");
-  return rga_decode_impl(q, q_stride_b, kcache, vcache, E, pad_bits, out, B, h, dh, max_seq, 0, t_dev, dtype, stream);
+  MT_REQUIRE(q && kcache && vcache && E && out, "decode_attend: null pointer");
+  MT_REQUIRE(B > 0 && h > 0 && max_seq > 0 && B <= 65535, "decode_attend: bad shape");
+  MT_REQUIRE(aligned(kcache, 16) && aligned(vcache, 16) && aligned(E, 16) && aligned(q, 16) && q_stride_b % 8 == 0, "decode_attend: misaligned");
+  const size_t need = mt_decode_attend_workspace_bytes(B, h, dh, max_seq);
+  if (!workspace || workspace_bytes < need || !aligned(workspace, 16)) {
+    set_error("decode_attend: workspace too small or misaligned (%zu < %zu); it must be zeroed once before the first call", workspace_bytes, need);
+    return MT_E_WORKSPACE;
+  }
+  const int nsplit = (int)((max_seq + DEC_CHUNK - 1) / DEC_CHUNK);
+  int32_t* counters = reinterpret_cast<int32_t*>(workspace);
+  // partials start at a 16-byte boundary after the counters
+  float* part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + (((size_t)(B * h) * sizeof(int32_t) + 15) / 16) * 16);
+  MT_REQUIRE((size_t)(reinterpret_cast<uint8_t*>(part) - reinterpret_cast<uint8_t*>(workspace)) + (size_t)(B * h * nsplit * (dh + 2)) * sizeof(float) <= workspace_bytes + 16, "decode_attend: workspace layout");
+  dim3 grid((unsigned)h, (unsigned)B, (unsigned)nsplit);
+  const float isd = 1.f / sqrtf((float)dh);
+#define MT_LAUNCH_DECS(T, DHC) \
+  rga_decode_split_kernel<T, DHC><<<grid, 128, 0, as_stream(stream)>>>((const T*)q, (T*)kcache, (T*)vcache, (const T*)E, pad_bits, (T*)out, q_stride_b, (int)h, (int)max_seq, t_dev, isd, counters, part, nsplit, append);
+  MT_DISPATCH_F32_BF16(dtype, T, {
+    if (dh == 32) { MT_LAUNCH_DECS(T, 32) }
+    else if (dh == 64) { MT_LAUNCH_DECS(T, 64) }
+    else if (dh == 128) { MT_LAUNCH_DECS(T, 128) }
+    else { set_error("decode_attend: head dim %ld not built (32, 64, 128)", (long)dh); return MT_E_UNSUPPORTED; }
+  });
+#undef MT_LAUNCH_DECS
+  return check_launch("decode_attend");
 }
 
 int mt_decode_sample(const float* logits, const float* u, int32_t* ids, int64_t ld_ids, const int32_t* t_dev,

@@ -189,6 +189,7 @@ class _DecodeSession:
         self.g_mean, self.g_rstd = f32(B), f32(B)
         self.g_logits = f32(B, self.V)
         self.t_dev = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.g_ws = ops.decode_attend_workspace(B, cfg.h, cfg.dh, cfg.max_seq, dev)
 
     def _graph_step(self, ids, prior_len, u, temperature, top_k, greedy):
         """Enqueue one decode step at position *t_dev (embed -> layers -> vocabulary GEMM -> sample ->
@@ -196,14 +197,13 @@ class _DecodeSession:
         cfg, B = self.cfg, self.B
         d, h, dh = cfg.d, cfg.h, cfg.dh
         lp = cfg.act != torch.float32
-        ops.decode_embed(ids, self.t_dev, self.emb, self.pe, self.g_x[0], self.g_xlp[0], math.sqrt(d))
+        ops.decode_embed(ids, self.t_dev, self.emb, self.pe, self.g_x[0], self.g_xlp[0], math.sqrt(d),
+                         config.pad_token, self.pad_bits)
         for li, W in enumerate(self.Ws):
             x, xl = self.g_x[li], (self.g_xlp[li] if lp else self.g_x[li])
             engine.linear_fwd(xl, W.Wqkv, W.bqkv, self.g_qkv, cfg)
-            ops.decode_kv_append(self.g_qkv, self.kc[li], self.vc[li], ids, config.pad_token,
-                                 self.pad_bits if li == 0 else None, self.t_dev, B, h, dh, cfg.max_seq)
             ops.decode_attend(self.g_qkv, 3 * d, self.kc[li], self.vc[li], W.E, self.pad_bits, self.g_o,
-                              self.t_dev, B, h, dh, cfg.max_seq)
+                              self.t_dev, B, h, dh, cfg.max_seq, self.g_ws, append=True)
             engine.linear_fwd(self.g_o, W.Wfc, W.bfc, self.g_a, cfg)
             ops.add_ln_fwd(self.g_a, x, W.g1, W.b1, self.g_out1, self.g_out1lp, self.g_mean, self.g_rstd,
                            1e-6, 0.0, 0, 0)

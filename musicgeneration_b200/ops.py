@@ -206,12 +206,13 @@ def sample(logits, u, ids_out, temperature, top_k, greedy):
 
 
 # ---- decode with a device-resident step index (CUDA-graph replayable) ----------------------
-def decode_embed(ids, t_dev, emb, pe, out_f32, out_lp, scale):
+def decode_embed(ids, t_dev, emb, pe, out_f32, out_lp, scale, pad_token=0, pad_bits=None):
     B, ld = ids.shape
     V, d = emb.shape
     L.check(L.load().mt_decode_embed(_ptr(ids), ld, _ptr(t_dev), _ptr(emb), _ptr(pe), _ptr(out_f32),
                                      _ptr(out_lp), dt(out_lp) if out_lp is not None else L.MT_F32, B, d, V,
-                                     scale, _stream()), "decode_embed")
+                                     scale, pad_token, _ptr(pad_bits),
+                                     pad_bits.shape[1] if pad_bits is not None else 0, _stream()), "decode_embed")
 
 
 def decode_kv_append(qkv, kcache, vcache, ids, pad_token, pad_bits, t_dev, B, h, dh, max_seq):
@@ -220,10 +221,17 @@ def decode_kv_append(qkv, kcache, vcache, ids, pad_token, pad_bits, t_dev, B, h,
                                          _stream()), "decode_kv_append")
 
 
-def decode_attend(q, q_stride_b, kcache, vcache, E, pad_bits, out, t_dev, B, h, dh, max_seq):
+def decode_attend_workspace(B, h, dh, max_seq, device):
+    """Zeroed scratch for decode_attend (per-chunk partials + arrival counters); allocate once per session."""
+    n = L.load().mt_decode_attend_workspace_bytes(B, h, dh, max_seq) + 16
+    return torch.zeros(n, dtype=torch.uint8, device=device)
+
+
+def decode_attend(q, q_stride_b, kcache, vcache, E, pad_bits, out, t_dev, B, h, dh, max_seq, ws, append=False):
+    """append=True: ``q`` is the fused projection row [3, h, dh]; K / V of position t are stored by this launch."""
     L.check(L.load().mt_decode_attend(_ptr(q), q_stride_b, _ptr(kcache), _ptr(vcache), _ptr(E),
                                       _ptr(pad_bits), _ptr(out), _ptr(t_dev), B, h, dh, max_seq, dt(q),
-                                      _stream()), "decode_attend")
+                                      int(append), _ptr(ws), ws.numel(), _stream()), "decode_attend")
 
 
 def decode_sample(logits, u, ids, t_dev, prior_len, temperature, top_k, greedy):

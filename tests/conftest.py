@@ -32,3 +32,13 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _restore_runtime_config():
+    """Tests overwrite ``config.pad_token`` / ``threshold_len`` like the reference's callers do; put the
+    module defaults back afterwards so test order does not matter."""
+    import musicgeneration_b200 as mtb
+    saved = (mtb.config.pad_token, mtb.config.threshold_len)
+    yield
+    mtb.config.pad_token, mtb.config.threshold_len = saved

@@ -187,6 +187,12 @@ int mt_decode_sample(const float* logits, const float* u, int32_t* ids, int64_t 
                      int32_t prior_len, int64_t B, int64_t V, float temperature, int32_t top_k, int greedy,
                      void* stream);
 int mt_decode_advance(int32_t* t_dev, void* stream);
+/* Programmatic dependent launch for the kernels of a decode step (strip GEMM, residual+LayerNorm,
+ * mt_decode_*): while enabled, each of them may start launching before its predecessor in the
+ * stream has drained and waits for it on the device (griddepcontrol), which hides most of the
+ * per-launch latency of the ~46 dependent kernels of a step.  Process-wide switch; leave it off
+ * outside a decode step. */
+int mt_decode_chain(int enable);
 
 #ifdef __cplusplus
 }

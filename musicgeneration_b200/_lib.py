@@ -56,6 +56,7 @@ SIGNATURES = {
     "mt_decode_attend": (_int, [_p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _int, _int, _p, C.c_size_t, _p]),
     "mt_decode_sample": (_int, [_p, _p, _p, _i64, _p, _i32, _i64, _i64, _f, _i32, _int, _p]),
     "mt_decode_advance": (_int, [_p, _p]),
+    "mt_decode_chain": (_int, [_int]),
 }
 
 _lib = None

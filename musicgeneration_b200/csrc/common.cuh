@@ -25,6 +25,27 @@ int check_launch(const char* what);  // cudaGetLastError -> code
     }                                           \
   } while (0)
 
+// Programmatic dependent launch (decode step: ~46 dependent, few-microsecond kernels per event).
+// A kernel launched through launch_chain() while chaining is on may start before its predecessor in
+// the stream has finished; chain_prologue() at its very top lets ITS successor start launching and
+// then blocks until the predecessor grid has completed and flushed.  Both are no-ops for a plain
+// launch, so the same kernels serve the training path unchanged.
+bool chain_enabled();
+__device__ __forceinline__ void chain_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline void launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = chain_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 inline int dtype_size(int dt) { return dt == MT_F32 ? 4 : 2; }
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -139,6 +139,7 @@ rga_decode_split_kernel(const T* __restrict__ q, T* kc, T* vc,
   __shared__ float wred[8];
   __shared__ uint8_t spad[DEC_CHUNK];
   __shared__ int s_last;
+  chain_prologue();
   const int t = *t_dev;
   const int tid = threadIdx.x, hh = blockIdx.x, b = blockIdx.y, sp = blockIdx.z;
   const int j0 = sp * DEC_CHUNK;
@@ -282,6 +283,7 @@ decode_embed_kernel(const int32_t* __restrict__ ids, int64_t ld_ids, const int32
                     const float* __restrict__ emb, const float* __restrict__ pe, float* __restrict__ out,
                     TL* __restrict__ out_lp, int B, int d4, int V, float scale, int32_t pad_token,
                     uint8_t* __restrict__ pad_bits, int64_t max_seq) {
+  chain_prologue();
   const int e4 = blockIdx.x * blockDim.x + threadIdx.x;
   if (e4 >= B * d4) return;
   const int b = e4 / d4, c4 = e4 - b * d4;
@@ -298,7 +300,7 @@ decode_embed_kernel(const int32_t* __restrict__ ids, int64_t ld_ids, const int32
   if (out_lp) store4<TL>(out_lp + (int64_t)e4 * 4, r);
 }
 
-__global__ void decode_advance_kernel(int32_t* t_dev) { *t_dev += 1; }
+__global__ void decode_advance_kernel(int32_t* t_dev) { chain_prologue(); *t_dev += 1; }
 
 // one block per sequence.  z = logits/T; greedy: first arg-max.  Otherwise keep the top_k
 // values (ties: lower id first), softmax, inverse CDF over ascending ids with uniform u.
@@ -313,6 +315,7 @@ sample_kernel(const float* __restrict__ logits, const float* __restrict__ u, int
   __shared__ int ri[8];
   __shared__ float s_thr_v;
   __shared__ int s_thr_i;
+  chain_prologue();
   const int tid = threadIdx.x, b = blockIdx.x;
   if (t_dev) {
     // graph-replayed decode: `out` is the id matrix [B, ld_ids]; the event drawn from position t's
@@ -454,7 +457,7 @@ static int sample_impl(const float* logits, const float* u, int32_t* ids_out, in
     cudaError_t e = cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("sample: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
   }
-  sample_kernel<<<(unsigned)B, 256, smem, as_stream(stream)>>>(logits, u, ids_out, (int)V, temperature, top_k, greedy, t_dev, ld_ids, prior_len, (int)B);
+  launch_chain(sample_kernel, dim3((unsigned)B), dim3(256), smem, as_stream(stream), logits, u, ids_out, (int)V, temperature, (int)top_k, greedy, t_dev, ld_ids, (int)prior_len, (int)B);
   return check_launch("sample");
 }
 
@@ -471,7 +474,7 @@ int mt_decode_embed(const int32_t* ids, int64_t ld_ids, const int32_t* t_dev, co
   if (!out_lp) lp_dtype = MT_F32;
   int64_t n4 = B * (d / 4);
   MT_DISPATCH_F32_BF16(lp_dtype, TL,
-      (decode_embed_kernel<TL><<<(unsigned)((n4 + 255) / 256), 256, 0, as_stream(stream)>>>(ids, ld_ids, t_dev, emb, pe, out_f32, (TL*)out_lp, (int)B, (int)(d / 4), (int)V, scale, pad_token, pad_bits, max_seq)));
+      (launch_chain(decode_embed_kernel<TL>, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, as_stream(stream), ids, ld_ids, t_dev, emb, pe, out_f32, (TL*)out_lp, (int)B, (int)(d / 4), (int)V, scale, pad_token, pad_bits, max_seq)));
   return check_launch("decode_embed");
 }
 
@@ -507,7 +510,7 @@ int mt_decode_attend(const void* q, int64_t q_stride_b, void* kcache, void* vcac
   dim3 grid((unsigned)h, (unsigned)B, (unsigned)nsplit);
   const float isd = 1.f / sqrtf((float)dh);
 #define MT_LAUNCH_DECS(T, DHC) \
-  rga_decode_split_kernel<T, DHC><<<grid, 128, 0, as_stream(stream)>>>((const T*)q, (T*)kcache, (T*)vcache, (const T*)E, pad_bits, (T*)out, q_stride_b, (int)h, (int)max_seq, t_dev, isd, counters, part, nsplit, append);
+  launch_chain(rga_decode_split_kernel<T, DHC>, grid, dim3(128), 0, as_stream(stream), (const T*)q, (T*)kcache, (T*)vcache, (const T*)E, pad_bits, (T*)out, q_stride_b, (int)h, (int)max_seq, t_dev, isd, counters, part, nsplit, append);
   MT_DISPATCH_F32_BF16(dtype, T, {
     if (dh == 32) { MT_LAUNCH_DECS(T, 32) }
     else if (dh == 64) { MT_LAUNCH_DECS(T, 64) }
@@ -527,7 +530,7 @@ int mt_decode_sample(const float* logits, const float* u, int32_t* ids, int64_t 
 
 int mt_decode_advance(int32_t* t_dev, void* stream) {
   MT_REQUIRE(t_dev, "decode_advance: null step index");
-  decode_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(t_dev);
+  launch_chain(decode_advance_kernel, dim3(1), dim3(1), 0, as_stream(stream), t_dev);
   return check_launch("decode_advance");
 }
 

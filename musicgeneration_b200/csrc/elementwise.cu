@@ -22,6 +22,9 @@ int check_launch(const char* what) {
   }
   return 0;
 }
+static bool g_chain = false;
+bool chain_enabled() { return g_chain; }
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -102,6 +105,7 @@ add_ln_fwd_kernel(const TA* __restrict__ a, const float* __restrict__ resid,
                   float* __restrict__ out, TL* __restrict__ out_lp, float* __restrict__ mean,
                   float* __restrict__ rstd, int64_t T, int d, float eps, float p, float inv_keep,
                   uint64_t seed, uint64_t site) {
+  chain_prologue();
   const int lane = threadIdx.x & 31;
   const int d4 = d >> 2;
   int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -539,6 +543,7 @@ using namespace mt;
 extern "C" {
 
 int mt_version(void) { return 100; }
+int mt_decode_chain(int enable) { g_chain = enable != 0; return 0; }
 const char* mt_last_error(void) { return mt::g_err; }
 int mt_device_ok(void) {
   int dev = 0, major = 0;
@@ -596,7 +601,7 @@ int mt_add_ln_fwd(const void* a, int a_dtype, const float* resid, const float* g
   int d4 = (int)(d / 4);
   if (!out_lp) lp_dtype = MT_F32;
   MT_DISPATCH_F32_BF16(a_dtype, TA, MT_DISPATCH_F32_BF16(lp_dtype, TL, MT_LN_NV_DISPATCH(d4, NVC,
-      (add_ln_fwd_kernel<TA, TL, NVC><<<grid, 256, 0, as_stream(stream)>>>((const TA*)a, resid, gamma, beta, out_f32, (TL*)out_lp, mean, rstd, T, (int)d, eps, p_drop, inv_keep, seed, site)))));
+      (launch_chain(add_ln_fwd_kernel<TA, TL, NVC>, dim3(grid), dim3(256), 0, as_stream(stream), (const TA*)a, resid, gamma, beta, out_f32, (TL*)out_lp, mean, rstd, T, (int)d, eps, p_drop, inv_keep, seed, site)))));
   return check_launch("add_ln_fwd");
 }
 

@@ -46,6 +46,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 template <int MT>       // MT = number of 16-row tiles (1..4)
 __global__ void __launch_bounds__(SK_THREADS)
 gemm_skinny_kernel(const SkinnyParams p) {
+  chain_prologue();
   extern __shared__ __align__(16) uint8_t smem[];
   const int pitch = p.K + SK_PAD;                                   // elements
   __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem);       // [MT*16][pitch]
@@ -150,7 +151,7 @@ int gemm_skinny(const void* A, const void* B, void* C, const float* bias, int64_
       if (e != cudaSuccess) { set_error("gemm_skinny: smem attribute: %s", cudaGetErrorString(e)); return (int)e; } \
       attr = smem;                                                                                              \
     }                                                                                                           \
-    kern<<<grid, SK_THREADS, smem, st>>>(p);                                                                    \
+    launch_chain(kern, dim3(grid), dim3(SK_THREADS), smem, st, p);                                                                    \
   }
   switch (p.mtiles) {
     case 1: MT_SKINNY_LAUNCH(1) break;

@@ -9,6 +9,7 @@ reference loop (no mask, sliding window) is kept as ``generate_literal`` (SURVEY
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional
 
 import torch
@@ -228,8 +229,13 @@ class _DecodeSession:
             self.t_dev.zero_()
         torch.cuda.current_stream().wait_stream(side)
         graph = torch.cuda.CUDAGraph()
+        chain = os.environ.get("MT_DECODE_CHAIN", "1") != "0"
         with torch.cuda.graph(graph, stream=side):
-            self._graph_step(*args)
+            ops.decode_chain(chain)          # kernels of the captured step launch programmatically dependent
+            try:
+                self._graph_step(*args)
+            finally:
+                ops.decode_chain(False)
         self.t_dev.zero_()
         for _ in range(n_steps):
             graph.replay()

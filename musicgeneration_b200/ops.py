@@ -241,5 +241,10 @@ def decode_sample(logits, u, ids, t_dev, prior_len, temperature, top_k, greedy):
             "decode_sample")
 
 
+def decode_chain(enable: bool):
+    """Programmatic dependent launch for the kernels of a decode step (see include/mt_b200.h)."""
+    L.load().mt_decode_chain(int(enable))
+
+
 def decode_advance(t_dev):
     L.check(L.load().mt_decode_advance(_ptr(t_dev), _stream()), "decode_advance")

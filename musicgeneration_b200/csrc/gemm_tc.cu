@@ -21,13 +21,21 @@ namespace mt {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
-constexpr int TILE_BYTES = BM * BK * 2;          // 16 KB per operand tile
+// Tile shapes: 128 x 128 (3-stage ring) or 128 x 256 (2-stage ring, one N = 256 MMA per k-step).
+// With K of only 256..512 the kernel is bound by L2 -> shared-memory traffic, not by the tensor pipe:
+// a 128 x 128 x 64 block loads 32 KB for 2.1 MFLOP (64 FLOP/B), a 128 x 256 x 64 block 48 KB for
+// 4.2 MFLOP (87 FLOP/B).  Both shapes fit two CTAs per SM (<= 100 KB of shared memory, <= 256 TMEM columns).
+constexpr int BM = 128, BK = 64;
+constexpr int TILE_BYTES = BM * BK * 2;          // 16 KB: one [128 x 64] 16-bit tile (A stage; B stage per 128 columns)
 constexpr int TC_THREADS = 192;
-constexpr int TMEM_COLS = 128;
 constexpr int EPI_PITCH = 132;          // floats per staged row (== 4 mod 32: conflict-free 128-bit stores)
-static_assert(BM * EPI_PITCH * 4 <= 2 * STAGES * TILE_BYTES, "epilogue staging aliases the operand ring");
-constexpr size_t SMEM_BYTES = 2 * STAGES * TILE_BYTES + 256 + 1024;
+template <int BN_> struct Shape {
+  static constexpr int STAGES = (BN_ == 128) ? 3 : 2;
+  static constexpr int TILE_B = BN_ * BK * 2;
+  static constexpr int RING = STAGES * (TILE_BYTES + TILE_B);
+  static constexpr size_t SMEM = RING + 256 + 1024;
+  static_assert(BM * EPI_PITCH * 4 <= RING, "epilogue staging aliases the operand ring");
+};
 
 struct TcGemmParams {
   void* C;
@@ -96,15 +104,18 @@ __device__ __forceinline__ void epilogue_quad(const TcGemmParams& p, int64_t row
   }
 }
 
-template <int A_MN, int B_MN>
+template <int A_MN, int B_MN, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcGemmParams p, const int fmt) {
+  constexpr int STAGES = Shape<BN>::STAGES;
+  constexpr int TILE_B = Shape<BN>::TILE_B;
+  constexpr int TMEM_COLS = BN;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((tc::smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * TILE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * TILE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * TILE_B);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
@@ -138,21 +149,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         tc::mbar_wait(&empty[s], ph ^ 1);
-        tc::mbar_arrive_expect_tx(&full[s], 2 * TILE_BYTES);
+        tc::mbar_arrive_expect_tx(&full[s], TILE_BYTES + TILE_B);
         const int k = (int)(kbeg + (int64_t)kb * BK);
         uint8_t* a = sA + s * TILE_BYTES;
-        uint8_t* b = sB + s * TILE_BYTES;
+        uint8_t* b = sB + s * TILE_B;
         if (A_MN) {
           tc::tma_load_2d(a, &tmA, &full[s], m0, k);
           tc::tma_load_2d(a + TILE_BYTES / 2, &tmA, &full[s], m0 + 64, k);
         } else {
           tc::tma_load_2d(a, &tmA, &full[s], k, m0);
         }
-        if (B_MN) {
-          tc::tma_load_2d(b, &tmB, &full[s], n0, k);
-          tc::tma_load_2d(b + TILE_BYTES / 2, &tmB, &full[s], n0 + 64, k);
+        if (B_MN) {          // 64-column groups of the [K, N] matrix, 8 KB apart
+#pragma unroll
+          for (int g = 0; g < BN / 64; ++g) tc::tma_load_2d(b + g * (TILE_BYTES / 2), &tmB, &full[s], n0 + 64 * g, k);
         } else {
-          tc::tma_load_2d(b, &tmB, &full[s], k, n0);
+          tc::tma_load_2d(b, &tmB, &full[s], k, n0);      // one [BN x 64] box
         }
       }
     }
@@ -170,7 +181,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // MN-major: 16 k-rows of 128 B = 2048 B; the two 64-wide MN halves are 8192 B apart.
         // One descriptor per operand and stage; a k-step is an add on its 16-byte address field.
         const uint64_t ad0 = (A_MN ? ad_mn : ad_k) + (uint64_t)s * (TILE_BYTES >> 4);
-        const uint64_t bd0 = (B_MN ? bd_mn : bd_k) + (uint64_t)s * (TILE_BYTES >> 4);
+        const uint64_t bd0 = (B_MN ? bd_mn : bd_k) + (uint64_t)s * (TILE_B >> 4);
 #pragma unroll
         for (int k4 = 0; k4 < BK / 16; ++k4)
           tc::umma_f16(tmem_base, ad0 + (A_MN ? 128 : 2) * k4, bd0 + (B_MN ? 128 : 2) * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
@@ -188,36 +199,187 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc::mbar_wait(tmem_full, 0);
     tc::tc_fence_after();
     float* stage = reinterpret_cast<float*>(smem);            // [128][EPI_PITCH]
-    {
-      float* srow = stage + (q * 32 + lane) * EPI_PITCH;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<uint4*>(srow + c * 32 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-      }
-    }
-    tc::tc_fence_before();
-    tc::named_bar_sync(1, 128);
     const int et = threadIdx.x - 64;              // 0..127
-    const int col = (et & 31) * 4;                // 4 consecutive columns of the tile
-    const int64_t n = (int64_t)n0 + col;
+    const int col = (et & 31) * 4;                // 4 consecutive columns of a 128-column half
+#pragma unroll 1
+    for (int hn = 0; hn < BN / 128; ++hn) {
+      if (hn > 0) tc::named_bar_sync(1, 128);     // the previous half has been read out of the staging rows
+      {
+        float* srow = stage + (q * 32 + lane) * EPI_PITCH;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hn * 128 + c * 32), r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(srow + c * 32 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        }
+      }
+      tc::tc_fence_before();
+      tc::named_bar_sync(1, 128);
+      const int64_t n = (int64_t)n0 + hn * 128 + col;
 #pragma unroll 4
-    for (int r = et >> 5; r < BM; r += 4) {
-      const int64_t row = (int64_t)m0 + r;
-      if (row >= p.M || n >= p.N) continue;
-      const float4 acc = *reinterpret_cast<const float4*>(stage + r * EPI_PITCH + col);
-      float o[4] = {acc.x, acc.y, acc.z, acc.w};
-      epilogue_quad(p, row, n, o);
+      for (int r = et >> 5; r < BM; r += 4) {
+        const int64_t row = (int64_t)m0 + r;
+        if (row >= p.M || n >= p.N) continue;
+        const float4 acc = *reinterpret_cast<const float4*>(stage + r * EPI_PITCH + col);
+        float o[4] = {acc.x, acc.y, acc.z, acc.w};
+        epilogue_quad(p, row, n, o);
+      }
     }
   }
   __syncthreads();
   if (warp == 1) {
     tc::tc_fence_after();
     tc::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Persistent variant (A K-major: x.W^T and dgrad, no split-K).  One CTA per SM walks output tiles
+// (n fastest, so concurrently running CTAs share the A panel in L2); the operand ring and the
+// barriers run straight through tile boundaries, TWO accumulators live in TMEM, and eight epilogue
+// warps drain tile i (TMEM -> registers -> per-warp staging rows -> 128-byte row segments in global
+// memory, bias / ReLU / residual / ReLU-mask applied on the way) while the MMA warp already fills the
+// other accumulator with tile i+1.  In the one-tile-per-CTA kernel above the main loop and the
+// epilogue of a CTA are serial (ncu: 47 % of warp samples are warps parked at a barrier or at
+// EXIT waiting for the other phase).
+// ---------------------------------------------------------------------------------------
+constexpr int PS_THREADS = 320;                 // TMA warp, MMA warp, 8 epilogue warps
+constexpr int PS_STG_WORDS = 36;                // staging row pitch: 32 columns + 4 (16-byte stores conflict-free)
+constexpr int PS_STG_BYTES = 32 * PS_STG_WORDS * 4;
+template <int BN_> struct PShape {
+  static constexpr int STAGES = (BN_ == 256) ? 3 : 5;
+  static constexpr int TILE_B = BN_ * BK * 2;
+  static constexpr int RING = STAGES * (TILE_BYTES + TILE_B);
+  static constexpr size_t SMEM = RING + 8 * PS_STG_BYTES + 256 + 1024;
+  static_assert(SMEM <= 232448, "shared memory budget");
+};
+
+template <int B_MN, int BN>
+__global__ void __launch_bounds__(PS_THREADS, 1)
+gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const TcGemmParams p, const int fmt, const int tiles_n, const int num_tiles) {
+  constexpr int STAGES = PShape<BN>::STAGES;
+  constexpr int TILE_B = PShape<BN>::TILE_B;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((tc::smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * TILE_BYTES;
+  uint8_t* stg = sB + STAGES * TILE_B;
+  uint64_t* full = reinterpret_cast<uint64_t*>(stg + 8 * PS_STG_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;      // [2]
+  uint64_t* acc_empty = acc_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (int)((p.K + BK - 1) / BK);
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmA);
+    tc::tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(&acc_full[b], 1); tc::mbar_init(&acc_empty[b], 256); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 2 * BN);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int g = 0;                                  // k-blocks issued so far (over all tiles)
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const int s = g % STAGES;
+          tc::mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(&full[s], TILE_BYTES + TILE_B);
+          const int k = kb * BK;
+          uint8_t* b = sB + s * TILE_B;
+          tc::tma_load_2d(sA + s * TILE_BYTES, &tmA, &full[s], k, m0);
+          if (B_MN) {
+#pragma unroll
+            for (int gq = 0; gq < BN / 64; ++gq) tc::tma_load_2d(b + gq * (TILE_BYTES / 2), &tmB, &full[s], n0 + 64 * gq, k);
+          } else {
+            tc::tma_load_2d(b, &tmB, &full[s], k, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc(BM, BN, fmt, fmt, 0, B_MN);
+      const uint64_t ad_k = tc::make_sdesc(tc::smem_u32(sA), 16, 1024);
+      const uint64_t bd_k = tc::make_sdesc(tc::smem_u32(sB), 16, 1024), bd_mn = tc::make_sdesc(tc::smem_u32(sB), TILE_BYTES / 2, 1024);
+      int g = 0, i = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
+        const int buf = i & 1;
+        tc::mbar_wait(&acc_empty[buf], ((i >> 1) & 1) ^ 1);       // the epilogue has read this accumulator
+        tc::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const int s = g % STAGES;
+          tc::mbar_wait(&full[s], (g / STAGES) & 1);
+          tc::tc_fence_after();
+          const uint64_t ad0 = ad_k + (uint64_t)s * (TILE_BYTES >> 4);
+          const uint64_t bd0 = (B_MN ? bd_mn : bd_k) + (uint64_t)s * (TILE_B >> 4);
+#pragma unroll
+          for (int k4 = 0; k4 < BK / 16; ++k4)
+            tc::umma_f16(d_tmem, ad0 + 2 * k4, bd0 + (B_MN ? 128 : 2) * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+          tc::umma_commit(&empty[s]);
+        }
+        tc::umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // epilogue warps 2..9: TMEM quadrant = warp % 4 (hardware rule), column half = first / second set of four
+    const int ew = warp - 2, q = warp & 3, chalf = ew >> 2;
+    constexpr int CPW = BN / 2;                   // columns per warp
+    float* stage = reinterpret_cast<float*>(stg + ew * PS_STG_BYTES);
+    const int piece = lane & 7, rsub = lane >> 3;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      const int buf = i & 1;
+      tc::mbar_wait(&acc_full[buf], (i >> 1) & 1);
+      tc::tc_fence_after();
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + chalf * CPW);
+#pragma unroll 1
+      for (int c = 0; c < CPW / 32; ++c) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32(t0 + (uint32_t)(c * 32), r);
+        tc::tmem_ld_wait();
+        if (c == CPW / 32 - 1) {                  // last read of this accumulator: hand it back to the MMA warp
+          tc::tc_fence_before();
+          tc::mbar_arrive(&acc_empty[buf]);
+        }
+        __syncwarp();                             // the previous chunk's rows have been read by every lane
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(stage + lane * PS_STG_WORDS + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        __syncwarp();
+#pragma unroll 2
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + rsub;
+          const int64_t row = (int64_t)m0 + q * 32 + rr;
+          const int64_t n = (int64_t)n0 + chalf * CPW + c * 32 + piece * 4;
+          if (row >= p.M || n >= p.N) continue;
+          const float4 acc = *reinterpret_cast<const float4*>(stage + rr * PS_STG_WORDS + piece * 4);
+          float o[4] = {acc.x, acc.y, acc.z, acc.w};
+          epilogue_quad(p, row, n, o);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -238,7 +400,7 @@ __global__ void __launch_bounds__(256) tc_splitk_fold_kernel(TcGemmParams p) {
 }
 
 int tc_splits(int64_t M, int64_t N, int64_t K) {
-  int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  int64_t tiles = ((M + BM - 1) / BM) * ((N + 127) / 128);
   if (tiles >= sm_count() || K < 2048) return 1;
   int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;
   int64_t maxs = K / 512;
@@ -363,6 +525,10 @@ int gemm_tc(const void* A, const void* B, void* C, const float* bias, const floa
   if (a_mn) rc = tc::make_tmap_2d(&tmA, A, K, M, lda, 64, BK);
   else rc = tc::make_tmap_2d(&tmA, A, M, K, lda, BK, BM);
   if (rc) return rc;
+  // 128 x 256 tiles when the output is at least 256 columns wide and a plain (no split-K) product
+  const int splits0 = tc_splits(M, N, K);
+  const bool wide = (N % 256 == 0) && splits0 == 1 && !a_mn;
+  const int BN = wide ? 256 : 128;
   if (b_mn) rc = tc::make_tmap_2d(&tmB, B, K, N, ldb, 64, BK);
   else rc = tc::make_tmap_2d(&tmB, B, N, K, ldb, BK, BN);
   if (rc) return rc;
@@ -385,21 +551,42 @@ int gemm_tc(const void* A, const void* B, void* C, const float* bias, const floa
   p.part = reinterpret_cast<float*>(workspace);
   const int fmt = (in_dtype == MT_BF16) ? 1 : 0;
 
-  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)p.splits);
   cudaError_t e = cudaSuccess;
-#define MT_TC_LAUNCH(AM, BMJ)                                                                         \
+  if (!a_mn && p.splits == 1 && M * N >= (int64_t)BM * 128 * sm_count()) {
+    // persistent kernel: enough tiles to give every SM several
+    const int tiles_n = (int)((N + BN - 1) / BN), tiles_m = (int)((M + BM - 1) / BM);
+    const int num_tiles = tiles_n * tiles_m;
+    const unsigned pgrid = (unsigned)(num_tiles < sm_count() ? num_tiles : sm_count());
+#define MT_PS_LAUNCH(BMJ, BNC)                                                                        \
+    {                                                                                                 \
+      auto kern = gemm_tc_persist_kernel<BMJ, BNC>;                                                   \
+      static bool attr_done = false;                                                                  \
+      if (!attr_done) {                                                                               \
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PShape<BNC>::SMEM); \
+        attr_done = (e == cudaSuccess);                                                               \
+      }                                                                                               \
+      if (e == cudaSuccess) kern<<<pgrid, PS_THREADS, PShape<BNC>::SMEM, stream>>>(tmA, tmB, p, fmt, tiles_n, num_tiles); \
+    }
+    if (b_mn) { if (wide) MT_PS_LAUNCH(1, 256) else MT_PS_LAUNCH(1, 128) }
+    else { if (wide) MT_PS_LAUNCH(0, 256) else MT_PS_LAUNCH(0, 128) }
+#undef MT_PS_LAUNCH
+    if (e != cudaSuccess) { set_error("gemm_tc: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+    return check_launch("gemm_tc_persist");
+  }
+  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)p.splits);
+#define MT_TC_LAUNCH(AM, BMJ, BNC)                                                                    \
   {                                                                                                   \
-    auto kern = gemm_tc_kernel<AM, BMJ>;                                                              \
+    auto kern = gemm_tc_kernel<AM, BMJ, BNC>;                                                         \
     static bool attr_done = false;                                                                    \
     if (!attr_done) {                                                                                 \
-      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);   \
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape<BNC>::SMEM); \
       attr_done = (e == cudaSuccess);                                                                 \
     }                                                                                                 \
-    if (e == cudaSuccess) kern<<<grid, TC_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p, fmt);           \
+    if (e == cudaSuccess) kern<<<grid, TC_THREADS, Shape<BNC>::SMEM, stream>>>(tmA, tmB, p, fmt);     \
   }
-  if (!a_mn && !b_mn) MT_TC_LAUNCH(0, 0)
-  else if (!a_mn && b_mn) MT_TC_LAUNCH(0, 1)
-  else if (a_mn && b_mn) MT_TC_LAUNCH(1, 1)
+  if (!a_mn && !b_mn) { if (wide) MT_TC_LAUNCH(0, 0, 256) else MT_TC_LAUNCH(0, 0, 128) }
+  else if (!a_mn && b_mn) { if (wide) MT_TC_LAUNCH(0, 1, 256) else MT_TC_LAUNCH(0, 1, 128) }
+  else if (a_mn && b_mn) MT_TC_LAUNCH(1, 1, 128)
   else { set_error("gemm_tc: unsupported operand majors"); return MT_E_UNSUPPORTED; }
 #undef MT_TC_LAUNCH
   if (e != cudaSuccess) { set_error("gemm_tc: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }

@@ -39,16 +39,15 @@ constexpr int OFF_Q = 0;
 constexpr int OFF_K = OFF_Q + TILE;            // 2 stages
 constexpr int OFF_V = OFF_K + 2 * TILE;        // 2 stages
 constexpr int OFF_E = OFF_V + 2 * TILE;        // 2 stages: the new "hi" block of each step
-constexpr int OFF_P = OFF_E + 2 * TILE;        // 2 K-subtiles of [128 x 64] 16-bit
-constexpr int OFF_ELO = OFF_P;                 // "lo" block of the first step: dead before the first P is written
-constexpr int OFF_SCR = OFF_P + 2 * TILE;
+constexpr int OFF_ELO = OFF_E + 2 * TILE;      // "lo" block of the first step only
+constexpr int OFF_SCR = OFF_ELO + TILE;
 constexpr int OFF_XCH = OFF_SCR + FW_SCR_BYTES;   // [2 parities][4 quarters][128] floats: row max / row sum exchange
 constexpr int OFF_BAR = OFF_XCH + 2 * 4 * TT * 4;
 constexpr int FWD_SMEM = OFF_BAR + 256 + 1024;
 static_assert(FWD_SMEM <= 232448, "forward kernel exceeds the 227 KB shared-memory limit");
 
 // TMEM columns
-constexpr uint32_t TM_S = 0, TM_G0 = 128, TM_G1 = 256, TM_O = 384;
+constexpr uint32_t TM_S = 0, TM_G0 = 128, TM_G1 = 256, TM_O = 384, TM_P = 448;   // P: 128 x 128 16-bit = 64 columns
 
 // O is rescaled only when the running row maximum grows by more than 2^RESCALE_LOG2: P stays
 // below 2^8 (exact in the fp32 row sums, same relative precision in the 16-bit operand)
@@ -139,7 +138,6 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const uint64_t kd0 = tc::make_sdesc(tc::smem_u32(smem + OFF_K), 16, 1024);
       const uint64_t ed0 = tc::make_sdesc(tc::smem_u32(smem + OFF_E), 16, 1024);
       const uint64_t elod = tc::make_sdesc(tc::smem_u32(smem + OFF_ELO), 16, 1024);
-      const uint64_t pd0 = tc::make_sdesc(tc::smem_u32(smem + OFF_P), 16, 1024);
       const uint64_t vd0 = tc::make_sdesc(tc::smem_u32(smem + OFF_V), 1024, 1024);
       auto issue_s = [&](int jt) {
         const uint64_t so = (uint64_t)(jt & 1) * (TILE >> 4);
@@ -171,8 +169,8 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tc::tc_fence_after();
         const uint64_t vd = vd0 + (uint64_t)(jt & 1) * (TILE >> 4);
 #pragma unroll
-        for (int k8 = 0; k8 < TT / 16; ++k8)     // P sub-tile k8>>2, 16 keys = 32 B inside its rows; V: 16 key rows = 2048 B
-          tc::umma_f16(tmem + TM_O, pd0 + (k8 >> 2) * (TILE >> 4) + 2 * (k8 & 3), vd + 128 * k8, idesc_o, (jt | k8) != 0);
+        for (int k8 = 0; k8 < TT / 16; ++k8)     // P stays in TMEM (A operand): 16 keys = 8 columns; V: 16 key rows = 2048 B
+          tc::umma_f16_ts(tmem + TM_O, tmem + TM_P + 8 * k8, vd + 128 * k8, idesc_o, (jt | k8) != 0);
         tc::umma_commit(&kv_empty[jt & 1]);
         tc::umma_commit(o_done);
       }
@@ -294,13 +292,10 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           tc::tmem_st_wait();
         }
       }
-      // ---- P (16-bit) into the K-major 128B-swizzled operand layout: sub-tile qt>>1, chunks 4*(qt&1)..+3
-      uint8_t* ptile = smem + OFF_P + (qt >> 1) * TILE;
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<uint4*>(ptile + swz_chunk(a, (qt & 1) * 4 + c)) =
-            make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-      tc::fence_proxy_async();
+      // ---- P (16-bit pairs) into the TMEM A-operand of the P.V MMA: row = lane, this thread's 32
+      // key columns are 16 packed columns (no shared-memory round trip for P)
+      tc::tmem_st_32x16(tmem + TM_P + lane_base + qt * 16, pk);
+      tc::tmem_st_wait();
       tc::tc_fence_before();
       tc::mbar_arrive(p_full);
     }

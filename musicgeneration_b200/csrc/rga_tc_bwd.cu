@@ -20,6 +20,8 @@
 #include "ops.cuh"
 #include "rga_tc_common.cuh"
 
+#include <stdlib.h>
+
 namespace mt {
 
 using namespace rga;
@@ -503,6 +505,8 @@ int rga_bwd2_dkv(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tm
                  const CUtensorMap& tmDO, const CUtensorMap& tmE, cudaStream_t st);      // rga_tc_bwd2.cu
 int rga_bwd2_de(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                 const CUtensorMap& tmDO, const CUtensorMap& tmE, cudaStream_t st);
+int rga_bwd2_dq(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                const CUtensorMap& tmDO, const CUtensorMap& tmE, cudaStream_t st);
 
 bool rga_bwd_tc_supported(const RgaArgs& a, int dh, int dtype) {
   if (dh != DHC || dtype != MT_BF16 || !a.causal) return false;
@@ -533,7 +537,10 @@ int rga_bwd_tc(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
   dim3 grid(a.h, a.B, p.nT);
   // dK/dV and dE: second-generation two-group pipeline (rga_tc_bwd2.cu); dQ: the role kernel above
   if ((rc = rga_bwd2_dkv(a, tmQ, tmK, tmV, tmDO, tmE, st))) return rc;
-  if ((rc = launch_mode<MODE_DQ>(tmQ, tmK, tmV, tmDO, tmE, p, grid, st))) return rc;
+  // MT_RGA_DQ=1: the first-generation dQ role (kept for A/B timing)
+  static const bool old_dq = getenv("MT_RGA_DQ") != nullptr && getenv("MT_RGA_DQ")[0] == '1';
+  if (old_dq) { if ((rc = launch_mode<MODE_DQ>(tmQ, tmK, tmV, tmDO, tmE, p, grid, st))) return rc; }
+  else if ((rc = rga_bwd2_dq(a, tmQ, tmK, tmV, tmDO, tmE, st))) return rc;
   return rga_bwd2_de(a, tmQ, tmK, tmV, tmDO, tmE, st);
 }
 

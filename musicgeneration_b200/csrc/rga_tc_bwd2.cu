@@ -25,7 +25,7 @@ using namespace rga;
 
 namespace {
 
-enum { R_DKV = 0, R_DE = 2 };
+enum { R_DKV = 0, R_DQ = 1, R_DE = 2 };
 
 constexpr int B2_GROUP = 256;                       // threads of one math group
 constexpr int B2_THREADS = 2 * B2_GROUP + 64;       // A, B, TMA warp, MMA warp
@@ -45,15 +45,24 @@ template <> struct Lay2<R_DE> {      // E_lo,E_hi resident; Q x 2; K; {dO, V} (d
   static constexpr int ELO = 0, EHI = TILE, Q0 = 2 * TILE, K = 4 * TILE, DOV = 5 * TILE, DG = 7 * TILE;
   static constexpr int SCR = 11 * TILE, BAR = SCR + B2_SCR_BYTES;
 };
+template <> struct Lay2<R_DQ> {      // Q,dO resident; K x 2; V; E ring x 3 (one new block per step, as in the forward); dG
+  static constexpr int Q = 0, DO = TILE, K0 = 2 * TILE, V = 4 * TILE, E0 = 5 * TILE, DG = 8 * TILE;
+  static constexpr int SCR = 12 * TILE, BAR = SCR + B2_SCR_BYTES;
+};
 template <int ROLE> constexpr int smem2_bytes() { return Lay2<ROLE>::BAR + 512; }
-static_assert(smem2_bytes<R_DKV>() <= 232448 && smem2_bytes<R_DE>() <= 232448, "shared memory budget");
+static_assert(smem2_bytes<R_DKV>() <= 232448 && smem2_bytes<R_DE>() <= 232448 && smem2_bytes<R_DQ>() <= 232448,
+              "shared memory budget");
+// dQ role: the G blocks form a ring (G_hi of step n is G_lo of step n+1), dQ accumulates in 64 columns
+// and P / dS (bf16 pairs, 64 columns) never leave TMEM: group A stores P there, group B turns it into
+// dS in place, and the dS.K MMA reads it as its A operand
+constexpr uint32_t TM_DQ = 384, TM_PS = 448;
 
 // barrier slots (uint64 each)
 enum { BR_RES = 0, BR_QF = 1, BR_QE = 3, BR_KF = 5, BR_KE = 6, BR_VF = 7, BR_SFULL = 8, BR_SGFREE = 9,
        BR_DPFULL = 10, BR_DPFREE = 11, BR_PREADY = 12, BR_DSREADY = 13, BR_STEPDONE = 14, BR_TMEM = 15, BR_SPAD = 16 };
 
 struct Bwd2Params {
-  void* dk; void* dv;                    // 16-bit, k/v addressing
+  void* dk; void* dv; void* dq;          // 16-bit, q/k/v addressing
   int64_t sb, sl, sh;
   float* dE;
   const float* lse; const float* delta;
@@ -80,6 +89,7 @@ __device__ __forceinline__ int num_steps2(const Bwd2Params& p, int& bh0) {
   // dimension, so CTAs are dispatched longest-first over the whole launch
   bh0 = 0;
   if (ROLE == R_DKV) return p.nT - (int)blockIdx.z;
+  if (ROLE == R_DQ) return p.nT - (int)blockIdx.z;             // it = nT-1-blockIdx.z  ->  it+1 key tiles
   bh0 = (int)blockIdx.x * p.bh_per_cta;
   int nbh = min(p.bh_per_cta, p.B * p.h - bh0);
   return nbh > 0 ? nbh * (p.nT - (int)blockIdx.z) : 0;
@@ -88,6 +98,7 @@ template <int ROLE>
 __device__ __forceinline__ Step2 step2(const Bwd2Params& p, int n, int bh0) {
   Step2 s;
   if (ROLE == R_DKV) { s.jt = blockIdx.z; s.it = s.jt + n; s.hh = blockIdx.x; s.b = blockIdx.y; }
+  else if (ROLE == R_DQ) { s.it = p.nT - 1 - (int)blockIdx.z; s.jt = n; s.hh = blockIdx.x; s.b = blockIdx.y; }
   else {
     const int per = p.nT - (int)blockIdx.z;
     const int bh = bh0 + n / per, k = n % per;
@@ -100,6 +111,7 @@ __device__ __forceinline__ Step2 step2(const Bwd2Params& p, int n, int bh0) {
 template <int ROLE>
 __device__ __forceinline__ void step_advance(const Bwd2Params& p, Step2& s) {
   if (ROLE == R_DKV) { ++s.it; return; }
+  if (ROLE == R_DQ) { ++s.jt; return; }
   if (s.it + 1 < p.nT) { ++s.it; ++s.jt; return; }       // next tile down the diagonal
   s.it = (int)blockIdx.z; s.jt = 0;                      // next (batch, head) of the slice
   if (++s.hh == p.h) { s.hh = 0; ++s.b; }
@@ -183,14 +195,22 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // buffers of step n
   auto buf_q = [&](int n) -> uint8_t* {
     if (ROLE == R_DKV) return smem + Lay2<R_DKV>::ST0 + (n & 1) * Lay2<R_DKV>::ST_BYTES + Lay2<R_DKV>::sQ;
+    if (ROLE == R_DQ) return smem + Lay2<R_DQ>::Q;
     return smem + Lay2<R_DE>::Q0 + (n & 1) * TILE;
   };
   auto buf_do = [&](int n) -> uint8_t* {
     if (ROLE == R_DKV) return smem + Lay2<R_DKV>::ST0 + (n & 1) * Lay2<R_DKV>::ST_BYTES + Lay2<R_DKV>::sDO;
+    if (ROLE == R_DQ) return smem + Lay2<R_DQ>::DO;
     return smem + Lay2<R_DE>::DOV;
   };
-  auto buf_k = [&]() -> uint8_t* { return smem + (ROLE == R_DKV ? Lay2<R_DKV>::K : Lay2<R_DE>::K); };
-  auto buf_v = [&]() -> uint8_t* { return smem + (ROLE == R_DKV ? Lay2<R_DKV>::V : Lay2<R_DE>::DOV + TILE); };
+  auto buf_k = [&]() -> uint8_t* {          // DQ: slot 0 of the K ring (slot n&1 holds the key tile of step n)
+    return smem + (ROLE == R_DKV ? Lay2<R_DKV>::K : (ROLE == R_DQ ? Lay2<R_DQ>::K0 : Lay2<R_DE>::K));
+  };
+  auto buf_v = [&]() -> uint8_t* {
+    return smem + (ROLE == R_DKV ? Lay2<R_DKV>::V : (ROLE == R_DQ ? Lay2<R_DQ>::V : Lay2<R_DE>::DOV + TILE));
+  };
+  // DQ: E block m (the hi block of step m; block -1 = the lo block of step 0) lives in ring slot (m+1) % 3
+  auto buf_eblk = [&](int m) -> uint8_t* { return smem + Lay2<R_DQ>::E0 + ((m + 1) % 3) * TILE; };
   auto buf_elo = [&](int n) -> uint8_t* {
     if (ROLE == R_DKV) return smem + Lay2<R_DKV>::ST0 + (n & 1) * Lay2<R_DKV>::ST_BYTES + Lay2<R_DKV>::sE;
     return smem + Lay2<R_DE>::ELO;
@@ -200,7 +220,7 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     return smem + Lay2<R_DE>::EHI;
   };
   // P hand-off A -> B: the P operand buffer (DKV) or the {dO, V} tiles, dead once dP is computed (DE)
-  uint8_t* const pbuf = smem + (ROLE == R_DKV ? Lay2<R_DKV>::P : Lay2<R_DE>::DOV);
+  uint8_t* const pbuf = smem + (ROLE == R_DKV ? Lay2<R_DKV>::P : Lay2<R_DE>::DOV);      // (DQ: P stays in TMEM)
 
   if (warp == 16) {
     // ================================ TMA producer ==========================================
@@ -224,6 +244,29 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (n + 2 < nsteps) {       // pull the tiles of step n+2 into L2
             tc::tma_prefetch_4d(&tmQ, 0, s.hh, (s.it + 2) * TT, s.b);
             tc::tma_prefetch_4d(&tmDO, 0, s.hh, (s.it + 2) * TT, s.b);
+          }
+        }
+      } else if (ROLE == R_DQ) {
+        Step2 s = step2<ROLE>(p, 0, bh0);
+        tc::mbar_arrive_expect_tx(bar_res, 2 * TILE);
+        tc::tma_load_4d(buf_q(0), &tmQ, bar_res, 0, s.hh, s.it * TT, s.b);
+        tc::tma_load_4d(buf_do(0), &tmDO, bar_res, 0, s.hh, s.it * TT, s.b);
+        for (int n = 0; n < nsteps; ++n, step_advance<ROLE>(p, s)) {
+          const int st = n & 1;
+          const int c0 = p.max_seq - 1 - (s.it - s.jt) * TT;
+          // K slot n&1 and E slot (n+1)%3 were last read by the role MMAs of step n-2
+          tc::mbar_wait(&q_empty[st], ((n >> 1) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(&q_full[st], (n == 0 ? 3 : 2) * TILE);
+          tc::tma_load_4d(buf_k() + st * TILE, &tmK, &q_full[st], 0, s.hh, s.jt * TT, s.b);
+          tc::tma_load_2d(buf_eblk(n), &tmE, &q_full[st], 0, c0 + 1);
+          if (n == 0) tc::tma_load_2d(buf_eblk(-1), &tmE, &q_full[st], 0, c0 - (TT - 1));
+          // V: single slot, free as soon as dP of the previous step has been computed
+          tc::mbar_wait(k_empty, (n & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(v_full, TILE);
+          tc::tma_load_4d(buf_v(), &tmV, v_full, 0, s.hh, s.jt * TT, s.b);
+          if (n + 2 < nsteps) {
+            tc::tma_prefetch_4d(&tmK, 0, s.hh, (s.jt + 2) * TT, s.b);
+            tc::tma_prefetch_4d(&tmV, 0, s.hh, (s.jt + 2) * TT, s.b);
           }
         }
       } else {
@@ -257,7 +300,73 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == 17) {
     // ================================ MMA issuer ============================================
-    if (lane == 0) {
+    if (ROLE == R_DQ) {
+      if (lane == 0) {
+        const uint32_t id_kk = tc::make_idesc(TT, TT, 1, 1, 0, 0);      // S, G, dP : K-major x K-major, N = 128
+        const uint32_t id_kmn = tc::make_idesc(TT, DHC, 1, 1, 0, 1);    // dQ: A K-major (TMEM dS / smem dG), B MN-major, N = 64
+        constexpr uint64_t TS16 = TILE >> 4;
+        const uint64_t qd = tc::make_sdesc(tc::smem_u32(buf_q(0)), 16, 1024);
+        const uint64_t dod = tc::make_sdesc(tc::smem_u32(buf_do(0)), 16, 1024);
+        const uint64_t vd = tc::make_sdesc(tc::smem_u32(buf_v()), 16, 1024);
+        const uint64_t kd_k0 = tc::make_sdesc(tc::smem_u32(buf_k()), 16, 1024);
+        const uint64_t kd_mn0 = tc::make_sdesc(tc::smem_u32(buf_k()), 1024, 1024);
+        const uint64_t ed_k0 = tc::make_sdesc(tc::smem_u32(smem + Lay2<R_DQ>::E0), 16, 1024);
+        const uint64_t ed_mn0 = tc::make_sdesc(tc::smem_u32(smem + Lay2<R_DQ>::E0), 1024, 1024);
+        const uint64_t dgd = tc::make_sdesc(tc::smem_u32(smem + Lay2<R_DQ>::DG), 16, 1024);
+        auto eslot = [](int m) -> uint64_t { return (uint64_t)((m + 1) % 3) * TS16; };
+        auto issue_ghi = [&](int n) {          // Q . blk(n)^T -> the G region that held G_lo of step n-1
+          const uint32_t g_hi = tmem + (((n + 1) & 1) ? TM_GHI : TM_GLO);
+#pragma unroll
+          for (int k4 = 0; k4 < DHC / 16; ++k4)
+            tc::umma_f16(g_hi, qd + 2 * k4, ed_k0 + eslot(n) + 2 * k4, id_kk, k4 != 0);
+        };
+        auto issue_s = [&](int n) {
+#pragma unroll
+          for (int k4 = 0; k4 < DHC / 16; ++k4)
+            tc::umma_f16(tmem + TM_S, qd + 2 * k4, kd_k0 + (uint64_t)(n & 1) * TS16 + 2 * k4, id_kk, k4 != 0);
+          tc::umma_commit(s_full);
+        };
+        tc::mbar_wait(bar_res, 0);
+        tc::mbar_wait(&q_full[0], 0);
+        tc::tc_fence_after();
+#pragma unroll
+        for (int k4 = 0; k4 < DHC / 16; ++k4)   // G_lo of step 0 (block -1)
+          tc::umma_f16(tmem + TM_GLO, qd + 2 * k4, ed_k0 + eslot(-1) + 2 * k4, id_kk, k4 != 0);
+        issue_ghi(0);
+        issue_s(0);
+        for (int n = 0; n < nsteps; ++n) {
+          const uint32_t par = n & 1;
+          tc::mbar_wait(sg_free, par);
+          tc::mbar_wait(v_full, par);
+          tc::tc_fence_after();
+#pragma unroll
+          for (int k4 = 0; k4 < DHC / 16; ++k4)   // dP = dO V^T into the S columns
+            tc::umma_f16(tmem + TM_S, dod + 2 * k4, vd + 2 * k4, id_kk, k4 != 0);
+          tc::umma_commit(dp_full);
+          tc::umma_commit(k_empty);               // V slot free
+          if (n + 1 < nsteps) {
+            tc::mbar_wait(&q_full[(n + 1) & 1], ((n + 1) >> 1) & 1);
+            tc::tc_fence_after();
+            issue_ghi(n + 1);
+            tc::mbar_wait(dp_free, par);
+            tc::tc_fence_after();
+            issue_s(n + 1);
+          }
+          tc::mbar_wait(ds_ready, par);
+          tc::tc_fence_after();
+#pragma unroll
+          for (int k16 = 0; k16 < TT / 16; ++k16)         // dQ += dS . K_j : dS is the TMEM A operand (8 columns per 16 keys)
+            tc::umma_f16_ts(tmem + TM_DQ, tmem + TM_PS + 8 * k16, kd_mn0 + (uint64_t)(n & 1) * TS16 + 128 * k16, id_kmn,
+                            (n | k16) != 0);
+#pragma unroll
+          for (int k16 = 0; k16 < 2 * TT / 16; ++k16)     // dQ += dG . [E_lo; E_hi] (contraction over the band)
+            tc::umma_f16(tmem + TM_DQ, dgd + (uint64_t)(k16 >> 2) * TS16 + 2 * (k16 & 3),
+                         ed_mn0 + (k16 < 8 ? eslot(n - 1) + 128 * k16 : eslot(n) + 128 * (k16 - 8)), id_kmn, 1);
+          tc::umma_commit(&q_empty[n & 1]);
+          tc::umma_commit(step_done);
+        }
+      }
+    } else if (lane == 0) {
       const uint32_t id_kk = tc::make_idesc(TT, TT, 1, 1, 0, 0);      // S, G, dP : K-major x K-major, N = 128
       const uint32_t id_mnmn = tc::make_idesc(TT, DHC, 1, 1, 1, 1);   // dK/dV/dE: A MN-major, B MN-major, N = 64
       // Shared-memory descriptors are built once; inside the loops a k-step is an add on the address
@@ -402,7 +511,10 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int ps = 0; ps < 2; ++ps) {
           const int cfirst = 64 * half + 32 * ps;
-          park64_st64(tmem + TM_GLO, tmem + TM_GHI, lane_base, 96 - 32 * w4 + cfirst, scr);
+          // DQ: the G blocks alternate (G_hi of step n is G_lo of step n+1)
+          const uint32_t g_lo = tmem + ((ROLE == R_DQ && (n & 1)) ? TM_GHI : TM_GLO);
+          const uint32_t g_hi = tmem + ((ROLE == R_DQ && (n & 1)) ? TM_GLO : TM_GHI);
+          park64_st64(g_lo, g_hi, lane_base, 96 - 32 * w4 + cfirst, scr);
           float sv[32];
           {
             uint32_t r[32];
@@ -445,21 +557,28 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // the hand-off buffer must be free: DKV -- dV MMA of the previous step has read P;
         // DE -- dP of THIS step has consumed the {dO, V} tiles it aliases
         if (threadIdx.x == 0) TRACE(0, n, 3);
-        if (ROLE == R_DKV) { if (n > 0) tc::mbar_wait(step_done, (n - 1) & 1); }
-        else tc::mbar_wait(dp_full, par);
+        if (ROLE == R_DE) tc::mbar_wait(dp_full, par);
+        else if (n > 0) tc::mbar_wait(step_done, (n - 1) & 1);      // DKV: dV MMA has read P; DQ: dS.K has read dS
         if (threadIdx.x == 0) TRACE(0, n, 4);
-        uint8_t* ptile = pbuf + half * TILE;
+        if (ROLE == R_DQ) {           // P (bf16 pairs) into the TMEM columns group B turns into dS in place
+          tc::tc_fence_after();
+          tc::tmem_st_32x32(tmem + TM_PS + lane_base + 32 * half, pk);
+          tc::tmem_st_wait();
+          tc::tc_fence_before();
+        } else {
+          uint8_t* ptile = pbuf + half * TILE;
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(ptile + swz_chunk(a, c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-        tc::fence_proxy_async();
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(ptile + swz_chunk(a, c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          tc::fence_proxy_async();
+        }
         tc::mbar_arrive(p_ready);
         if (threadIdx.x == 0) TRACE(0, n, 5);
       }
     } else {
       // ================================ group B: dP, P -> dS / dG =============================
-      uint8_t* const dg_base = smem + Lay2<R_DE>::DG;
-      if (ROLE == R_DE) {
+      uint8_t* const dg_base = smem + (ROLE == R_DQ ? Lay2<R_DQ>::DG : Lay2<R_DE>::DG);
+      if (ROLE != R_DKV) {
         // dG is zero outside the 128 band columns each row owns; those positions never change
         uint4* z = reinterpret_cast<uint4*>(dg_base);
         for (int x = threadIdx.x - B2_GROUP; x < 4 * TILE / 16; x += B2_GROUP) z[x] = make_uint4(0, 0, 0, 0);
@@ -498,19 +617,43 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (threadIdx.x == B2_GROUP) TRACE(1, n, 3);
         // dS = P o (dP - D) / sqrt(dh)
         uint32_t A[32];
-        const uint8_t* ptile = pbuf + half * TILE;
+        if (ROLE == R_DQ) {             // P sits in TMEM (this thread's 32 words of row a)
+          tc::tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 pw = *reinterpret_cast<const uint4*>(ptile + swz_chunk(a, c));
-          const uint32_t w[4] = {pw.x, pw.y, pw.z, pw.w};
+          for (int c = 0; c < 2; ++c) {
+            uint32_t w[16];
+            tc::tmem_ld_32x16(tmem + TM_PS + lane_base + 32 * half + 16 * c, w);
+            tc::tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float d0 = fmaf(__uint_as_float(dp[8 * c + 2 * e]), p.scale, -Ds) * bf16lo(w[e]);
-            const float d1 = fmaf(__uint_as_float(dp[8 * c + 2 * e + 1]), p.scale, -Ds) * bf16hi(w[e]);
-            A[4 * c + e] = pack_bf16x2(d0, d1);
+            for (int e = 0; e < 16; ++e) {
+              const float d0 = fmaf(__uint_as_float(dp[32 * c + 2 * e]), p.scale, -Ds) * bf16lo(w[e]);
+              const float d1 = fmaf(__uint_as_float(dp[32 * c + 2 * e + 1]), p.scale, -Ds) * bf16hi(w[e]);
+              A[16 * c + e] = pack_bf16x2(d0, d1);
+            }
+          }
+        } else {
+          const uint8_t* ptile = pbuf + half * TILE;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 pw = *reinterpret_cast<const uint4*>(ptile + swz_chunk(a, c));
+            const uint32_t w[4] = {pw.x, pw.y, pw.z, pw.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float d0 = fmaf(__uint_as_float(dp[8 * c + 2 * e]), p.scale, -Ds) * bf16lo(w[e]);
+              const float d1 = fmaf(__uint_as_float(dp[8 * c + 2 * e + 1]), p.scale, -Ds) * bf16hi(w[e]);
+              A[4 * c + e] = pack_bf16x2(d0, d1);
+            }
           }
         }
-        if (ROLE == R_DKV) {            // rectangular dS: sub-tile `half` of row a
+        if (ROLE == R_DQ) {
+          // dS replaces P in TMEM (A operand of dS.K); the same values in band coordinates go to the
+          // shared-memory dG operand of dG.E_band.  Both were last read by the role MMAs of step n-1,
+          // which group A waited for before it stored P of this step.
+          tc::tmem_st_32x32(tmem + TM_PS + lane_base + 32 * half, A);
+          band_store(dg_base, a, base_w, A);
+          tc::tmem_st_wait();
+          tc::tc_fence_before();
+        } else if (ROLE == R_DKV) {            // rectangular dS: sub-tile `half` of row a
           uint8_t* dstile = smem + Lay2<R_DKV>::DS + half * TILE;
 #pragma unroll
           for (int c = 0; c < 8; ++c)
@@ -534,7 +677,20 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint32_t r[32];
     tc::tmem_ld_32x32(tmem + (grpA ? TM_ACC0 : TM_ACC1) + lane_base + half * 32, r);
     tc::tmem_ld_wait();
-    if (ROLE == R_DE) {
+    if (ROLE == R_DQ) {            // one accumulator (TM_DQ == TM_ACC0): group A writes the query rows
+      const Step2 s = step2<ROLE>(p, 0, bh0);
+      const int row = s.it * TT + a;
+      if (grpA && row < p.L) {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dq) + (int64_t)s.b * p.sb +
+                                              (int64_t)row * p.sl + (int64_t)s.hh * p.sh + half * 32);
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+          dst[x] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * x]), __uint_as_float(r[8 * x + 1])),
+                              pack_bf16x2(__uint_as_float(r[8 * x + 2]), __uint_as_float(r[8 * x + 3])),
+                              pack_bf16x2(__uint_as_float(r[8 * x + 4]), __uint_as_float(r[8 * x + 5])),
+                              pack_bf16x2(__uint_as_float(r[8 * x + 6]), __uint_as_float(r[8 * x + 7])));
+      }
+    } else if (ROLE == R_DE) {
       const int c0 = p.max_seq - 1 - (int)blockIdx.z * TT;
       const int erow = (grpA ? c0 - (TT - 1) : c0 + 1) + a;
       if (erow >= 0 && erow < p.max_seq) {
@@ -608,7 +764,7 @@ int launch_role2(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorM
 
 Bwd2Params make_params2(const RgaArgs& a) {
   Bwd2Params p;
-  p.dk = a.dk; p.dv = a.dv; p.sb = a.sb; p.sl = a.sl; p.sh = a.sh;
+  p.dk = a.dk; p.dv = a.dv; p.dq = a.dq; p.sb = a.sb; p.sl = a.sl; p.sh = a.sh;
   p.dE = a.dE; p.lse = a.lse; p.delta = a.delta; p.pad = a.pad;
   p.B = a.B; p.h = a.h; p.L = a.L; p.max_seq = a.max_seq;
   p.nT = (a.L + TT - 1) / TT;
@@ -627,6 +783,13 @@ int rga_bwd2_dkv(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tm
                  const CUtensorMap& tmDO, const CUtensorMap& tmE, cudaStream_t st) {
   Bwd2Params p = make_params2(a);
   return launch_role2<R_DKV>(tmQ, tmK, tmV, tmDO, tmE, p, dim3(a.h, a.B, p.nT), st);
+}
+
+// dQ (query-tile owner walks the key tiles at or left of it; P / dS stay in TMEM)
+int rga_bwd2_dq(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                const CUtensorMap& tmDO, const CUtensorMap& tmE, cudaStream_t st) {
+  Bwd2Params p = make_params2(a);
+  return launch_role2<R_DQ>(tmQ, tmK, tmV, tmDO, tmE, p, dim3(a.h, a.B, p.nT), st);
 }
 
 // dE (tile-diagonal owner walks down the diagonal over a slice of (batch, head))

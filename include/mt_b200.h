@@ -119,6 +119,22 @@ int mt_rga_bwd(const void* q, const void* k, const void* v, int64_t sb, int64_t 
                int64_t ol, int64_t oh, const float* lse, float* delta, void* dq, void* dk,
                void* dv, float* dE, int64_t B, int64_t h, int64_t L, int64_t dh,
                int64_t max_seq, int causal, int dtype, int path, void* stream);
+/* Same with a caller-owned scratch buffer.  On the tcgen05 path a workspace of at least
+ * mt_rga_bwd_workspace_bytes() (128-byte aligned) selects the "dS-spill" variant: the dK/dV
+ * kernel computes S, the skew, P and dS once and writes every dS tile (bf16) to the workspace,
+ * the dQ and dE kernels only consume them.  NULL / too small: each kernel recomputes (no
+ * scratch, ~1.4x the time).  The contents are dead when the call's work has run; the buffer
+ * may be shared by all layers of a model on one stream.  Results are identical to mt_rga_bwd
+ * up to fp32 summation order. */
+int mt_rga_bwd_ws(const void* q, const void* k, const void* v, int64_t sb, int64_t sl, int64_t sh,
+                  const void* E, const uint8_t* pad_keys, const void* O, const void* dO, int64_t ob,
+                  int64_t ol, int64_t oh, const float* lse, float* delta, void* dq, void* dk,
+                  void* dv, float* dE, int64_t B, int64_t h, int64_t L, int64_t dh,
+                  int64_t max_seq, int causal, int dtype, int path, void* workspace,
+                  size_t workspace_bytes, void* stream);
+/* B*h*nT*(nT+1)/2 tiles of 32 KB, nT = ceil(L/128); 0 when the tcgen05 backward does not take
+ * the problem (dh != 64 or not bf16) */
+size_t mt_rga_bwd_workspace_bytes(int64_t B, int64_t h, int64_t L, int64_t dh, int dtype);
 
 /* ---- K6: label-smoothed cross entropy + step metrics  (MT/criterion.py:43-67, ------------
  *          MT/metrics.py:50-60) */

@@ -83,11 +83,26 @@ int mt_rga_weights(const void* q, const void* k, int64_t sb, int64_t sl, int64_t
   return rga_weights_simt(a, (int)dh, dtype, as_stream(stream));
 }
 
+size_t mt_rga_bwd_workspace_bytes(int64_t B, int64_t h, int64_t L, int64_t dh, int dtype) {
+  if (dh != 64 || dtype != MT_BF16 || B <= 0 || h <= 0 || L <= 0) return 0;
+  return rga_bwd3_workspace_bytes(B, h, L);
+}
+
 int mt_rga_bwd(const void* q, const void* k, const void* v, int64_t sb, int64_t sl, int64_t sh,
                const void* E, const uint8_t* pad_keys, const void* O, const void* dO, int64_t ob,
                int64_t ol, int64_t oh, const float* lse, float* delta, void* dq, void* dk,
                void* dv, float* dE, int64_t B, int64_t h, int64_t L, int64_t dh,
                int64_t max_seq, int causal, int dtype, int path, void* stream) {
+  return mt_rga_bwd_ws(q, k, v, sb, sl, sh, E, pad_keys, O, dO, ob, ol, oh, lse, delta, dq, dk, dv, dE, B, h, L,
+                       dh, max_seq, causal, dtype, path, nullptr, 0, stream);
+}
+
+int mt_rga_bwd_ws(const void* q, const void* k, const void* v, int64_t sb, int64_t sl, int64_t sh,
+                  const void* E, const uint8_t* pad_keys, const void* O, const void* dO, int64_t ob,
+                  int64_t ol, int64_t oh, const float* lse, float* delta, void* dq, void* dk,
+                  void* dv, float* dE, int64_t B, int64_t h, int64_t L, int64_t dh,
+                  int64_t max_seq, int causal, int dtype, int path, void* workspace,
+                  size_t workspace_bytes, void* stream) {
   RgaArgs a;
   int rc = fill_rga(a, q, k, v, sb, sl, sh, E, pad_keys, B, h, L, dh, max_seq, causal, dtype);
   if (rc) return rc;
@@ -97,7 +112,7 @@ int mt_rga_bwd(const void* q, const void* k, const void* v, int64_t sb, int64_t 
   a.lse = const_cast<float*>(lse); a.delta = delta; a.dq = dq; a.dk = dk; a.dv = dv; a.dE = dE;
   bool tc_ok = rga_tc_supported(a, (int)dh, dtype, true);
   if (path == 2 && !tc_ok) { set_error("rga_bwd: tcgen05 path does not take this problem"); return MT_E_UNSUPPORTED; }
-  if (path == 2 || (path == 0 && tc_ok)) return rga_bwd_tc(a, (int)dh, dtype, as_stream(stream));
+  if (path == 2 || (path == 0 && tc_ok)) return rga_bwd_tc(a, (int)dh, dtype, workspace, workspace_bytes, as_stream(stream));
   return rga_bwd_simt(a, (int)dh, dtype, as_stream(stream));
 }
 

@@ -42,6 +42,7 @@ int gemm_skinny(const void* A, const void* B, void* C, const float* bias, int64_
                 int64_t lda, int64_t ldb, int64_t ldc, int out_dtype, int epilogue, cudaStream_t st);
 bool rga_tc_supported(const RgaArgs& a, int dh, int dtype, bool backward);
 int rga_fwd_tc(const RgaArgs& a, int dh, int dtype, cudaStream_t st);
-int rga_bwd_tc(const RgaArgs& a, int dh, int dtype, cudaStream_t st);
+int rga_bwd_tc(const RgaArgs& a, int dh, int dtype, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t rga_bwd3_workspace_bytes(int64_t B, int64_t h, int64_t L);   // dS-spill workspace of the tcgen05 backward
 
 }  // namespace mt

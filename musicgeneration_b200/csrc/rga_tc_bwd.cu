@@ -502,7 +502,9 @@ int launch_mode(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMa
 }  // namespace
 
 int rga_bwd2_dkv(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
-                 const CUtensorMap& tmDO, const CUtensorMap& tmE, cudaStream_t st);      // rga_tc_bwd2.cu
+                 const CUtensorMap& tmDO, const CUtensorMap& tmE, void* ds_ws, cudaStream_t st);      // rga_tc_bwd2.cu
+int rga_bwd3_dq(const RgaArgs& a, const void* ws, const CUtensorMap& tmK, const CUtensorMap& tmE, cudaStream_t st);   // rga_tc_bwd3.cu
+int rga_bwd3_de(const RgaArgs& a, const void* ws, const CUtensorMap& tmQ, const CUtensorMap& tmE, cudaStream_t st);
 int rga_bwd2_de(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                 const CUtensorMap& tmDO, const CUtensorMap& tmE, cudaStream_t st);
 int rga_bwd2_dq(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
@@ -517,8 +519,11 @@ bool rga_bwd_tc_supported(const RgaArgs& a, int dh, int dtype) {
   return mt_device_ok() != 0;
 }
 
-int rga_bwd_tc(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
+int rga_bwd_tc(const RgaArgs& a, int dh, int dtype, void* ws, size_t ws_bytes, cudaStream_t st) {
   int rc;
+  // a workspace of rga_bwd3_workspace_bytes() selects the dS-spill variant (S/P/dS computed once, in the
+  // dK/dV role); without it every role recomputes them
+  const bool spill = ws != nullptr && ws_bytes >= rga_bwd3_workspace_bytes(a.B, a.h, a.L) && aligned(ws, 128);
   if ((rc = rga_delta_launch(a, dh, dtype, st))) return rc;
   CUtensorMap tmQ, tmK, tmV, tmDO, tmE;
   if ((rc = tc::make_tmap_blhd(&tmQ, a.q, dh, a.L, a.h, a.B, a.sl, a.sh, a.sb, DHC, TT))) return rc;
@@ -536,7 +541,11 @@ int rga_bwd_tc(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
   p.bh_per_cta = 1;
   dim3 grid(a.h, a.B, p.nT);
   // dK/dV and dE: second-generation two-group pipeline (rga_tc_bwd2.cu); dQ: the role kernel above
-  if ((rc = rga_bwd2_dkv(a, tmQ, tmK, tmV, tmDO, tmE, st))) return rc;
+  if ((rc = rga_bwd2_dkv(a, tmQ, tmK, tmV, tmDO, tmE, spill ? ws : nullptr, st))) return rc;
+  if (spill) {
+    if ((rc = rga_bwd3_dq(a, ws, tmK, tmE, st))) return rc;
+    return rga_bwd3_de(a, ws, tmQ, tmE, st);
+  }
   // MT_RGA_DQ=1: the first-generation dQ role (kept for A/B timing)
   static const bool old_dq = getenv("MT_RGA_DQ") != nullptr && getenv("MT_RGA_DQ")[0] == '1';
   if (old_dq) { if ((rc = launch_mode<MODE_DQ>(tmQ, tmK, tmV, tmDO, tmE, p, grid, st))) return rc; }

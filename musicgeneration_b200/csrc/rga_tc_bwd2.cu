@@ -69,6 +69,7 @@ struct Bwd2Params {
   const uint8_t* pad;
   int B, h, L, max_seq, nT;
   int bh_per_cta;                        // DE role
+  uint8_t* ds_ws; int nTri;              // DKV role: spill every dS tile image here (rga_tc_bwd3.cu consumes them)
   float scale, scale_log2;
   long long* trace;                      // MT_RGA_TRACE=z: clock64 stamps of CTA (0,0,z), [4 agents][32 steps][8 events]
   int trace_z;
@@ -444,11 +445,20 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc::tc_fence_after();
         TRACE(3, n, 6);
         if (ROLE == R_DKV) {
+          if (p.ds_ws) {        // the dS operand image (32 KB, swizzled) goes to the workspace as it is
+            const int it = (int)blockIdx.z + n, jt = (int)blockIdx.z;
+            uint8_t* dst = p.ds_ws + (((int64_t)blockIdx.y * p.h + blockIdx.x) * p.nTri + (it * (it + 1) / 2 + jt)) *
+                                         (int64_t)(2 * TILE);
+            tc::bulk_store_1d(dst, smem + Lay2<R_DKV>::DS, 2 * TILE);
+            tc::bulk_commit();
+          }
 #pragma unroll
           for (int k16 = 0; k16 < TT / 16; ++k16) {      // contraction over the 128 query rows
             tc::umma_f16(tmem + TM_ACC1, opd0 + 128 * k16, dod_mn + 128 * k16, id_mnmn, (n | k16) != 0);   // dV += P^T dO
             tc::umma_f16(tmem + TM_ACC0, opd1 + 128 * k16, qd_mn + 128 * k16, id_mnmn, (n | k16) != 0);    // dK += dS^T Q
           }
+          // group B overwrites the dS buffer once step_done is signalled: the copy must have read it
+          if (p.ds_ws) tc::bulk_wait_read0();
         } else {
 #pragma unroll
           for (int k16 = 0; k16 < TT / 16; ++k16) {       // dG_blk^T . Q (contraction over the query rows)
@@ -459,6 +469,7 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc::umma_commit(&q_empty[n & 1]);
         tc::umma_commit(step_done);
       }
+      if (ROLE == R_DKV && p.ds_ws) tc::bulk_wait0();
     }
   } else {
     const bool grpA = warp < 8;
@@ -771,6 +782,8 @@ Bwd2Params make_params2(const RgaArgs& a) {
   p.scale = 1.f / a.inv_scale_div;
   p.scale_log2 = LOG2E / a.inv_scale_div;
   p.bh_per_cta = 1;
+  p.ds_ws = nullptr;
+  p.nTri = p.nT * (p.nT + 1) / 2;
   p.trace = nullptr;
   p.trace_z = 0;
   return p;
@@ -778,10 +791,11 @@ Bwd2Params make_params2(const RgaArgs& a) {
 
 }  // namespace
 
-// dK, dV (key-tile owner walks the query tiles at or below it)
+// dK, dV (key-tile owner walks the query tiles at or below it); ds_ws != NULL: also spill the dS tiles
 int rga_bwd2_dkv(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
-                 const CUtensorMap& tmDO, const CUtensorMap& tmE, cudaStream_t st) {
+                 const CUtensorMap& tmDO, const CUtensorMap& tmE, void* ds_ws, cudaStream_t st) {
   Bwd2Params p = make_params2(a);
+  p.ds_ws = static_cast<uint8_t*>(ds_ws);
   return launch_role2<R_DKV>(tmQ, tmK, tmV, tmDO, tmE, p, dim3(a.h, a.B, p.nT), st);
 }
 

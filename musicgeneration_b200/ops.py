@@ -158,15 +158,35 @@ def rga_weights(q, k, strides, E, pad_keys, lse, P, B, h, Lq, dh, max_seq, causa
             "rga_weights")
 
 
+_RGA_WS = {}     # device index -> uint8 scratch shared by every layer's attention backward (one stream)
+
+
+def rga_bwd_workspace(q, B, h, Lq, dh):
+    """Scratch for the dS-spill variant of the tcgen05 backward (grow-only, one per device); None when
+    that variant does not take the problem."""
+    need = L.load().mt_rga_bwd_workspace_bytes(B, h, Lq, dh, dt(q))
+    if need == 0:
+        return None
+    key = q.device.index
+    ws = _RGA_WS.get(key)
+    if ws is None or ws.numel() < need:
+        _RGA_WS[key] = ws = torch.empty(need, dtype=torch.uint8, device=q.device)
+    return ws
+
+
 def rga_bwd(q, k, v, strides, E, pad_keys, O, dO, ostrides, lse, delta, dq, dk, dv, dE, B, h, Lq, dh,
-            max_seq, causal, path=L.PATH_AUTO):
+            max_seq, causal, path=L.PATH_AUTO, spill=True):
+    """spill=True: give the tcgen05 path its dS workspace (S, P, dS computed once); False: every
+    backward role recomputes them (no scratch memory)."""
     _need_cuda(q, k, v, E, O, dO, lse, delta, dq, dk, dv, dE)
     sb, sl, sh = strides
     ob, ol, oh = ostrides
-    L.check(L.load().mt_rga_bwd(_ptr(q), _ptr(k), _ptr(v), sb, sl, sh, _ptr(E), _ptr(pad_keys),
-                                _ptr(O), _ptr(dO), ob, ol, oh, _ptr(lse), _ptr(delta), _ptr(dq),
-                                _ptr(dk), _ptr(dv), _ptr(dE), B, h, Lq, dh, max_seq, int(causal),
-                                dt(q), path, _stream()), "rga_bwd")
+    ws = rga_bwd_workspace(q, B, h, Lq, dh) if (spill and path != L.PATH_SIMT) else None
+    L.check(L.load().mt_rga_bwd_ws(_ptr(q), _ptr(k), _ptr(v), sb, sl, sh, _ptr(E), _ptr(pad_keys),
+                                   _ptr(O), _ptr(dO), ob, ol, oh, _ptr(lse), _ptr(delta), _ptr(dq),
+                                   _ptr(dk), _ptr(dv), _ptr(dE), B, h, Lq, dh, max_seq, int(causal),
+                                   dt(q), path, _ptr(ws), ws.numel() if ws is not None else 0, _stream()),
+            "rga_bwd")
 
 
 def smooth_ce_fwd(logits, target, row_ws, argmax, sums, eps, ignore):

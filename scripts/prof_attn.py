@@ -19,13 +19,14 @@ lse = torch.empty(B, h, L, device=dev)
 dqkv = torch.zeros(B, L, 3, h, dh, dtype=torch.bfloat16, device=dev)
 dE = torch.zeros(max_seq, dh, device=dev)
 delta = torch.empty(B, h, L, device=dev)
-for it in range(2):
+SPILL = os.environ.get("SPILL", "1") == "1"
+for it in range(3):
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     e[0].record()
     ops.rga_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], strides, E, None, Od, ostr, lse, B, h, L, dh, max_seq, True, path=2)
     e[1].record()
     ops.rga_bwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], strides, E, None, Od, dO, ostr, lse, delta,
-                dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], dE, B, h, L, dh, max_seq, True, path=2)
+                dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], dE, B, h, L, dh, max_seq, True, path=2, spill=SPILL)
     e[2].record()
     torch.cuda.synchronize()
     print("fwd ms", e[0].elapsed_time(e[1]), "bwd ms", e[1].elapsed_time(e[2]))

@@ -18,7 +18,7 @@ def rel(a, b):
     return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
 
 
-def run_case(B, h, L, dh, max_seq, causal, pad, dtype, path, seed=0, scale=1.0):
+def run_case(B, h, L, dh, max_seq, causal, pad, dtype, path, seed=0, scale=1.0, spill=True):
     from musicgeneration_b200 import ops
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(seed)
@@ -50,7 +50,7 @@ def run_case(B, h, L, dh, max_seq, causal, pad, dtype, path, seed=0, scale=1.0):
     dE = torch.zeros(max_seq, dh, device=dev)
     delta = torch.empty(B, h, L, device=dev)
     ops.rga_bwd(qd, kd, vd, strides, Ed, pk, Od, dO.to(dev), ostr, lse, delta, dqkv[:, :, 0],
-                dqkv[:, :, 1], dqkv[:, :, 2], dE, B, h, L, dh, max_seq, causal, path=path)
+                dqkv[:, :, 1], dqkv[:, :, 2], dE, B, h, L, dh, max_seq, causal, path=path, spill=spill)
     res = dict(
         o=rel(Od.float().cpu().permute(0, 2, 1, 3), o_ref.detach()),
         lse=float((lse.cpu().double() - lse_ref.detach()).abs().max()),
@@ -158,9 +158,12 @@ def test_rga_fwd_tcgen05(B, h, L, max_seq, causal, pad, dtype):
     (2, 4, 512, 512, False),
     (1, 8, 1024, 2048, True),
 ])
-def test_rga_bwd_tcgen05(B, h, L, max_seq, pad):
-    """forward + backward both on the tcgen05 path; bf16 operands, fp64 oracle on the same inputs."""
-    r = run_case(B, h, L, 64, max_seq, True, pad, torch.bfloat16, PATHS["tc"], seed=L + 3 * h)
+@pytest.mark.parametrize("spill", [True, False])
+def test_rga_bwd_tcgen05(B, h, L, max_seq, pad, spill):
+    """forward + backward both on the tcgen05 path; bf16 operands, fp64 oracle on the same inputs.
+    spill: dS tiles written once by the dK/dV kernel and consumed by the dQ / dE kernels (the default)
+    against every kernel recomputing them."""
+    r = run_case(B, h, L, 64, max_seq, True, pad, torch.bfloat16, PATHS["tc"], seed=L + 3 * h, spill=spill)
     assert r["o"] < 6e-3, r
     # P and dS are rounded to bf16 before the gradient GEMMs
     assert max(r["dq"], r["dk"], r["dv"]) < 1.2e-2 and r["dE"] < 1.2e-2, r
@@ -178,7 +181,7 @@ def test_rga_bwd_tcgen05_matches_simt_backward():
     dO = torch.randn(B, L, h, dh, generator=g).to(torch.bfloat16).to(dev)
     strides, ostr = (L * 3 * d, 3 * d, dh), (L * d, d, dh)
     outs = {}
-    for name, path in PATHS.items():
+    for name, path, spill in (("simt", PATHS["simt"], False), ("tc", PATHS["tc"], True), ("tc_recompute", PATHS["tc"], False)):
         Od = torch.empty(B, L, h, dh, dtype=torch.bfloat16, device=dev)
         lse = torch.empty(B, h, L, device=dev)
         ops.rga_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], strides, E, None, Od, ostr, lse, B, h, L, dh,
@@ -187,11 +190,14 @@ def test_rga_bwd_tcgen05_matches_simt_backward():
         dE = torch.zeros(max_seq, dh, device=dev)
         delta = torch.empty(B, h, L, device=dev)
         ops.rga_bwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], strides, E, None, Od, dO, ostr, lse, delta,
-                    dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], dE, B, h, L, dh, max_seq, True, path=path)
+                    dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], dE, B, h, L, dh, max_seq, True, path=path, spill=spill)
         outs[name] = (dqkv.float().cpu(), dE.cpu())
     assert rel(outs["tc"][0], outs["simt"][0]) < 1.2e-2
     assert rel(outs["tc"][1], outs["simt"][1]) < 1.2e-2
     assert float(outs["tc"][1][:max_seq - L].abs().max()) == 0.0      # only rows max_seq-L.. get gradient
+    # the two tensor-core variants see the same bf16 dS tiles: equal up to fp32 summation order / bf16 rounding of dq
+    assert rel(outs["tc"][0], outs["tc_recompute"][0]) < 2e-3
+    assert rel(outs["tc"][1], outs["tc_recompute"][1]) < 1e-4
 
 
 def test_rga_fwd_tcgen05_large_logits():

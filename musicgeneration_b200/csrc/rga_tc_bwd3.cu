@@ -9,16 +9,25 @@
 //     dQ role : dQ  = sum_j dS_ij K_j + dG_ij [E_lo; E_hi]      (3 tile products per step)
 //     dE role : dE_band += dG_ij^T Q_i                          (2 tile products per step)
 // where dG is dS in band coordinates (dG[a][127-a+b] = dS[a][b], the transpose of the reference's
-// skew, MT/layers.py:116-125).  The band shift is per-row variable, so it is done by 8 converter
-// warps: swizzled dS image -> registers -> band_store into the dG operand.  No S, no G, no exp, no
-// row statistics.  Workspace traffic: one write + two reads of 32 KB per tile pair (config B: 557 MB
-// per layer each way) against the 4/6 of the tensor work and 2/3 of the MUFU work it removes.
+// skew, MT/layers.py:116-125).  No S, no G, no exp, no row statistics.  Workspace traffic: one write
+// + two reads of 32 KB per tile pair (config B: 557 MB per layer each way) against the 4/6 of the
+// tensor work and 2/3 of the MUFU work it removes.
 //
-//   warps 0-7 : converters (row a = 32*(w&3)+lane, key columns 64*(w>>2)..+63)
-//   warp 8    : loader (1-D bulk copies of the dS images, TMA tiles of K/E or Q)
-//   warp 9    : tcgen05.mma issuer
+// The dS tiles stream from global memory THROUGH REGISTERS: the band shift is per-row variable, so
+// 16 converter warps own the rows anyway (row a = 32*(w&3)+lane, key columns 32*(w>>2)..+31);
+// each thread fetches its 64 bytes of a tile with two 256-bit loads, two tiles ahead of the one it
+// is converting (a shared-memory staging ring deep enough to cover the HBM latency does not fit
+// next to a double-buffered dG operand; 64 K registers do).  From the registers the values go
+//   * into the dG operand in shared memory (band_store; A of dG.E_band, or A of dG^T.Q), and
+//   * dQ role: as they are into TMEM, where dS is the A operand of dS.K (no shared-memory copy).
+//
+//   warps 0-15 : converters
+//   warp 16    : TMA loader of the K tile + one new E block (dQ role) or the Q tile (dE role)
+//   warp 17    : tcgen05.mma issuer
 #include "ops.cuh"
 #include "rga_tc_common.cuh"
+
+#include <stdlib.h>
 
 namespace mt {
 
@@ -28,25 +37,25 @@ namespace {
 
 enum { L_DQ = 0, L_DE = 1 };
 
-constexpr int CV_THREADS = 256;
+constexpr int CV_THREADS = 512;
+constexpr int W_LOAD = CV_THREADS / 32, W_MMA = W_LOAD + 1;
 constexpr int B3_THREADS = CV_THREADS + 64;
 constexpr int DS_BYTES = 2 * TILE;       // one dS tile image: two [128 x 64] swizzled sub-tiles
 
 template <int ROLE> struct Lay3;
-template <> struct Lay3<L_DQ> {      // dS x 2; K x 2; E ring x 3; dG (4 sub-tiles)
-  static constexpr int DS0 = 0, X0 = 4 * TILE, E0 = 6 * TILE, DG = 9 * TILE, BAR = 13 * TILE;
-  static constexpr int NDG = 1;
-  static constexpr uint32_t TMEM_COLS = 64;
+template <> struct Lay3<L_DQ> {      // K x 2; E ring x 3; dG x 2 (4 sub-tiles each)
+  static constexpr int X0 = 0, E0 = 2 * TILE, DG = 5 * TILE, BAR = 13 * TILE;
+  static constexpr uint32_t TMEM_COLS = 256;       // dQ accumulator (64) | dS slot 0 (64) | dS slot 1 (64)
 };
-template <> struct Lay3<L_DE> {      // dS x 2; Q x 2; dG x 2
-  static constexpr int DS0 = 0, X0 = 4 * TILE, DG = 6 * TILE, BAR = 14 * TILE;
-  static constexpr int NDG = 2;
-  static constexpr uint32_t TMEM_COLS = 128;
+template <> struct Lay3<L_DE> {      // Q x 2; dG x 2
+  static constexpr int X0 = 0, E0 = 0, DG = 2 * TILE, BAR = 10 * TILE;
+  static constexpr uint32_t TMEM_COLS = 128;       // dE_lo | dE_hi
 };
+constexpr uint32_t TM3_DS = 64;          // dQ role: dS slot s at columns 64 + 64*s
 template <int ROLE> constexpr int smem3_bytes() { return Lay3<ROLE>::BAR + 256; }
 static_assert(smem3_bytes<L_DQ>() <= 232448 && smem3_bytes<L_DE>() <= 232448, "shared memory budget");
 
-enum { B3_DSF = 0, B3_DSE = 2, B3_XF = 4, B3_XE = 6, B3_DGR = 8, B3_DGF = 10, B3_DONE = 12, B3_TMEM = 13 };
+enum { B3_XF = 0, B3_XE = 2, B3_DGR = 4, B3_DGF = 6, B3_DONE = 8, B3_TMEM = 9 };
 
 struct Bwd3Params {
   const uint8_t* ws;                     // dS tiles: [(b*h+hh)][it*(it+1)/2 + jt][32 KB]
@@ -54,7 +63,16 @@ struct Bwd3Params {
   float* dE;
   int B, h, L, max_seq, nT, nTri;
   int bh_per_cta;                        // dE role
+  long long* trace;                      // MT_RGA_TRACE=z: clock64 stamps of CTA (0,0,z), [2 agents][32 steps][4 events]
+  int trace_z;
 };
+
+// pipeline timeline of one CTA (debug aid, off unless the launcher passes a buffer)
+#define TRACE3(agent, n, ev)                                                                         \
+  do {                                                                                               \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (int)blockIdx.z == p.trace_z && (n) < 32)   \
+      p.trace[((agent) * 32 + (n)) * 4 + (ev)] = clock64();                                          \
+  } while (0)
 
 struct Step3 { int it, jt, b, hh; };
 
@@ -92,12 +110,10 @@ rga_bwd3_kernel(const __grid_constant__ CUtensorMap tmX,      // K (dQ role) or 
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((tc::smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LY::BAR);
-  uint64_t* ds_full = bars + B3_DSF;      // [2] loader -> converters (and the dS.K MMA)
-  uint64_t* ds_empty = bars + B3_DSE;     // [2] converters (+ MMA commit in the dQ role) -> loader
   uint64_t* x_full = bars + B3_XF;        // [2] K + E block / Q
   uint64_t* x_empty = bars + B3_XE;       // [2]
-  uint64_t* dg_ready = bars + B3_DGR;     // [NDG] converters -> MMA
-  uint64_t* dg_free = bars + B3_DGF;      // [NDG] MMA -> converters
+  uint64_t* dg_ready = bars + B3_DGR;     // [2] converters -> MMA : dG operand (and the TMEM dS slot) written
+  uint64_t* dg_free = bars + B3_DGF;      // [2] MMA -> converters
   uint64_t* acc_done = bars + B3_DONE;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B3_TMEM);
 
@@ -105,93 +121,86 @@ rga_bwd3_kernel(const __grid_constant__ CUtensorMap tmX,      // K (dQ role) or 
   int bh0;
   const int nsteps = num_steps3<ROLE>(p, bh0);
 
-  if (warp == 8 && lane == 0) {
+  if (warp == W_LOAD && lane == 0) {
     tc::tma_prefetch_desc(&tmX);
     if (ROLE == L_DQ) tc::tma_prefetch_desc(&tmE);
     for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(&ds_full[s], 1);
-      tc::mbar_init(&ds_empty[s], CV_THREADS + (ROLE == L_DQ ? 1 : 0));
       tc::mbar_init(&x_full[s], 1);
       tc::mbar_init(&x_empty[s], 1);
-      tc::mbar_init(&dg_ready[s], CV_THREADS);
+      tc::mbar_init(&dg_ready[s], CV_THREADS / 32);
       tc::mbar_init(&dg_free[s], 1);
     }
     tc::mbar_init(acc_done, 1);
     tc::fence_barrier_init();
   }
-  if (warp == 9) tc::tmem_alloc(tmem_slot, LY::TMEM_COLS);
+  if (warp == W_MMA) tc::tmem_alloc(tmem_slot, LY::TMEM_COLS);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (nsteps <= 0) {            // (dE role: empty slice) -- uniform for the whole CTA
     __syncthreads();
-    if (warp == 9) tc::tmem_dealloc(tmem, LY::TMEM_COLS);
+    if (warp == W_MMA) tc::tmem_dealloc(tmem, LY::TMEM_COLS);
     return;
   }
   constexpr uint64_t TS16 = TILE >> 4;
   // dQ role: E block m (hi block of step m; block -1 = lo block of step 0) lives in ring slot (m+1) % 3
   auto eslot = [](int m) -> int { return (m + 1) % 3; };
 
-  if (warp == 8) {
+  if (warp == W_LOAD) {
     // ================================ loader ===============================================
     if (lane == 0) {
       Step3 s = step3_first<ROLE>(p, bh0);
       for (int n = 0; n < nsteps; ++n, step3_advance<ROLE>(p, s)) {
         const int st = n & 1;
-        const uint32_t par = ((n >> 1) & 1) ^ 1;
-        tc::mbar_wait(&x_empty[st], par);
+        tc::mbar_wait(&x_empty[st], ((n >> 1) & 1) ^ 1);
         if (ROLE == L_DQ) {
           const int c0 = p.max_seq - 1 - (s.it - s.jt) * TT;
           tc::mbar_arrive_expect_tx(&x_full[st], (n == 0 ? 3 : 2) * TILE);
           tc::tma_load_4d(smem + LY::X0 + st * TILE, &tmX, &x_full[st], 0, s.hh, s.jt * TT, s.b);
-          tc::tma_load_2d(smem + Lay3<L_DQ>::E0 + eslot(n) * TILE, &tmE, &x_full[st], 0, c0 + 1);
-          if (n == 0) tc::tma_load_2d(smem + Lay3<L_DQ>::E0 + eslot(-1) * TILE, &tmE, &x_full[st], 0, c0 - (TT - 1));
+          tc::tma_load_2d(smem + LY::E0 + eslot(n) * TILE, &tmE, &x_full[st], 0, c0 + 1);
+          if (n == 0) tc::tma_load_2d(smem + LY::E0 + eslot(-1) * TILE, &tmE, &x_full[st], 0, c0 - (TT - 1));
         } else {
           tc::mbar_arrive_expect_tx(&x_full[st], TILE);
           tc::tma_load_4d(smem + LY::X0 + st * TILE, &tmX, &x_full[st], 0, s.hh, s.it * TT, s.b);
         }
-        tc::mbar_wait(&ds_empty[st], par);
-        tc::mbar_arrive_expect_tx(&ds_full[st], DS_BYTES);
-        tc::bulk_load_1d(smem + LY::DS0 + st * DS_BYTES, ds_tile(p, s), DS_BYTES, &ds_full[st]);
-        if (n + 2 < nsteps) {         // pull the tiles of step n+2 into L2
+        if (n + 2 < nsteps) {         // pull the tile of step n+2 into L2
           Step3 t = s;
           step3_advance<ROLE>(p, t);
           step3_advance<ROLE>(p, t);
-          tc::bulk_prefetch_l2(ds_tile(p, t), DS_BYTES);
           tc::tma_prefetch_4d(&tmX, 0, t.hh, (ROLE == L_DQ ? t.jt : t.it) * TT, t.b);
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == W_MMA) {
     // ================================ MMA issuer ============================================
     if (lane == 0) {
       if (ROLE == L_DQ) {
-        const uint32_t id_kmn = tc::make_idesc(TT, DHC, 1, 1, 0, 1);    // A K-major (dS / dG), B MN-major (K / E), N = 64
-        const uint64_t dsd0 = tc::make_sdesc(tc::smem_u32(smem + LY::DS0), 16, 1024);
+        const uint32_t id_kmn = tc::make_idesc(TT, DHC, 1, 1, 0, 1);    // A K-major (TMEM dS / smem dG), B MN-major (K / E), N = 64
         const uint64_t kd_mn0 = tc::make_sdesc(tc::smem_u32(smem + LY::X0), 1024, 1024);
-        const uint64_t ed_mn0 = tc::make_sdesc(tc::smem_u32(smem + Lay3<L_DQ>::E0), 1024, 1024);
-        const uint64_t dgd = tc::make_sdesc(tc::smem_u32(smem + LY::DG), 16, 1024);
+        const uint64_t ed_mn0 = tc::make_sdesc(tc::smem_u32(smem + LY::E0), 1024, 1024);
+        const uint64_t dgd0 = tc::make_sdesc(tc::smem_u32(smem + LY::DG), 16, 1024);
         for (int n = 0; n < nsteps; ++n) {
           const uint64_t st = n & 1;
           const uint32_t par = (n >> 1) & 1;
           tc::mbar_wait(&x_full[st], par);
-          tc::mbar_wait(&ds_full[st], par);
+          TRACE3(1, n, 0);
+          tc::mbar_wait(&dg_ready[st], par);
           tc::tc_fence_after();
+          TRACE3(1, n, 1);
 #pragma unroll
-          for (int k16 = 0; k16 < TT / 16; ++k16)         // dQ += dS . K_j (contraction over the 128 keys)
-            tc::umma_f16(tmem, dsd0 + st * 2 * TS16 + (uint64_t)(k16 >> 2) * TS16 + 2 * (k16 & 3),
-                         kd_mn0 + st * TS16 + 128 * k16, id_kmn, (n | k16) != 0);
-          tc::umma_commit(&ds_empty[st]);
-          tc::mbar_wait(&dg_ready[0], n & 1);
-          tc::tc_fence_after();
+          for (int k16 = 0; k16 < TT / 16; ++k16)         // dQ += dS . K_j : dS is the TMEM A operand (8 columns per 16 keys)
+            tc::umma_f16_ts(tmem, tmem + TM3_DS + 64 * (uint32_t)st + 8 * k16, kd_mn0 + st * TS16 + 128 * k16, id_kmn,
+                            (n | k16) != 0);
           const uint64_t elo = (uint64_t)eslot(n - 1) * TS16, ehi = (uint64_t)eslot(n) * TS16;
+          const uint64_t dgd = dgd0 + st * 4 * TS16;
 #pragma unroll
           for (int k16 = 0; k16 < 2 * TT / 16; ++k16)     // dQ += dG . [E_lo; E_hi] (contraction over the band)
             tc::umma_f16(tmem, dgd + (uint64_t)(k16 >> 2) * TS16 + 2 * (k16 & 3),
                          ed_mn0 + (k16 < 8 ? elo + 128 * k16 : ehi + 128 * (k16 - 8)), id_kmn, 1);
-          tc::umma_commit(&dg_free[0]);
+          tc::umma_commit(&dg_free[st]);
           tc::umma_commit(&x_empty[st]);
+          TRACE3(1, n, 2);
         }
       } else {
         const uint32_t id_mnmn = tc::make_idesc(TT, DHC, 1, 1, 1, 1);   // A MN-major (dG block), B MN-major (Q), N = 64
@@ -202,8 +211,10 @@ rga_bwd3_kernel(const __grid_constant__ CUtensorMap tmX,      // K (dQ role) or 
           const uint64_t st = n & 1;
           const uint32_t par = (n >> 1) & 1;
           tc::mbar_wait(&x_full[st], par);
+          TRACE3(1, n, 0);
           tc::mbar_wait(&dg_ready[st], par);
           tc::tc_fence_after();
+          TRACE3(1, n, 1);
 #pragma unroll
           for (int k16 = 0; k16 < TT / 16; ++k16) {       // dE_blk += dG_blk^T . Q (contraction over the query rows)
             tc::umma_f16(tmem, dg_lo0 + st * 4 * TS16 + 128 * k16, qd_mn0 + st * TS16 + 128 * k16, id_mnmn, (n | k16) != 0);
@@ -211,79 +222,116 @@ rga_bwd3_kernel(const __grid_constant__ CUtensorMap tmX,      // K (dQ role) or 
           }
           tc::umma_commit(&dg_free[st]);
           tc::umma_commit(&x_empty[st]);
+          TRACE3(1, n, 2);
         }
       }
       tc::umma_commit(acc_done);
     }
   } else {
-    // ================================ converters: dS image -> band dG ========================
-    const int w4 = warp & 3, half = warp >> 2;
+    // ================================ converters: dS tile -> registers -> band dG (+ TMEM dS) =====
+    const int w4 = warp & 3, q4 = warp >> 2;             // quarter q4: key columns 32*q4 .. +31
     const int a = w4 * 32 + lane;
+    const int a7 = a & 7;
     const uint32_t lane_base = (uint32_t)(w4 * 32) << 16;
     {
       // dG is zero outside the 128 band columns each row owns; those positions never change
       uint4* z = reinterpret_cast<uint4*>(smem + LY::DG);
-      for (int x = threadIdx.x; x < LY::NDG * 4 * TILE / 16; x += CV_THREADS) z[x] = make_uint4(0, 0, 0, 0);
+      for (int x = threadIdx.x; x < 2 * 4 * TILE / 16; x += CV_THREADS) z[x] = make_uint4(0, 0, 0, 0);
       tc::fence_proxy_async();
       tc::named_bar_sync(1, CV_THREADS);
     }
-    const int base_w = ((127 - a) >> 1) + 32 * half;     // first 32-bit word of this thread's band run in dG
-    for (int n = 0; n < nsteps; ++n) {
-      const int st = n & 1;
-      tc::mbar_wait(&ds_full[st], (n >> 1) & 1);
-      uint32_t A[32];
-      const uint8_t* img = smem + LY::DS0 + st * DS_BYTES + half * TILE;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint4 w = *reinterpret_cast<const uint4*>(img + swz_chunk(a, c));
-        A[4 * c] = w.x; A[4 * c + 1] = w.y; A[4 * c + 2] = w.z; A[4 * c + 3] = w.w;
+    const int base_w = ((127 - a) >> 1) + 16 * q4;       // first 32-bit word of this thread's band run in dG
+    // This thread's 32 values of a tile are logical 16-byte chunks 4*(q4&1)..+3 of row a in sub-tile q4>>1;
+    // the 128B swizzle puts them at physical chunks (4*(q4&1)+j) ^ a7: one aligned 64-byte run, fetched
+    // with two 256-bit loads and put back into logical order with two conditional swaps.
+    const int64_t my_off = (int64_t)(q4 >> 1) * TILE + a * 128 + (((q4 & 1) ^ (a7 >> 2)) << 6);
+    Step3 sf = step3_first<ROLE>(p, bh0);                 // fetch cursor (runs two tiles ahead)
+    int nf = 0;
+    auto fetch = [&](uint32_t (&R)[16]) {
+      if (nf < nsteps) {
+        const uint8_t* src = ds_tile(p, sf) + my_off;
+        tc::ldg256_stream(src, R[0], R[1], R[2], R[3], R[4], R[5], R[6], R[7]);
+        tc::ldg256_stream(src + 32, R[8], R[9], R[10], R[11], R[12], R[13], R[14], R[15]);
+        step3_advance<ROLE>(p, sf);
       }
-      tc::mbar_arrive(&ds_empty[st]);
-      const int buf = (LY::NDG == 2) ? st : 0;
-      if (LY::NDG == 1) { if (n > 0) tc::mbar_wait(&dg_free[0], (n - 1) & 1); }
-      else if (n >= 2) tc::mbar_wait(&dg_free[st], ((n >> 1) - 1) & 1);
-      band_store(smem + LY::DG + buf * 4 * TILE, a, base_w, A);
+      ++nf;
+    };
+    auto process = [&](const uint32_t (&R)[16], int n) {
+      uint32_t A[16];
+      if (threadIdx.x == 0) TRACE3(0, n, 0);
+      {
+        uint32_t T[16];
+        const bool s1 = a7 & 1, s2 = a7 & 2;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) T[4 * c + e] = s1 ? R[4 * (c ^ 1) + e] : R[4 * c + e];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) A[4 * c + e] = s2 ? T[4 * (c ^ 2) + e] : T[4 * c + e];
+      }
+      const int st = n & 1;
+      if (threadIdx.x == 0) TRACE3(0, n, 1);                          // (registers of the tile have arrived)
+      if (n >= 2) tc::mbar_wait(&dg_free[st], ((n >> 1) - 1) & 1);   // MMAs of step n-2 have read dG / the dS slot
+      if (threadIdx.x == 0) TRACE3(0, n, 2);
+      if (ROLE == L_DQ) {
+        tc::tc_fence_after();
+        tc::tmem_st_32x16(tmem + TM3_DS + 64 * st + lane_base + 16 * q4, A);
+      }
+      band_store_n<16>(smem + LY::DG + st * 4 * TILE, a, base_w, A);
+      if (ROLE == L_DQ) {
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+      }
       tc::fence_proxy_async();
-      tc::mbar_arrive(&dg_ready[buf]);
+      tc::mbar_arrive_warp(&dg_ready[st]);
+      if (threadIdx.x == 0) TRACE3(0, n, 3);
+    };
+    uint32_t R0[16], R1[16], R2[16];
+    fetch(R0);
+    fetch(R1);
+    for (int n = 0; n < nsteps; n += 3) {
+      fetch(R2);
+      process(R0, n);
+      if (n + 1 < nsteps) { fetch(R0); process(R1, n + 1); }
+      if (n + 2 < nsteps) { fetch(R1); process(R2, n + 2); }
     }
 
     // ---- epilogue
     tc::mbar_wait(acc_done, 0);
     tc::tc_fence_after();
-    if (ROLE == L_DQ) {           // 64 accumulator columns: this thread takes 32 of row a
-      uint32_t r[32];
-      tc::tmem_ld_32x32(tmem + lane_base + half * 32, r);
+    if (ROLE == L_DQ) {           // 64 accumulator columns: this thread takes 16 of row a
+      uint32_t r[16];
+      tc::tmem_ld_32x16(tmem + lane_base + q4 * 16, r);
       tc::tmem_ld_wait();
       const Step3 s = step3_first<ROLE>(p, bh0);
       const int row = s.it * TT + a;
       if (row < p.L) {
         uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dq) + (int64_t)s.b * p.sb +
-                                              (int64_t)row * p.sl + (int64_t)s.hh * p.sh + half * 32);
+                                              (int64_t)row * p.sl + (int64_t)s.hh * p.sh + q4 * 16);
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
+        for (int x = 0; x < 2; ++x)
           dst[x] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * x]), __uint_as_float(r[8 * x + 1])),
                               pack_bf16x2(__uint_as_float(r[8 * x + 2]), __uint_as_float(r[8 * x + 3])),
                               pack_bf16x2(__uint_as_float(r[8 * x + 4]), __uint_as_float(r[8 * x + 5])),
                               pack_bf16x2(__uint_as_float(r[8 * x + 6]), __uint_as_float(r[8 * x + 7])));
       }
-    } else {                      // two blocks of 128 E rows x 64: warps 0-3 the lo block, 4-7 the hi block
+    } else {                      // two blocks of 128 E rows x 64: quarters 0,1 the lo block, 2,3 the hi block
       const int c0 = p.max_seq - 1 - (int)blockIdx.z * TT;
-      const int erow = (half == 0 ? c0 - (TT - 1) : c0 + 1) + a;
+      const int erow = ((q4 >> 1) == 0 ? c0 - (TT - 1) : c0 + 1) + a;
+      uint32_t r[32];
+      tc::tmem_ld_32x32(tmem + lane_base + 32 * q4, r);
+      tc::tmem_ld_wait();
+      if (erow >= 0 && erow < p.max_seq) {
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32(tmem + lane_base + 64 * half + 32 * q, r);
-        tc::tmem_ld_wait();
-        if (erow >= 0 && erow < p.max_seq) {
-#pragma unroll
-          for (int x = 0; x < 32; ++x) atomicAdd(p.dE + (int64_t)erow * DHC + 32 * q + x, __uint_as_float(r[x]));
-        }
+        for (int x = 0; x < 32; ++x) atomicAdd(p.dE + (int64_t)erow * DHC + 32 * (q4 & 1) + x, __uint_as_float(r[x]));
       }
     }
     tc::tc_fence_before();
   }
   __syncthreads();
-  if (warp == 9) {
+  if (warp == W_MMA) {
     tc::tc_fence_after();
     tc::tmem_dealloc(tmem, LY::TMEM_COLS);
   }
@@ -298,7 +346,34 @@ int launch_role3(const CUtensorMap& tmX, const CUtensorMap& tmE, const Bwd3Param
     if (e != cudaSuccess) { set_error("rga_bwd3: smem attribute (%d B): %s", smem3_bytes<ROLE>(), cudaGetErrorString(e)); return (int)e; }
     attr_done = true;
   }
-  kern<<<grid, B3_THREADS, smem3_bytes<ROLE>(), st>>>(tmX, tmE, p);
+  Bwd3Params q = p;
+  static const bool want_trace = getenv("MT_RGA_TRACE") != nullptr;
+  static long long* trace_dev = nullptr;
+  const size_t trace_n = 2 * 32 * 4;
+  if (want_trace) {
+    if (!trace_dev) cudaMalloc(&trace_dev, trace_n * sizeof(long long));
+    cudaMemsetAsync(trace_dev, 0, trace_n * sizeof(long long), st);
+    q.trace = trace_dev;
+    q.trace_z = atoi(getenv("MT_RGA_TRACE"));
+  }
+  kern<<<grid, B3_THREADS, smem3_bytes<ROLE>(), st>>>(tmX, tmE, q);
+  if (want_trace) {
+    static long long host[2 * 32 * 4];
+    cudaMemcpyAsync(host, trace_dev, sizeof(host), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    long long t0 = 0;
+    for (size_t x = 0; x < trace_n; ++x) if (host[x] && (!t0 || host[x] < t0)) t0 = host[x];
+    static const char* agent[2] = {"CV", "MMA"};
+    for (int ag = 0; ag < 2; ++ag)
+      for (int n = 0; n < 32; ++n) {
+        bool any = false;
+        for (int e = 0; e < 4; ++e) any |= host[(ag * 32 + n) * 4 + e] != 0;
+        if (!any) continue;
+        fprintf(stderr, "trace3 role %d %-3s step %2d:", ROLE, agent[ag], n);
+        for (int e = 0; e < 4; ++e) fprintf(stderr, " %8lld", host[(ag * 32 + n) * 4 + e] ? host[(ag * 32 + n) * 4 + e] - t0 : -1LL);
+        fprintf(stderr, "\n");
+      }
+  }
   return check_launch("rga_bwd3");
 }
 
@@ -310,6 +385,8 @@ Bwd3Params make_params3(const RgaArgs& a, const void* ws) {
   p.nT = (a.L + TT - 1) / TT;
   p.nTri = p.nT * (p.nT + 1) / 2;
   p.bh_per_cta = 1;
+  p.trace = nullptr;
+  p.trace_z = 0;
   return p;
 }
 

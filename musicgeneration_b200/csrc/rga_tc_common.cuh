@@ -138,12 +138,14 @@ __device__ __forceinline__ int swz_word(int a, int win) {
 // half from two neighbours and the first / last element are 16-bit stores.  The word addresses are
 // chunk address (9 per thread, 16-byte granules) + one of 4 in-chunk offsets: two integer ops per
 // store instead of the full swizzle arithmetic.
-__device__ __forceinline__ void band_store(uint8_t* dg_base, int a, int base_w, const uint32_t (&A)[32]) {
+template <int NW>
+__device__ __forceinline__ void band_store_n(uint8_t* dg_base, int a, int base_w, const uint32_t (&A)[NW]) {
+  constexpr int NC = NW / 4 + 1;
   const int cb = base_w >> 2, r0 = base_w & 3, a7 = a & 7;
   uint8_t* const rowbase = dg_base + a * 128;
-  uint8_t* ca[9];
+  uint8_t* ca[NC];
 #pragma unroll
-  for (int q = 0; q < 9; ++q) {
+  for (int q = 0; q < NC; ++q) {
     const int c = cb + q;
     ca[q] = rowbase + (c >> 3) * TILE + (((c & 7) ^ a7) << 4);
   }
@@ -153,17 +155,21 @@ __device__ __forceinline__ void band_store(uint8_t* dg_base, int a, int base_w, 
   for (int j = 0; j < 4; ++j) { carry[j] = (r0 + j) >= 4; offs[j] = ((r0 + j) & 3) * 4; }
   auto wp = [&](int k) -> uint8_t* {
     const int j = k & 3, q = k >> 2;
-    return ((q < 8 && carry[j]) ? ca[q + 1 < 9 ? q + 1 : 8] : ca[q]) + offs[j];
+    return ((q < NC - 1 && carry[j]) ? ca[q + 1 < NC ? q + 1 : NC - 1] : ca[q]) + offs[j];
   };
   if (a & 1) {
 #pragma unroll
-    for (int k = 0; k < 32; ++k) *reinterpret_cast<uint32_t*>(wp(k)) = A[k];
+    for (int k = 0; k < NW; ++k) *reinterpret_cast<uint32_t*>(wp(k)) = A[k];
   } else {
     *reinterpret_cast<uint16_t*>(wp(0) + 2) = (uint16_t)(A[0] & 0xffffu);
 #pragma unroll
-    for (int k = 1; k < 32; ++k) *reinterpret_cast<uint32_t*>(wp(k)) = __byte_perm(A[k - 1], A[k], 0x5432);
-    *reinterpret_cast<uint16_t*>(wp(32)) = (uint16_t)(A[31] >> 16);
+    for (int k = 1; k < NW; ++k) *reinterpret_cast<uint32_t*>(wp(k)) = __byte_perm(A[k - 1], A[k], 0x5432);
+    *reinterpret_cast<uint16_t*>(wp(NW)) = (uint16_t)(A[NW - 1] >> 16);
   }
+}
+// (a thread may also hold only 32 of the values -- NW = 16 words, base_w = ((127-a)>>1) + 16*quarter)
+__device__ __forceinline__ void band_store(uint8_t* dg_base, int a, int base_w, const uint32_t (&A)[32]) {
+  band_store_n<32>(dg_base, a, base_w, A);
 }
 
 }  // namespace rga

@@ -48,6 +48,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One arrival per WARP: 32 lanes arriving on one barrier word are 32 serialised shared-memory atomics;
+// the warp converges first (its lanes' writes are ordered before lane 0's releasing arrive), so the
+// barrier is initialised with the number of warps.  Each lane must have issued its own proxy / tcgen05
+// fence before the call.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -131,6 +139,13 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes)
                : "memory");
+}
+// 256-bit streaming load (one full 32-byte sector per lane; read-only data, no L1 allocation)
+__device__ __forceinline__ void ldg256_stream(const void* g, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,
+                                              uint32_t& r4, uint32_t& r5, uint32_t& r6, uint32_t& r7) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+               : "l"(reinterpret_cast<uint64_t>(g)));
 }
 // named barrier among a subset of the CTA's warps
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

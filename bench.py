@@ -350,6 +350,90 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+SWEEP_L = (512, 1024, 2048, 4096, 8192)
+SWEEP_DH = (64, 128)
+
+
+def run_sweep(args):
+    """BASELINE configs[4]: relative attention alone, forward + backward, L = 512 .. 8192, head dim 64 /
+    128, 32 768 tokens and d = h*dh = 512 per point.  One JSON line per point.  dh = 64 bf16 runs on the
+    tcgen05 kernels; dh = 128 does not occur in the drop-in model (MT/layers.py:219 fixes dh = 64) and is
+    served by the fp32-math SIMT kernels.  `--impl reference`: the oracle port of the reference op
+    sequence (QE^T, mask, pad/reshape skew, softmax, AV) on the host cores, one (batch, head-set) sample,
+    L <= 2048 (the L x L x h fp32 intermediates of larger points do not fit the time budget)."""
+    import torch
+    pk = peaks()
+    if args.impl == "reference":
+        import math
+        from oracle import restate as O
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        torch.set_num_threads(os.cpu_count() or 1)
+        for dh in SWEEP_DH:
+            for L in SWEEP_L:
+                if L > 2048:
+                    continue
+                h = 512 // dh
+                g = torch.Generator().manual_seed(L)
+                q, k, v = [torch.randn(1, h, L, dh, generator=g).requires_grad_(True) for _ in range(3)]
+                E = torch.randn(L, dh, generator=g).requires_grad_(True)
+                ar = torch.arange(L)
+                mask = (ar[None, :] > ar[:, None])[None, None]
+                best = [1e9, 1e9]
+                for it in range(3):
+                    t0 = time.time()
+                    logits = O.rga_scores(q, k, E, L) + (mask.to(torch.int64) * -1e9).float()
+                    o = torch.matmul(torch.softmax(logits, -1), v)
+                    t1 = time.time()
+                    o.sum().backward()
+                    t2 = time.time()
+                    if it:
+                        best = [min(best[0], t1 - t0), min(best[1], t2 - t1)]
+                U = L * L * dh * h
+                print(json.dumps({"impl": "reference", "metric": "rga_fwd_bwd_ms", "L": L, "dh": dh, "B": 1, "h": h,
+                                  "fwd_ms": 1e3 * best[0], "bwd_ms": 1e3 * best[1],
+                                  "tokens_per_s": L / (best[0] + best[1]), "cores": os.cpu_count(),
+                                  "fwd_tflops": 3 * U / best[0] / 1e12, "kind": "port"}), flush=True)
+        return
+    from musicgeneration_b200 import ops
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    for dh in SWEEP_DH:
+        for L in SWEEP_L:
+            h, B = 512 // dh, max(1, 32768 // L)
+            d = h * dh
+            g = torch.Generator().manual_seed(L)
+            qkv = torch.randn(B, L, 3, h, dh, generator=g).to(torch.bfloat16).to(dev)
+            E = torch.randn(L, dh, generator=g).to(torch.bfloat16).to(dev)
+            dO = torch.randn(B, L, h, dh, generator=g).to(torch.bfloat16).to(dev)
+            strides, ostr = (L * 3 * d, 3 * d, dh), (L * d, d, dh)
+            Od = torch.empty(B, L, h, dh, dtype=torch.bfloat16, device=dev)
+            lse = torch.empty(B, h, L, device=dev)
+            dqkv = torch.zeros(B, L, 3, h, dh, dtype=torch.bfloat16, device=dev)
+            dE = torch.zeros(L, dh, device=dev)
+            delta = torch.empty(B, h, L, device=dev)
+            iters = 10 if dh == 64 else 3
+            ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(iters)]
+            for it in range(-2, iters):
+                e = ev[max(it, 0)]
+                e[0].record()
+                ops.rga_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], strides, E, None, Od, ostr, lse, B, h, L, dh, L, True)
+                e[1].record()
+                ops.rga_bwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], strides, E, None, Od, dO, ostr, lse, delta,
+                            dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], dE, B, h, L, dh, L, True)
+                e[2].record()
+            torch.cuda.synchronize()
+            fwd = sum(e[0].elapsed_time(e[1]) for e in ev) / iters
+            bwd = sum(e[1].elapsed_time(e[2]) for e in ev) / iters
+            U = L * L * dh * B * h
+            print(json.dumps({"metric": "rga_fwd_bwd_ms", "L": L, "dh": dh, "B": B, "h": h,
+                              "kernels": "tcgen05" if dh == 64 else "simt fp32 math",
+                              "fwd_ms": fwd, "bwd_ms": bwd, "tokens_per_s": B * L / ((fwd + bwd) / 1e3),
+                              "fwd_tflops": 3 * U / (fwd / 1e3) / 1e12, "bwd_tflops": 6 * U / (bwd / 1e3) / 1e12,
+                              "fwd_bwd_frac_of_bf16_sustained": 9 * U / ((fwd + bwd) / 1e3) / 1e12 / pk["tf_sust"]}),
+                  flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -364,8 +448,11 @@ def main():
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--decode-seqs", type=int, default=32)
     ap.add_argument("--decode-events", type=int, default=2047)
+    ap.add_argument("--sweep", action="store_true", help="relative-attention microbench sweep (configs[4])")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.sweep:
+        run_sweep(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

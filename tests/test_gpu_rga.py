@@ -200,6 +200,46 @@ def test_rga_bwd_tcgen05_matches_simt_backward():
     assert rel(outs["tc"][1], outs["tc_recompute"][1]) < 1e-4
 
 
+def test_rga_tcgen05_long_context_against_oracle():
+    """BASELINE config C's context (L = max_seq = 4096, 32 key tiles per row) on one head against the
+    fp64 closed form; ragged last tile included (L = 4000 < max_seq)."""
+    r = run_case(1, 1, 4000, 64, 4096, True, False, torch.bfloat16, PATHS["tc"], seed=11)
+    assert r["o"] < 6e-3 and r["lse"] < 2e-3, r
+    assert max(r["dq"], r["dk"], r["dv"]) < 1.2e-2 and r["dE"] < 1.2e-2, r
+
+
+@pytest.mark.parametrize("B,h,L", [(1, 12, 4096), (1, 2, 8192)])
+def test_rga_tcgen05_long_context_matches_simt(B, h, L):
+    """Config C's attention shape (12 heads, L = 4096) and the top of the microbench sweep (L = 8192):
+    the tensor-core kernels (dS-spill backward) against the fp32-math SIMT kernels on the same bf16
+    inputs (the fp64 oracle would need several L x L fp64 matrices per head on the host)."""
+    from musicgeneration_b200 import ops
+    dev = torch.device("cuda:0")
+    dh, max_seq = 64, L
+    d = h * dh
+    g = torch.Generator().manual_seed(L + h)
+    qkv = torch.randn(B, L, 3, h, dh, generator=g).to(torch.bfloat16).to(dev)
+    E = torch.randn(max_seq, dh, generator=g).to(torch.bfloat16).to(dev)
+    dO = torch.randn(B, L, h, dh, generator=g).to(torch.bfloat16).to(dev)
+    strides, ostr = (L * 3 * d, 3 * d, dh), (L * d, d, dh)
+    outs = {}
+    for name, path in PATHS.items():
+        Od = torch.empty(B, L, h, dh, dtype=torch.bfloat16, device=dev)
+        lse = torch.empty(B, h, L, device=dev)
+        ops.rga_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], strides, E, None, Od, ostr, lse, B, h, L, dh,
+                    max_seq, True, path=path)
+        dqkv = torch.zeros(B, L, 3, h, dh, dtype=torch.bfloat16, device=dev)
+        dE = torch.zeros(max_seq, dh, device=dev)
+        delta = torch.empty(B, h, L, device=dev)
+        ops.rga_bwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], strides, E, None, Od, dO, ostr, lse, delta,
+                    dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], dE, B, h, L, dh, max_seq, True, path=path)
+        outs[name] = (Od.float().cpu(), lse.cpu(), dqkv.float().cpu(), dE.cpu())
+    assert rel(outs["tc"][0], outs["simt"][0]) < 6e-3
+    assert float((outs["tc"][1] - outs["simt"][1]).abs().max()) < 2e-3
+    assert rel(outs["tc"][2], outs["simt"][2]) < 1.2e-2
+    assert rel(outs["tc"][3], outs["simt"][3]) < 1.2e-2
+
+
 def test_rga_fwd_tcgen05_large_logits():
     r = run_fwd_tc(1, 2, 256, 64, 256, True, False, torch.bfloat16, seed=5, scale=6.0)
     assert r["o"] < 8e-3 and r["lse"] < 2e-2, r

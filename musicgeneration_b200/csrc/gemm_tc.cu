@@ -44,6 +44,7 @@ struct TcGemmParams {
   const void* aux;
   int64_t M, N, K, ldc;
   int epi, out_bf16, vec_ok;
+  int add_inplace;          // EPI_ADD with addend == C (fp32, no ReLU / mask): accumulate with red.global.add.v4.f32
   int splits;
   int64_t k_per_split;
   float* part;
@@ -67,6 +68,14 @@ __device__ __forceinline__ void epilogue_quad(const TcGemmParams& p, int64_t row
     if (p.epi & MT_EPI_BIAS) {
       float4 b = *reinterpret_cast<const float4*>(p.bias + n);
       o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
+    }
+    if (p.add_inplace) {
+      // C += acc (fp32, the addend IS the output: residual-path gradient): one vector reduction, done by
+      // L2 -- no load and so no exposed DRAM latency in the epilogue.  One contribution per element, so the
+      // result does not depend on any ordering.
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(reinterpret_cast<float*>(p.C) + off),
+                   "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
+      return;
     }
     if (p.epi & MT_EPI_ADD) {
       float4 a = *reinterpret_cast<const float4*>(p.addend + off);
@@ -102,6 +111,32 @@ __device__ __forceinline__ void epilogue_quad(const TcGemmParams& p, int64_t row
       else reinterpret_cast<float*>(p.C)[off + t] = x;
     }
   }
+}
+
+// The same quad with its residual addend / ReLU-mask operand already in registers (vectorised case only).
+__device__ __forceinline__ void epilogue_quad_pre(const TcGemmParams& p, int64_t row, int64_t n, float (&o)[4],
+                                                  const float4& add, const uint2& aux, bool has_add, bool has_aux) {
+  const int64_t off = row * p.ldc + n;
+  if (p.epi & MT_EPI_BIAS) {
+    float4 b = *reinterpret_cast<const float4*>(p.bias + n);
+    o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
+  }
+  if (has_add) { o[0] += add.x; o[1] += add.y; o[2] += add.z; o[3] += add.w; }
+  if (p.epi & MT_EPI_RELU) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) o[t] = fmaxf(o[t], 0.f);
+  }
+  if (has_aux) {
+    const float m0 = __uint_as_float(aux.x << 16), m1 = __uint_as_float(aux.x & 0xffff0000u);
+    const float m2 = __uint_as_float(aux.y << 16), m3 = __uint_as_float(aux.y & 0xffff0000u);
+    if (!(m0 > 0.f)) o[0] = 0.f;
+    if (!(m1 > 0.f)) o[1] = 0.f;
+    if (!(m2 > 0.f)) o[2] = 0.f;
+    if (!(m3 > 0.f)) o[3] = 0.f;
+  }
+  float4 r = make_float4(o[0], o[1], o[2], o[3]);
+  if (p.out_bf16) store4<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.C) + off, r);
+  else store4<float>(reinterpret_cast<float*>(p.C) + off, r);
 }
 
 template <int A_MN, int B_MN, int BN>
@@ -342,36 +377,99 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     constexpr int CPW = BN / 2;                   // columns per warp
     float* stage = reinterpret_cast<float*>(stg + ew * PS_STG_BYTES);
     const int piece = lane & 7, rsub = lane >> 3;
-    int i = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
-      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
-      const int buf = i & 1;
-      tc::mbar_wait(&acc_full[buf], (i >> 1) & 1);
-      tc::tc_fence_after();
-      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + chalf * CPW);
-#pragma unroll 1
-      for (int c = 0; c < CPW / 32; ++c) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32(t0 + (uint32_t)(c * 32), r);
-        tc::tmem_ld_wait();
-        if (c == CPW / 32 - 1) {                  // last read of this accumulator: hand it back to the MMA warp
-          tc::tc_fence_before();
-          tc::mbar_arrive(&acc_empty[buf]);
-        }
-        __syncwarp();                             // the previous chunk's rows have been read by every lane
+    // The residual addend (fp32, 16 B per quad) and the ReLU-mask operand (bf16, 8 B per quad) are the
+    // only global READS of the epilogue.  Loaded where they are used, two at a time, they are a chain
+    // of exposed DRAM latencies (qkv dgrad + residual: 110 us against 59 us without the addend), so
+    // the 8 quads a thread owns in a 32-column chunk are fetched one chunk ahead -- for the first
+    // chunk of a tile before the accumulator is even complete.  (Plain loads: the addend may alias
+    // the output; a thread reads exactly the quads it later writes.)
+    const bool pre_add = (p.epi & MT_EPI_ADD) && p.vec_ok && p.splits == 1 && !p.add_inplace;
+    const bool pre_aux = (p.epi & MT_EPI_RELU_MASK) && p.vec_ok && p.splits == 1;
+    auto prefetch = [&](int m0, int n0, int c, float4 (&pa)[8], uint2 (&px)[8]) {
+      if (!(pre_add || pre_aux)) return;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<uint4*>(stage + lane * PS_STG_WORDS + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-        __syncwarp();
+      for (int it = 0; it < 8; ++it) {
+        const int64_t row = (int64_t)m0 + q * 32 + it * 4 + rsub;
+        const int64_t n = (int64_t)n0 + chalf * CPW + c * 32 + piece * 4;
+        const bool ok = row < p.M && n + 3 < p.N;
+        const int64_t off = row * p.ldc + n;
+        pa[it] = (pre_add && ok) ? *reinterpret_cast<const float4*>(p.addend + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        px[it] = (pre_aux && ok) ? *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + off)
+                                 : make_uint2(0x3f803f80u, 0x3f803f80u);
+      }
+    };
+    int i = 0;
+    if (pre_add || pre_aux) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        const int buf = i & 1;
+        float4 pa[8], pa_next[8];
+        uint2 px[8], px_next[8];
+        prefetch(m0, n0, 0, pa, px);
+        tc::mbar_wait(&acc_full[buf], (i >> 1) & 1);
+        tc::tc_fence_after();
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + chalf * CPW);
+#pragma unroll 1
+        for (int c = 0; c < CPW / 32; ++c) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(t0 + (uint32_t)(c * 32), r);
+          if (c + 1 < CPW / 32) prefetch(m0, n0, c + 1, pa_next, px_next);
+          tc::tmem_ld_wait();
+          if (c == CPW / 32 - 1) {                  // last read of this accumulator: hand it back to the MMA warp
+            tc::tc_fence_before();
+            tc::mbar_arrive(&acc_empty[buf]);
+          }
+          __syncwarp();                             // the previous chunk's rows have been read by every lane
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(stage + lane * PS_STG_WORDS + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rsub;
+            const int64_t row = (int64_t)m0 + q * 32 + rr;
+            const int64_t n = (int64_t)n0 + chalf * CPW + c * 32 + piece * 4;
+            if (row >= p.M || n >= p.N) continue;
+            const float4 acc = *reinterpret_cast<const float4*>(stage + rr * PS_STG_WORDS + piece * 4);
+            float o[4] = {acc.x, acc.y, acc.z, acc.w};
+            if (n + 3 < p.N) epilogue_quad_pre(p, row, n, o, pa[it], px[it], pre_add, pre_aux);
+            else epilogue_quad(p, row, n, o);
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) { pa[it] = pa_next[it]; px[it] = px_next[it]; }
+        }
+      }
+    } else {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        const int buf = i & 1;
+        tc::mbar_wait(&acc_full[buf], (i >> 1) & 1);
+        tc::tc_fence_after();
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + chalf * CPW);
+#pragma unroll 1
+        for (int c = 0; c < CPW / 32; ++c) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(t0 + (uint32_t)(c * 32), r);
+          tc::tmem_ld_wait();
+          if (c == CPW / 32 - 1) {                  // last read of this accumulator: hand it back to the MMA warp
+            tc::tc_fence_before();
+            tc::mbar_arrive(&acc_empty[buf]);
+          }
+          __syncwarp();                             // the previous chunk's rows have been read by every lane
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(stage + lane * PS_STG_WORDS + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+          __syncwarp();
 #pragma unroll 2
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + rsub;
-          const int64_t row = (int64_t)m0 + q * 32 + rr;
-          const int64_t n = (int64_t)n0 + chalf * CPW + c * 32 + piece * 4;
-          if (row >= p.M || n >= p.N) continue;
-          const float4 acc = *reinterpret_cast<const float4*>(stage + rr * PS_STG_WORDS + piece * 4);
-          float o[4] = {acc.x, acc.y, acc.z, acc.w};
-          epilogue_quad(p, row, n, o);
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rsub;
+            const int64_t row = (int64_t)m0 + q * 32 + rr;
+            const int64_t n = (int64_t)n0 + chalf * CPW + c * 32 + piece * 4;
+            if (row >= p.M || n >= p.N) continue;
+            const float4 acc = *reinterpret_cast<const float4*>(stage + rr * PS_STG_WORDS + piece * 4);
+            float o[4] = {acc.x, acc.y, acc.z, acc.w};
+            epilogue_quad(p, row, n, o);
+          }
         }
       }
     }
@@ -542,6 +640,8 @@ int gemm_tc(const void* A, const void* B, void* C, const float* bias, const floa
              (!(epilogue & MT_EPI_ADD) || aligned(addend, 16)) && (!(epilogue & MT_EPI_RELU_MASK) || aligned(aux, 8));
   p.splits = tc_splits(M, N, K);
   if (p.splits > 1 && (!workspace || workspace_bytes < (size_t)p.splits * M * N * sizeof(float))) p.splits = 1;
+  p.add_inplace = (epilogue & MT_EPI_ADD) && addend == C && !p.out_bf16 && p.vec_ok &&
+                  !(epilogue & (MT_EPI_RELU | MT_EPI_RELU_MASK)) && (N % 4 == 0);
   p.k_per_split = K;
   if (p.splits > 1) {
     int64_t kps = (((K + p.splits - 1) / p.splits + BK - 1) / BK) * BK;

@@ -172,7 +172,9 @@ def rga_block_bwd(d_a, s, W: LayerWeights, cfg: StackCfg, g: Dict[str, torch.Ten
     g["bqkv"] = _gbuf(dst, "bqkv", (3 * d,), dev)
     if s["same"]:
         linear_wgrad(dqkv, s["xq"], g["Wqkv"], g["bqkv"], cfg)
-        dx = _empty((T, d), torch.float32, dev)
+        # dx = dx_addend + dqkv . Wqkv, accumulated IN PLACE into the residual-path gradient (its last
+        # use): the GEMM epilogue then needs no addend read (red.global.add, see gemm_tc.cu)
+        dx = dx_addend if dx_addend is not None else _empty((T, d), torch.float32, dev)
         linear_dgrad(dqkv, W.Wqkv, dx, cfg, addend=dx_addend)
         return dx, dx, dx
     outs = []

@@ -191,6 +191,16 @@ def _act_copy(x_f32_2d: torch.Tensor, act: torch.dtype) -> torch.Tensor:
     return y
 
 
+def _weight_copy(w_f32: torch.Tensor, act: torch.dtype) -> torch.Tensor:
+    """16-bit operand copy of a weight: a view of the optimizer's refreshed shadow when one is active
+    (optim.weight_shadow), else a cast launch."""
+    if act == torch.float32:
+        return w_f32
+    from .optim import weight_shadow
+    sh = weight_shadow(w_f32, act)
+    return sh if sh is not None else _act_copy(w_f32, act)
+
+
 def _as_f32_2d(x: torch.Tensor, d: int) -> torch.Tensor:
     if not x.is_cuda:
         raise RuntimeError("musicgeneration_b200 runs on CUDA tensors only (no CPU fallback)")
@@ -205,11 +215,11 @@ def _rga_weights_for(rga: RelativeGlobalAttention, act: torch.dtype, ffn=None, l
     wqkv, bqkv = rga.packed()
 
     def a(t):
-        return _act_copy(t.data, act)
+        return _weight_copy(t.data, act)
 
     z = torch.empty(0, device=wqkv.device)
     return LayerWeights(
-        Wqkv=_act_copy(wqkv, act), bqkv=bqkv,
+        Wqkv=_weight_copy(wqkv, act), bqkv=bqkv,
         Wfc=a(rga.fc.weight), bfc=rga.fc.bias.data,
         Wpre=a(ffn[0].weight) if ffn else z, bpre=ffn[0].bias.data if ffn else z,
         Wsuf=a(ffn[1].weight) if ffn else z, bsuf=ffn[1].bias.data if ffn else z,
@@ -466,7 +476,7 @@ class _LinearFunction(torch.autograd.Function):
         x2 = _as_f32_2d(x, K)
         lp = getattr(x, "_mt_lp", None)
         xa = lp if (lp is not None and cfg.act != torch.float32) else _act_copy(x2, cfg.act)
-        Wa = _act_copy(weight.data, cfg.act)
+        Wa = _weight_copy(weight.data, cfg.act)
         out = torch.empty((x2.shape[0], N), dtype=torch.float32, device=x.device)
         engine.linear_fwd(xa, Wa, bias.data, out, cfg)
         ctx.cfg, ctx.xa, ctx.Wa, ctx.shape = cfg, xa, Wa, shape

@@ -50,8 +50,19 @@ class MusicTransformer(torch.nn.Module, _PrecisionMixin):
     def forward(self, x, length=None, writer=None):
         if self.training or not self.infer:
             _, _, look_ahead_mask = utils.get_masked_with_pad_tensor(self.max_seq, x, x, config.pad_token)
-            decoder, w = self.Decoder(x, mask=look_ahead_mask)
-            fc = _LinearFunction.apply(self.Decoder.cfg(), decoder, self.fc.weight, self.fc.bias)
+            # parameters living in a FlatAdam buffer: ONE cast of the flat buffer gives every layer its
+            # 16-bit weight operand (instead of a cast launch per matrix)
+            from . import optim as _optim
+            opt = getattr(self.fc.weight, "_mt_opt", None)
+            act = self.Decoder.cfg().act
+            if opt is not None and act != torch.float32 and x.is_cuda:
+                opt.refresh_lp(act)
+                _optim._ACTIVE_SHADOW[0] = opt
+            try:
+                decoder, w = self.Decoder(x, mask=look_ahead_mask)
+                fc = _LinearFunction.apply(self.Decoder.cfg(), decoder, self.fc.weight, self.fc.bias)
+            finally:
+                _optim._ACTIVE_SHADOW[0] = None
             return fc.contiguous() if self.training else (fc.contiguous(), [weight.contiguous() for weight in w])
         else:
             return self.generate(x, length, None).contiguous().tolist()

@@ -19,6 +19,25 @@ def _ordered(params: List[torch.nn.Parameter]) -> List[torch.nn.Parameter]:
     return list(params)
 
 
+# The optimizer whose 16-bit weight shadow has been refreshed for the forward pass in progress
+# (MusicTransformer.forward sets / clears it).  While set, the layers take their 16-bit weight
+# operands as views of the shadow instead of casting ~30 matrices one launch each.
+_ACTIVE_SHADOW = [None]
+
+
+def weight_shadow(t: torch.Tensor, act: torch.dtype) -> Optional[torch.Tensor]:
+    """The 16-bit copy of fp32 weight tensor ``t`` inside the active shadow, or None."""
+    opt = _ACTIVE_SHADOW[0]
+    if opt is None or opt.flat_lp is None or opt.flat_lp.dtype != act or t.dtype != torch.float32 \
+            or not t.is_contiguous():
+        return None
+    off = t.data_ptr() - opt.flat_p.data_ptr()
+    if off < 0 or off + t.numel() * 4 > opt.n * 4 or off % 4:
+        return None
+    off //= 4
+    return opt.flat_lp[off:off + t.numel()].view(t.shape)
+
+
 class FlatAdam:
     def __init__(self, model: torch.nn.Module, lr: float = 0.0, betas=(0.9, 0.98), eps: float = 1e-9,
                  process_group=None, grad_accum: int = 1):
@@ -41,7 +60,7 @@ class FlatAdam:
         dev = order[0].device
         if dev.type != "cuda":
             raise RuntimeError("FlatAdam needs the model on a CUDA device (no CPU fallback)")
-        sizes = [(p.numel() + 3) // 4 * 4 for p in order]       # 16-byte aligned slots
+        sizes = [(p.numel() + 63) // 64 * 64 for p in order]    # 256-byte aligned fp32 slots = 128-byte aligned slots of the 16-bit shadow (TMA needs 16)
         self.n = sum(sizes)
         self.flat_p = torch.zeros(self.n, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(self.n, dtype=torch.float32, device=dev)
@@ -58,6 +77,7 @@ class FlatAdam:
         # to autograd, which then launches one `grad += tmp` per parameter) as long as that view is
         # known to be zero: ``fresh`` holds the ids of the parameters not written since zero_grad().
         self.fresh = set()
+        self.flat_lp = None           # 16-bit shadow of flat_p, (re)written by refresh_lp()
         for p in order:
             p._mt_opt = self
         self.lr, self.betas, self.eps = lr, betas, eps
@@ -69,6 +89,13 @@ class FlatAdam:
     def zero_grad(self, set_to_none: bool = False):
         self.flat_g.zero_()
         self.fresh = {id(p) for p in self.params}
+
+    def refresh_lp(self, act: torch.dtype) -> None:
+        """One cast launch over the whole flat parameter buffer (always from the current fp32 values, so
+        parameters changed behind the optimizer's back -- load_state_dict, manual edits -- are picked up)."""
+        if self.flat_lp is None or self.flat_lp.dtype != act:
+            self.flat_lp = torch.empty(self.n, dtype=act, device=self.flat_p.device)
+        ops.cast(self.flat_p, self.flat_lp)
 
     def all_reduce_grads(self):
         """Data-parallel exchange: sum of the flat gradient over ranks (NCCL, one call)."""

@@ -18,7 +18,7 @@ for name, N, K in shapes:
     ldn = (N + 7) // 8 * 8
     dy = torch.randn(T, ldn, generator=g).to(bf).to(dev)
     b = torch.randn(N).to(dev)
-    for kind in ("fwd_bf16", "fwd_f32", "dgrad", "wgrad"):
+    for kind in ("fwd_bf16", "fwd_f32", "dgrad", "dgrad_add", "dgrad_mask", "wgrad"):
         if kind.startswith("fwd"):
             out = torch.empty(T, N, dtype=bf if kind == "fwd_bf16" else torch.float32, device=dev)
             fn = lambda: ops.gemm(x, W, out, T, N, K, K, K, N, False, True, bias=b)
@@ -26,6 +26,15 @@ for name, N, K in shapes:
         elif kind == "dgrad":
             out = torch.empty(T, K, dtype=torch.float32, device=dev)
             fn = lambda: ops.gemm(dy, W, out, T, K, N, ldn, K, K, False, False)
+            byts = T * N * 2 + W.numel() * 2 + out.numel() * 4
+        elif kind == "dgrad_add":       # residual-path gradient added in place (fp32), as in engine.layer_bwd
+            out = torch.zeros(T, K, dtype=torch.float32, device=dev)
+            fn = lambda: ops.gemm(dy, W, out, T, K, N, ldn, K, K, False, False, addend=out)
+            byts = T * N * 2 + W.numel() * 2 + out.numel() * 8
+        elif kind == "dgrad_mask":      # bf16 output masked by the saved ReLU activations
+            out = torch.empty(T, K, dtype=bf, device=dev)
+            aux = torch.randn(T, K, generator=g).to(bf).to(dev)
+            fn = lambda: ops.gemm(dy, W, out, T, K, N, ldn, K, K, False, False, aux=aux, relu_mask=True)
             byts = T * N * 2 + W.numel() * 2 + out.numel() * 4
         else:
             out = torch.empty(N, K, dtype=torch.float32, device=dev)

@@ -123,6 +123,46 @@ __device__ __forceinline__ void skew_fetch_add_32(float (&sv)[32], const uint32_
   }
 }
 
+// ---- the same 32-column unit WITHOUT shared memory: the 64-column window stays in registers as 32
+// f16 pairs and is moved by the per-lane offset o = 31 - lane with a barrel shifter -- four stages of
+// word selects (8, 4, 2, 1 words; the predicates are constants of the thread) and one 16-bit funnel
+// shift for odd o.  ~80 SEL per 32 outputs instead of 8 STS.64 + 17 LDS: the attention kernels are
+// bound by shared-memory bandwidth (UMMA operand reads alone take most of it), not by issue slots.
+__device__ __forceinline__ void skew_window_64(uint32_t g_lo, uint32_t g_hi, uint32_t lane_base, int w0,
+                                               uint32_t (&W)[32]) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t r[32];
+    const int cc = w0 + 32 * c;
+    tc::tmem_ld_32x32((cc < 128 ? g_lo + cc : g_hi + (cc - 128)) + lane_base, r);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int x = 0; x < 32; x += 2) W[16 * c + x / 2] = pack_f16x2(__uint_as_float(r[x]), __uint_as_float(r[x + 1]));
+  }
+}
+// sv[x] += window[o + x], x in [0, 32), o = 31 - lane
+__device__ __forceinline__ void skew_shift_add_32(float (&sv)[32], const uint32_t (&W)[32], int lane) {
+  const int o = 31 - lane;
+  const bool b8 = o & 16, b4 = o & 8, b2 = o & 4, b1 = o & 2;      // word offset o >> 1 = 8*b8 + 4*b4 + 2*b2 + b1
+  const uint32_t sh = (uint32_t)(o & 1) * 16u;
+  uint32_t A[24], B[20], C[18], D[17];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) A[i] = b8 ? W[i + 8] : W[i];
+#pragma unroll
+  for (int i = 0; i < 20; ++i) B[i] = b4 ? A[i + 4] : A[i];
+#pragma unroll
+  for (int i = 0; i < 18; ++i) C[i] = b2 ? B[i + 2] : B[i];
+#pragma unroll
+  for (int i = 0; i < 17; ++i) D[i] = b1 ? C[i + 1] : C[i];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    uint32_t u = __funnelshift_r(D[k], D[k + 1], sh);
+    float2 f = __half22float2(*reinterpret_cast<__half2*>(&u));
+    sv[2 * k] += f.x;
+    sv[2 * k + 1] += f.y;
+  }
+}
+
 // Byte offset of 16-byte chunk `chunk` (0..7) of row `a` inside a [128 x 64] 16-bit tile stored in
 // the UMMA 128B-swizzled layout (rows of 128 B, chunk index XOR-ed with row & 7).
 __device__ __forceinline__ int swz_chunk(int a, int chunk) { return a * 128 + ((chunk ^ (a & 7)) << 4); }

@@ -446,10 +446,18 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         tc::mbar_wait(&acc_full[buf], (i >> 1) & 1);
         tc::tc_fence_after();
         const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + chalf * CPW);
+        // interior tile, vectorised output, no operand to read back: the bias quad is loaded once per
+        // chunk (it depends on the column only) and the 8 rows of a thread are independent LDS -> FADD ->
+        // STG chains (per-quad bias loads sat in every chain: 'FADD ... stall_long_sb' in the source page)
+        const bool fast = p.vec_ok && p.splits == 1 && !(p.epi & MT_EPI_RELU_MASK) &&
+                          (!(p.epi & MT_EPI_ADD) || p.add_inplace) && m0 + BM <= p.M && n0 + BN <= p.N;
 #pragma unroll 1
         for (int c = 0; c < CPW / 32; ++c) {
           uint32_t r[32];
           tc::tmem_ld_32x32(t0 + (uint32_t)(c * 32), r);
+          const int64_t nq = (int64_t)n0 + chalf * CPW + c * 32 + piece * 4;
+          float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (fast && (p.epi & MT_EPI_BIAS)) bq = *reinterpret_cast<const float4*>(p.bias + nq);
           tc::tmem_ld_wait();
           if (c == CPW / 32 - 1) {                  // last read of this accumulator: hand it back to the MMA warp
             tc::tc_fence_before();
@@ -460,15 +468,35 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<uint4*>(stage + lane * PS_STG_WORDS + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
           __syncwarp();
+          if (fast) {
+            float4 acc[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              acc[it] = *reinterpret_cast<const float4*>(stage + (it * 4 + rsub) * PS_STG_WORDS + piece * 4);
+            const bool relu = (p.epi & MT_EPI_RELU) != 0;
+            const int64_t off0 = ((int64_t)m0 + q * 32 + rsub) * p.ldc + nq;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              float4 v = make_float4(acc[it].x + bq.x, acc[it].y + bq.y, acc[it].z + bq.z, acc[it].w + bq.w);
+              if (relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+              const int64_t off = off0 + (int64_t)(it * 4) * p.ldc;
+              if (p.add_inplace)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(reinterpret_cast<float*>(p.C) + off),
+                             "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+              else if (p.out_bf16) store4<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.C) + off, v);
+              else store4<float>(reinterpret_cast<float*>(p.C) + off, v);
+            }
+          } else {
 #pragma unroll 2
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + rsub;
-            const int64_t row = (int64_t)m0 + q * 32 + rr;
-            const int64_t n = (int64_t)n0 + chalf * CPW + c * 32 + piece * 4;
-            if (row >= p.M || n >= p.N) continue;
-            const float4 acc = *reinterpret_cast<const float4*>(stage + rr * PS_STG_WORDS + piece * 4);
-            float o[4] = {acc.x, acc.y, acc.z, acc.w};
-            epilogue_quad(p, row, n, o);
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + rsub;
+              const int64_t row = (int64_t)m0 + q * 32 + rr;
+              const int64_t n = (int64_t)n0 + chalf * CPW + c * 32 + piece * 4;
+              if (row >= p.M || n >= p.N) continue;
+              const float4 acc = *reinterpret_cast<const float4*>(stage + rr * PS_STG_WORDS + piece * 4);
+              float o[4] = {acc.x, acc.y, acc.z, acc.w};
+              epilogue_quad(p, row, n, o);
+            }
           }
         }
       }

@@ -321,9 +321,16 @@ def run_ours(args):
             "e2e": {"value": tokens * K / e2e_s, "unit": "tokens/s",
                     "h2d_bytes_per_step": 2 * Bg * L * 4, "d2h_bytes_per_step": 4, "last_loss": last},
             "gpu_launches": launches,
-            "roofline": {"kernel": "rga_bwd (relative attention backward, one layer)", "bound": "tensor",
+            "roofline": {"kernel": "rga_bwd (relative attention backward of one layer: delta + dK/dV kernel that "
+                                   "spills dS + dQ kernel + dE kernel, one C-ABI call)", "bound": "tensor",
                          "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                         "frac": ach / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " sustained",
+                         "frac": ach / pk["tf_sust"],
+                         # dram__bytes_read+write of the four kernels of one call, ncu --set full capture of the
+                         # config-B layer shape (profiles/r1c_ncu_attention_kernels.summary.txt); algorithmic
+                         # operand bytes (q,k,v,O,dO,dq,dk,dv once) are 0.27 GB -- the rest is the dS workspace
+                         "traffic": 2.51e9 if (args.config == "B" and Bg == 16) else None,
+                         "traffic_source": "profiles/r1c_ncu_attention_kernels.summary.txt",
+                         "peak_source": pk["src"] + " sustained",
                          "ms_per_launch": bwd_ms, "flops_per_launch": bwd_flops,
                          "fwd_ms_per_launch": fwd_ms,
                          "fwd_achieved": fwd_flops / (fwd_ms / 1e3) / 1e12 if fwd_ms > 0 else 0.0},

@@ -35,8 +35,20 @@ enum { R_DKV = 0, R_DQ = 1, R_DE = 2 };
 #define MT_SKEW_REGS 0
 #endif
 
+// dK/dV role, third generation (default): the 16 math warps split the tile by COLUMNS instead of by
+// function -- a thread owns row a and 32 key columns and does everything for them (S + skew -> P -> dS).
+// The trace of the two-group pipeline showed why it stalls: group A reads its second 32-column pass of
+// S / G only after the math of the first, so `sg_free` (and with it dP, then group B, then the next S)
+// waits ~1.3 k cycles per step, group B idles 70 % of the time.  Here all S / G columns are read at
+// once (sg_free after ~350 cycles), dP is computed under the exponentials, P stays in registers for dS
+// (no shared-memory hand-off), the skew runs through the register barrel shifter (no scratch for 512
+// threads), and the next step's S / G products run under the dS math.
+#ifndef MT_DKV_FUSED16
+#define MT_DKV_FUSED16 1
+#endif
+
 constexpr int B2_GROUP = 256;                       // threads of one math group
-constexpr int B2_THREADS = 2 * B2_GROUP + 64;       // A, B, TMA warp, MMA warp
+constexpr int B2_THREADS = 2 * B2_GROUP + 96;       // A, B, TMA warp, MMA warp, second MMA warp (dK/dV role)
 constexpr int SCRB_WORDS = 34;                      // skew scratch pitch (8-byte stores conflict-free)
 constexpr int B2_SCR_BYTES = B2_GROUP * SCRB_WORDS * 4;
 
@@ -182,11 +194,12 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int s = 0; s < 2; ++s) { tc::mbar_init(&q_full[s], 1); tc::mbar_init(&q_empty[s], 1); }
     tc::mbar_init(k_full, 1); tc::mbar_init(k_empty, 1); tc::mbar_init(v_full, 1);
     tc::mbar_init(s_full, 1);
-    tc::mbar_init(sg_free, B2_GROUP);
+    constexpr int NARR = (ROLE == R_DKV && MT_DKV_FUSED16) ? 2 * B2_GROUP : B2_GROUP;   // arrivals per math barrier
+    tc::mbar_init(sg_free, NARR);
     tc::mbar_init(dp_full, 1);
-    tc::mbar_init(dp_free, B2_GROUP);
-    tc::mbar_init(p_ready, B2_GROUP);
-    tc::mbar_init(ds_ready, B2_GROUP);
+    tc::mbar_init(dp_free, NARR);
+    tc::mbar_init(p_ready, NARR);
+    tc::mbar_init(ds_ready, NARR);
     tc::mbar_init(step_done, 1);
     tc::fence_barrier_init();
   }
@@ -245,6 +258,9 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const int c0 = p.max_seq - 1 - (s.it - s.jt) * TT;
           tc::mbar_wait(&q_empty[st], ((n >> 1) & 1) ^ 1);
           if (n == 1) tc::mbar_wait(s_full, 0);     // stage 1's E slot held E_hi of step 0 until G(0) was computed
+          // two MMA issuers: q_empty only covers the dV / dK products; the G product of step n-1 (it reads this
+          // stage's E block as its hi block) is covered by s_full(n-1), committed after it by the first issuer
+          if (MT_DKV_FUSED16 && n >= 2) tc::mbar_wait(s_full, (n - 1) & 1);
           tc::mbar_arrive_expect_tx(&q_full[st], (n == 0 ? 4 : 3) * TILE);
           tc::tma_load_4d(buf_q(n), &tmQ, &q_full[st], 0, s.hh, s.it * TT, s.b);
           tc::tma_load_2d(buf_elo(n), &tmE, &q_full[st], 0, c0 - (TT - 1));
@@ -446,6 +462,7 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           TRACE(3, n, 4);
           issue_s(n + 1);
         }
+        if (ROLE == R_DKV && MT_DKV_FUSED16) continue;      // dV / dK products: second issuer (warp 18)
         // ---- role MMAs on the operands written by the math groups
         tc::mbar_wait(p_ready, par);
         TRACE(3, n, 5);
@@ -477,7 +494,44 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc::umma_commit(&q_empty[n & 1]);
         tc::umma_commit(step_done);
       }
-      if (ROLE == R_DKV && p.ds_ws) tc::bulk_wait0();
+      if (ROLE == R_DKV && !MT_DKV_FUSED16 && p.ds_ws) tc::bulk_wait0();
+    }
+  } else if (warp == 18) {
+    // ================================ second MMA issuer (dK/dV role) ========================
+    // The first issuer's loop is a chain of waits (sg_free -> dP, q_full -> G, dp_free -> S); with the 16
+    // N = 64 products of dV / dK (and the dS spill) in the same thread every one of those waits was added
+    // to the products' issue time (trace: 5.7 k cycles per loop iteration = the step).  The two groups of
+    // products touch disjoint TMEM columns and shared-memory stages, so they are issued by two threads.
+    if (ROLE == R_DKV && MT_DKV_FUSED16 && lane == 0) {
+      const uint32_t id_mnmn = tc::make_idesc(TT, DHC, 1, 1, 1, 1);   // A MN-major (P / dS), B MN-major (dO / Q), N = 64
+      constexpr uint64_t STR = Lay2<R_DKV>::ST_BYTES >> 4;
+      const uint64_t qd_mn0 = tc::make_sdesc(tc::smem_u32(buf_q(0)), 1024, 1024);
+      const uint64_t dod_mn0 = tc::make_sdesc(tc::smem_u32(buf_do(0)), 1024, 1024);
+      const uint64_t opd0 = tc::make_sdesc(tc::smem_u32(smem + Lay2<R_DKV>::P), TILE, 1024);
+      const uint64_t opd1 = tc::make_sdesc(tc::smem_u32(smem + Lay2<R_DKV>::DS), TILE, 1024);
+      for (int n = 0; n < nsteps; ++n) {
+        const uint32_t par = n & 1;
+        const uint64_t dod_mn = dod_mn0 + (uint64_t)par * STR, qd_mn = qd_mn0 + (uint64_t)par * STR;
+        tc::mbar_wait(p_ready, par);
+        tc::mbar_wait(ds_ready, par);
+        tc::tc_fence_after();
+        if (p.ds_ws) {        // the dS operand image (32 KB, swizzled) goes to the workspace as it is
+          const int it = (int)blockIdx.z + n, jt = (int)blockIdx.z;
+          uint8_t* dst = p.ds_ws + (((int64_t)blockIdx.y * p.h + blockIdx.x) * p.nTri + (it * (it + 1) / 2 + jt)) *
+                                       (int64_t)(2 * TILE);
+          tc::bulk_store_1d(dst, smem + Lay2<R_DKV>::DS, 2 * TILE);
+          tc::bulk_commit();
+        }
+#pragma unroll
+        for (int k16 = 0; k16 < TT / 16; ++k16) {      // contraction over the 128 query rows
+          tc::umma_f16(tmem + TM_ACC1, opd0 + 128 * k16, dod_mn + 128 * k16, id_mnmn, (n | k16) != 0);   // dV += P^T dO
+          tc::umma_f16(tmem + TM_ACC0, opd1 + 128 * k16, qd_mn + 128 * k16, id_mnmn, (n | k16) != 0);    // dK += dS^T Q
+        }
+        if (p.ds_ws) tc::bulk_wait_read0();            // the math warps overwrite dS once step_done is signalled
+        tc::umma_commit(&q_empty[n & 1]);
+        tc::umma_commit(step_done);
+      }
+      if (p.ds_ws) tc::bulk_wait0();
     }
   } else {
     const bool grpA = warp < 8;
@@ -485,7 +539,115 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int a = w4 * 32 + lane;
     const uint32_t lane_base = (uint32_t)(w4 * 32) << 16;
 
-    if (grpA) {
+    if (ROLE == R_DKV && MT_DKV_FUSED16) {
+      // ================================ 16 warps, 32 columns each: S + skew -> P -> dS ==========
+      const int grp = warp >> 3;
+      const int cfirst = 64 * half + 32 * grp;                // this thread's key columns of the tile
+      const uint8_t* pad = p.pad;
+      if (pad) {            // any padded key in the sequences this CTA touches?  if not, the unmasked fast path
+        const Step2 sf = step2<ROLE>(p, 0, bh0), sl = step2<ROLE>(p, nsteps - 1, bh0);
+        bool mine = false;
+        for (int64_t x = (int64_t)sf.b * p.L + threadIdx.x; x < (int64_t)(sl.b + 1) * p.L; x += 2 * B2_GROUP)
+          mine |= (pad[x] != 0);
+        if (!tc::named_bar_red_or(1, 2 * B2_GROUP, mine)) pad = nullptr;
+      }
+      auto row_stat = [&](const float* src, const Step2& t) -> float {
+        const int i = t.it * TT + a;
+        return i < p.L ? src[((int64_t)t.b * p.h + t.hh) * p.L + i] : 0.f;
+      };
+      Step2 s = step2<ROLE>(p, 0, bh0), snext = s;
+      float lse_next = row_stat(p.lse, s), d_next = row_stat(p.delta, s);
+      uint8_t* const ptile = pbuf + half * TILE;
+      uint8_t* const dstile = smem + Lay2<R_DKV>::DS + half * TILE;
+      for (int n = 0; n < nsteps; ++n, s = snext) {
+        const uint32_t par = n & 1;
+        const int i0 = s.it * TT, j0 = s.jt * TT;
+        const bool row_ok = i0 + a < p.L;
+        const float lse2 = lse_next * LOG2E, Ds = d_next * p.scale;
+        step_advance<ROLE>(p, snext);
+        if (n + 1 < nsteps) { lse_next = row_stat(p.lse, snext); d_next = row_stat(p.delta, snext); }
+        if (pad) {
+          tc::named_bar_sync(1, 2 * B2_GROUP);
+          if (warp < 4) spad[a] = (j0 + a < p.L) ? pad[(int64_t)s.b * p.L + j0 + a] : 1;
+          tc::named_bar_sync(1, 2 * B2_GROUP);
+        }
+        const bool diag = (i0 == j0);
+        const bool need_mask = diag || (j0 + TT > p.L) || (i0 + TT > p.L) || pad != nullptr;
+        if (threadIdx.x == 0) TRACE(0, n, 0);
+        tc::mbar_wait(s_full, par);
+        tc::tc_fence_after();
+        if (threadIdx.x == 0) TRACE(0, n, 1);
+        uint32_t Wn[32];
+        skew_window_64(tmem + TM_GLO, tmem + TM_GHI, lane_base, 96 - 32 * w4 + cfirst, Wn);
+        float sv[32];
+        {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(tmem + TM_S + lane_base + cfirst, r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int x = 0; x < 32; ++x) sv[x] = __uint_as_float(r[x]);
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive(sg_free);               // S and G are in registers: dP and the next G may overwrite them
+        if (threadIdx.x == 0) TRACE(0, n, 2);
+        skew_shift_add_32(sv, Wn, lane);
+#pragma unroll
+        for (int x = 0; x < 32; ++x) sv[x] = tc::fast_exp2(fmaf(sv[x], p.scale_log2, -lse2));
+        if (need_mask) {
+          int lim = 31;
+          if (diag) lim = min(lim, a - cfirst);
+          lim = min(lim, p.L - 1 - j0 - cfirst);
+          if (!row_ok) lim = -1;
+#pragma unroll
+          for (int x = 0; x < 32; ++x) sv[x] = (x > lim) ? 0.f : sv[x];
+          if (pad) {
+            const uint32_t* sp = reinterpret_cast<const uint32_t*>(spad + cfirst);
+#pragma unroll
+            for (int x4 = 0; x4 < 8; ++x4) {
+              const uint32_t w = sp[x4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) sv[4 * x4 + e] = ((w >> (8 * e)) & 0xffu) ? 0.f : sv[4 * x4 + e];
+            }
+          }
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int x = 0; x < 16; ++x) pk[x] = pack_bf16x2(sv[2 * x], sv[2 * x + 1]);
+        if (threadIdx.x == 0) TRACE(0, n, 3);
+        if (n > 0) tc::mbar_wait(step_done, (n - 1) & 1);      // dV / dK of the previous step have read P and dS
+        if (threadIdx.x == 0) TRACE(0, n, 4);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(ptile + swz_chunk(a, 4 * grp + c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        tc::fence_proxy_async();
+        tc::mbar_arrive(p_ready);
+        if (threadIdx.x == 0) TRACE(0, n, 5);
+        tc::mbar_wait(dp_full, par);
+        tc::tc_fence_after();
+        if (threadIdx.x == 0) TRACE(0, n, 6);
+        uint32_t A16[16];
+        {
+          uint32_t dp[32];
+          tc::tmem_ld_32x32(tmem + TM_S + lane_base + cfirst, dp);
+          tc::tmem_ld_wait();
+          tc::tc_fence_before();
+          tc::mbar_arrive(dp_free);             // the S columns may take the next step's S
+          // dS = P o (dP - D) / sqrt(dh), with the bf16-rounded P the dV product sees
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float d0 = fmaf(__uint_as_float(dp[2 * k]), p.scale, -Ds) * bf16lo(pk[k]);
+            const float d1 = fmaf(__uint_as_float(dp[2 * k + 1]), p.scale, -Ds) * bf16hi(pk[k]);
+            A16[k] = pack_bf16x2(d0, d1);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(dstile + swz_chunk(a, 4 * grp + c)) = make_uint4(A16[4 * c], A16[4 * c + 1], A16[4 * c + 2], A16[4 * c + 3]);
+        tc::fence_proxy_async();
+        tc::mbar_arrive(ds_ready);
+        if (threadIdx.x == 0) TRACE(0, n, 7);
+      }
+    } else if (grpA) {
       // ================================ group A: S + skew -> P ================================
       uint32_t* scr = reinterpret_cast<uint32_t*>(smem + LY::SCR) + threadIdx.x * SCRB_WORDS;
       // training batches carry no pad tokens: decide once per CTA whether any key of the sequences

@@ -46,6 +46,7 @@ enum { R_DKV = 0, R_DQ = 1, R_DE = 2 };
 #ifndef MT_DKV_FUSED16
 #define MT_DKV_FUSED16 1
 #endif
+static_assert(MT_DKV_FUSED16 == 1, "the two-group dK/dV variant needs the skew scratch, which the three-slot {Q, dO} ring has replaced");
 
 constexpr int B2_GROUP = 256;                       // threads of one math group
 constexpr int B2_THREADS = 2 * B2_GROUP + 96;       // A, B, TMA warp, MMA warp, second MMA warp (dK/dV role)
@@ -56,10 +57,11 @@ constexpr int B2_SCR_BYTES = B2_GROUP * SCRB_WORDS * 4;
 constexpr uint32_t TM_S = 0, TM_GLO = 128, TM_GHI = 256, TM_ACC0 = 384, TM_ACC1 = 448;
 
 template <int ROLE> struct Lay2;
-template <> struct Lay2<R_DKV> {     // K,V resident; stage = {Q, dO, E_lo} x 2 (E_hi of a step = E_lo of the previous one)
-  static constexpr int K = 0, V = TILE, ST0 = 2 * TILE, ST_BYTES = 3 * TILE;
-  static constexpr int sQ = 0, sDO = TILE, sE = 2 * TILE;
-  static constexpr int P = ST0 + 2 * ST_BYTES, DS = P + 2 * TILE, SCR = DS + 2 * TILE, BAR = SCR + B2_SCR_BYTES;
+template <> struct Lay2<R_DKV> {     // K,V resident; Q x 3, dO x 3 (held until the dV / dK products of their step are done);
+                                     // E block x 2 (E_hi of a step = E_lo of the previous one; free as soon as G is computed); P; dS
+  static constexpr int K = 0, V = TILE, Q0 = 2 * TILE, DO0 = 5 * TILE, E0 = 8 * TILE;
+  static constexpr int P = 10 * TILE, DS = 12 * TILE, BAR = 14 * TILE, SCR = 0;       // (no skew scratch: register barrel shifter)
+  static constexpr int ST0 = Q0, ST_BYTES = TILE, sQ = 0, sDO = 0, sE = 0;            // (names the two-stage code paths of the other roles mention)
 };
 template <> struct Lay2<R_DE> {      // E_lo,E_hi resident; Q x 2; K; {dO, V} (doubles as the P hand-off); dG
   static constexpr int ELO = 0, EHI = TILE, Q0 = 2 * TILE, K = 4 * TILE, DOV = 5 * TILE, DG = 7 * TILE;
@@ -79,7 +81,8 @@ constexpr uint32_t TM_DQ = 384, TM_PS = 448;
 
 // barrier slots (uint64 each)
 enum { BR_RES = 0, BR_QF = 1, BR_QE = 3, BR_KF = 5, BR_KE = 6, BR_VF = 7, BR_SFULL = 8, BR_SGFREE = 9,
-       BR_DPFULL = 10, BR_DPFREE = 11, BR_PREADY = 12, BR_DSREADY = 13, BR_STEPDONE = 14, BR_TMEM = 15, BR_SPAD = 16 };
+       BR_DPFULL = 10, BR_DPFREE = 11, BR_PREADY = 12, BR_DSREADY = 13, BR_STEPDONE = 14, BR_TMEM = 15, BR_SPAD = 16,
+       BR_QD_FULL = 32, BR_QD_EMPTY = 35, BR_E_FULL = 38 };      // dK/dV role: {Q, dO} ring of 3, E ring of 2
 
 struct Bwd2Params {
   void* dk; void* dv; void* dq;          // 16-bit, q/k/v addressing
@@ -182,6 +185,9 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* step_done = bars + BR_STEPDONE;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BR_TMEM);
   uint8_t* spad = reinterpret_cast<uint8_t*>(bars + BR_SPAD);      // [128]
+  uint64_t* qd_full = bars + BR_QD_FULL;      // [3] dK/dV role: Q and dO of a step
+  uint64_t* qd_empty = bars + BR_QD_EMPTY;    // [3]
+  uint64_t* e_full = bars + BR_E_FULL;        // [2] dK/dV role: the step's new E block
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int bh0;
@@ -201,6 +207,8 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc::mbar_init(p_ready, NARR);
     tc::mbar_init(ds_ready, NARR);
     tc::mbar_init(step_done, 1);
+    for (int q = 0; q < 3; ++q) { tc::mbar_init(&qd_full[q], 1); tc::mbar_init(&qd_empty[q], 1); }
+    for (int q = 0; q < 2; ++q) tc::mbar_init(&e_full[q], 1);
     tc::fence_barrier_init();
   }
   if (warp == 17) tc::tmem_alloc(tmem_slot, 512);
@@ -216,12 +224,12 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   // buffers of step n
   auto buf_q = [&](int n) -> uint8_t* {
-    if (ROLE == R_DKV) return smem + Lay2<R_DKV>::ST0 + (n & 1) * Lay2<R_DKV>::ST_BYTES + Lay2<R_DKV>::sQ;
+    if (ROLE == R_DKV) return smem + Lay2<R_DKV>::Q0 + (n % 3) * TILE;
     if (ROLE == R_DQ) return smem + Lay2<R_DQ>::Q;
     return smem + Lay2<R_DE>::Q0 + (n & 1) * TILE;
   };
   auto buf_do = [&](int n) -> uint8_t* {
-    if (ROLE == R_DKV) return smem + Lay2<R_DKV>::ST0 + (n & 1) * Lay2<R_DKV>::ST_BYTES + Lay2<R_DKV>::sDO;
+    if (ROLE == R_DKV) return smem + Lay2<R_DKV>::DO0 + (n % 3) * TILE;
     if (ROLE == R_DQ) return smem + Lay2<R_DQ>::DO;
     return smem + Lay2<R_DE>::DOV;
   };
@@ -233,12 +241,12 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   };
   // DQ: E block m (the hi block of step m; block -1 = the lo block of step 0) lives in ring slot (m+1) % 3
   auto buf_eblk = [&](int m) -> uint8_t* { return smem + Lay2<R_DQ>::E0 + ((m + 1) % 3) * TILE; };
-  auto buf_elo = [&](int n) -> uint8_t* {
-    if (ROLE == R_DKV) return smem + Lay2<R_DKV>::ST0 + (n & 1) * Lay2<R_DKV>::ST_BYTES + Lay2<R_DKV>::sE;
+  auto buf_elo = [&](int n) -> uint8_t* {       // DKV: slot n & 1
+    if (ROLE == R_DKV) return smem + Lay2<R_DKV>::E0 + (n & 1) * TILE;
     return smem + Lay2<R_DE>::ELO;
   };
   auto buf_ehi = [&](int n) -> uint8_t* {       // DKV: the E_lo block of the previous step
-    if (ROLE == R_DKV) return smem + Lay2<R_DKV>::ST0 + ((n + 1) & 1) * Lay2<R_DKV>::ST_BYTES + Lay2<R_DKV>::sE;
+    if (ROLE == R_DKV) return smem + Lay2<R_DKV>::E0 + ((n + 1) & 1) * TILE;
     return smem + Lay2<R_DE>::EHI;
   };
   // P hand-off A -> B: the P operand buffer (DKV) or the {dO, V} tiles, dead once dP is computed (DE)
@@ -254,22 +262,22 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc::tma_load_4d(buf_v(), &tmV, bar_res, 0, s0.hh, s0.jt * TT, s0.b);
         Step2 s = s0;
         for (int n = 0; n < nsteps; ++n, step_advance<ROLE>(p, s)) {
-          const int st = n & 1;
-          const int c0 = p.max_seq - 1 - (s.it - s.jt) * TT;
-          tc::mbar_wait(&q_empty[st], ((n >> 1) & 1) ^ 1);
-          if (n == 1) tc::mbar_wait(s_full, 0);     // stage 1's E slot held E_hi of step 0 until G(0) was computed
-          // two MMA issuers: q_empty only covers the dV / dK products; the G product of step n-1 (it reads this
-          // stage's E block as its hi block) is covered by s_full(n-1), committed after it by the first issuer
-          if (MT_DKV_FUSED16 && n >= 2) tc::mbar_wait(s_full, (n - 1) & 1);
-          tc::mbar_arrive_expect_tx(&q_full[st], (n == 0 ? 4 : 3) * TILE);
-          tc::tma_load_4d(buf_q(n), &tmQ, &q_full[st], 0, s.hh, s.it * TT, s.b);
-          tc::tma_load_2d(buf_elo(n), &tmE, &q_full[st], 0, c0 - (TT - 1));
-          if (n == 0) tc::tma_load_2d(buf_ehi(0), &tmE, &q_full[st], 0, c0 + 1);
-          tc::tma_load_4d(buf_do(n), &tmDO, &q_full[st], 0, s.hh, s.it * TT, s.b);
-          if (n + 2 < nsteps) {       // pull the tiles of step n+2 into L2
-            tc::tma_prefetch_4d(&tmQ, 0, s.hh, (s.it + 2) * TT, s.b);
-            tc::tma_prefetch_4d(&tmDO, 0, s.hh, (s.it + 2) * TT, s.b);
+          // {Q, dO} slot n % 3: last read by the dV / dK products of step n-3 -- these loads run two steps ahead
+          const int q3 = n % 3;
+          tc::mbar_wait(&qd_empty[q3], ((n / 3) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(&qd_full[q3], 2 * TILE);
+          tc::tma_load_4d(buf_q(n), &tmQ, &qd_full[q3], 0, s.hh, s.it * TT, s.b);
+          tc::tma_load_4d(buf_do(n), &tmDO, &qd_full[q3], 0, s.hh, s.it * TT, s.b);
+          if (n + 3 < nsteps) {       // pull the tiles of step n+3 into L2
+            tc::tma_prefetch_4d(&tmQ, 0, s.hh, (s.it + 3) * TT, s.b);
+            tc::tma_prefetch_4d(&tmDO, 0, s.hh, (s.it + 3) * TT, s.b);
           }
+          // E slot n & 1 held the hi block of step n-1: free once G(n-1) is computed, which s_full(n-1) covers
+          if (n >= 1) tc::mbar_wait(s_full, (n - 1) & 1);
+          const int c0 = p.max_seq - 1 - (s.it - s.jt) * TT;
+          tc::mbar_arrive_expect_tx(&e_full[n & 1], (n == 0 ? 2 : 1) * TILE);
+          tc::tma_load_2d(buf_elo(n), &tmE, &e_full[n & 1], 0, c0 - (TT - 1));
+          if (n == 0) tc::tma_load_2d(buf_ehi(0), &tmE, &e_full[0], 0, c0 + 1);
         }
       } else if (ROLE == R_DQ) {
         Step2 s = step2<ROLE>(p, 0, bh0);
@@ -325,7 +333,63 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == 17) {
     // ================================ MMA issuer ============================================
-    if (ROLE == R_DQ) {
+    if (ROLE == R_DKV) {
+      if (lane == 0) {         // S, G, dP products (dV / dK: second issuer, warp 18)
+        const uint32_t id_kk = tc::make_idesc(TT, TT, 1, 1, 0, 0);      // K-major x K-major, N = 128
+        constexpr uint64_t TS16 = TILE >> 4;
+        const uint64_t kd = tc::make_sdesc(tc::smem_u32(buf_k()), 16, 1024);
+        const uint64_t vd = tc::make_sdesc(tc::smem_u32(buf_v()), 16, 1024);
+        const uint64_t qd0 = tc::make_sdesc(tc::smem_u32(smem + Lay2<R_DKV>::Q0), 16, 1024);
+        const uint64_t dod0 = tc::make_sdesc(tc::smem_u32(smem + Lay2<R_DKV>::DO0), 16, 1024);
+        const uint64_t ed0 = tc::make_sdesc(tc::smem_u32(smem + Lay2<R_DKV>::E0), 16, 1024);
+        auto issue_g = [&](int n) {
+          const uint64_t qd = qd0 + (uint64_t)(n % 3) * TS16;
+          const uint64_t lo = ed0 + (uint64_t)(n & 1) * TS16, hi = ed0 + (uint64_t)((n + 1) & 1) * TS16;
+#pragma unroll
+          for (int k4 = 0; k4 < DHC / 16; ++k4) {
+            tc::umma_f16(tmem + TM_GLO, qd + 2 * k4, lo + 2 * k4, id_kk, k4 != 0);
+            tc::umma_f16(tmem + TM_GHI, qd + 2 * k4, hi + 2 * k4, id_kk, k4 != 0);
+          }
+        };
+        auto issue_s = [&](int n) {
+          const uint64_t qd = qd0 + (uint64_t)(n % 3) * TS16;
+#pragma unroll
+          for (int k4 = 0; k4 < DHC / 16; ++k4)
+            tc::umma_f16(tmem + TM_S, qd + 2 * k4, kd + 2 * k4, id_kk, k4 != 0);
+          tc::umma_commit(s_full);
+        };
+        tc::mbar_wait(bar_res, 0);
+        tc::mbar_wait(&qd_full[0], 0);
+        tc::mbar_wait(&e_full[0], 0);
+        tc::tc_fence_after();
+        issue_g(0);
+        issue_s(0);
+        for (int n = 0; n < nsteps; ++n) {
+          const uint32_t par = n & 1;
+          tc::mbar_wait(sg_free, par);            // every math warp has S and G of the step in registers
+          tc::tc_fence_after();
+          TRACE(3, n, 0);
+          const uint64_t dod = dod0 + (uint64_t)(n % 3) * TS16;
+#pragma unroll
+          for (int k4 = 0; k4 < DHC / 16; ++k4)   // dP = dO V^T into the S columns
+            tc::umma_f16(tmem + TM_S, dod + 2 * k4, vd + 2 * k4, id_kk, k4 != 0);
+          tc::umma_commit(dp_full);
+          TRACE(3, n, 1);
+          if (n + 1 < nsteps) {
+            tc::mbar_wait(&qd_full[(n + 1) % 3], ((n + 1) / 3) & 1);
+            tc::mbar_wait(&e_full[(n + 1) & 1], ((n + 1) >> 1) & 1);
+            tc::tc_fence_after();
+            TRACE(3, n, 2);
+            issue_g(n + 1);
+            TRACE(3, n, 3);
+            tc::mbar_wait(dp_free, par);
+            tc::tc_fence_after();
+            TRACE(3, n, 4);
+            issue_s(n + 1);
+          }
+        }
+      }
+    } else if (ROLE == R_DQ) {
       if (lane == 0) {
         const uint32_t id_kk = tc::make_idesc(TT, TT, 1, 1, 0, 0);      // S, G, dP : K-major x K-major, N = 128
         const uint32_t id_kmn = tc::make_idesc(TT, DHC, 1, 1, 0, 1);    // dQ: A K-major (TMEM dS / smem dG), B MN-major, N = 64
@@ -504,14 +568,14 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // products touch disjoint TMEM columns and shared-memory stages, so they are issued by two threads.
     if (ROLE == R_DKV && MT_DKV_FUSED16 && lane == 0) {
       const uint32_t id_mnmn = tc::make_idesc(TT, DHC, 1, 1, 1, 1);   // A MN-major (P / dS), B MN-major (dO / Q), N = 64
-      constexpr uint64_t STR = Lay2<R_DKV>::ST_BYTES >> 4;
-      const uint64_t qd_mn0 = tc::make_sdesc(tc::smem_u32(buf_q(0)), 1024, 1024);
-      const uint64_t dod_mn0 = tc::make_sdesc(tc::smem_u32(buf_do(0)), 1024, 1024);
+      constexpr uint64_t STR = TILE >> 4;
+      const uint64_t qd_mn0 = tc::make_sdesc(tc::smem_u32(smem + Lay2<R_DKV>::Q0), 1024, 1024);
+      const uint64_t dod_mn0 = tc::make_sdesc(tc::smem_u32(smem + Lay2<R_DKV>::DO0), 1024, 1024);
       const uint64_t opd0 = tc::make_sdesc(tc::smem_u32(smem + Lay2<R_DKV>::P), TILE, 1024);
       const uint64_t opd1 = tc::make_sdesc(tc::smem_u32(smem + Lay2<R_DKV>::DS), TILE, 1024);
       for (int n = 0; n < nsteps; ++n) {
         const uint32_t par = n & 1;
-        const uint64_t dod_mn = dod_mn0 + (uint64_t)par * STR, qd_mn = qd_mn0 + (uint64_t)par * STR;
+        const uint64_t dod_mn = dod_mn0 + (uint64_t)(n % 3) * STR, qd_mn = qd_mn0 + (uint64_t)(n % 3) * STR;
         tc::mbar_wait(p_ready, par);
         tc::mbar_wait(ds_ready, par);
         tc::tc_fence_after();
@@ -528,7 +592,7 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tc::umma_f16(tmem + TM_ACC0, opd1 + 128 * k16, qd_mn + 128 * k16, id_mnmn, (n | k16) != 0);    // dK += dS^T Q
         }
         if (p.ds_ws) tc::bulk_wait_read0();            // the math warps overwrite dS once step_done is signalled
-        tc::umma_commit(&q_empty[n & 1]);
+        tc::umma_commit(&qd_empty[n % 3]);
         tc::umma_commit(step_done);
       }
       if (p.ds_ws) tc::bulk_wait0();

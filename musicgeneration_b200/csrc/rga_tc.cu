@@ -19,6 +19,8 @@
 #include "ops.cuh"
 #include "rga_tc_common.cuh"
 
+#include <stdlib.h>
+
 namespace mt {
 
 using namespace rga;
@@ -59,7 +61,16 @@ struct FwdParams {
   const uint8_t* pad;
   int B, h, L, max_seq, causal, fmt;
   float scale_log2;     // log2(e) / sqrt(dh)
+  long long* trace;     // MT_RGA_TRACE=z: clock64 stamps of CTA (0,0,z), [2 agents][32 steps][8 events]
+  int trace_z;
 };
+
+// pipeline timeline of one CTA (debug aid, off unless the launcher passes a buffer)
+#define FTRACE(agent, n, ev)                                                                        \
+  do {                                                                                              \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (int)blockIdx.z == p.trace_z && (n) < 32)  \
+      p.trace[((agent) * 32 + (n)) * 8 + (ev)] = clock64();                                         \
+  } while (0)
 
 __global__ void __launch_bounds__(FW_THREADS, 1)
 rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -161,18 +172,23 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       for (int jt = 0; jt < n_kt; ++jt) {
         if (jt + 1 < n_kt) {
           tc::mbar_wait(s_consumed, jt & 1);
+          FTRACE(1, jt, 0);
           tc::mbar_wait(&kv_full[(jt + 1) & 1], ((jt + 1) >> 1) & 1);
           tc::tc_fence_after();
+          FTRACE(1, jt, 1);
           issue_s(jt + 1);
+          FTRACE(1, jt, 2);
         }
         tc::mbar_wait(p_full, jt & 1);
         tc::tc_fence_after();
+        FTRACE(1, jt, 3);
         const uint64_t vd = vd0 + (uint64_t)(jt & 1) * (TILE >> 4);
 #pragma unroll
         for (int k8 = 0; k8 < TT / 16; ++k8)     // P stays in TMEM (A operand): 16 keys = 8 columns; V: 16 key rows = 2048 B
           tc::umma_f16_ts(tmem + TM_O, tmem + TM_P + 8 * k8, vd + 128 * k8, idesc_o, (jt | k8) != 0);
         tc::umma_commit(&kv_empty[jt & 1]);
         tc::umma_commit(o_done);
+        FTRACE(1, jt, 4);
       }
     }
   } else {
@@ -202,8 +218,10 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         if (qt == 0) spad[a] = (j0 + a < L) ? padrow[j0 + a] : 1;
         tc::named_bar_sync(1, FW_MATH_THREADS);
       }
+      if (threadIdx.x == 0) FTRACE(0, jt, 0);
       tc::mbar_wait(s_full, jt & 1);
       tc::tc_fence_after();
+      if (threadIdx.x == 0) FTRACE(0, jt, 1);
       const uint32_t g_lo = tmem + ((jt & 1) ? TM_G1 : TM_G0);
       const uint32_t g_hi = tmem + (((jt + 1) & 1) ? TM_G1 : TM_G0);
 
@@ -220,6 +238,7 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       // S / G fully read: the MMA warp may overwrite them with the next key tile
       tc::tc_fence_before();
       tc::mbar_arrive(s_consumed);
+      if (threadIdx.x == 0) FTRACE(0, jt, 2);
       skew_fetch_add_32(sv, scr, lane);
 
       // ---- mask (only on the diagonal / ragged / padded tiles) + online softmax (log2 domain)
@@ -255,7 +274,9 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       // passed the following step's barrier
       float* xs = xch + (jt & 1) * 4 * TT;
       xs[qt * TT + a] = mx;
+      if (threadIdx.x == 0) FTRACE(0, jt, 3);
       tc::named_bar_sync(rowbar, 128);
+      if (threadIdx.x == 0) FTRACE(0, jt, 4);
       mx = fmaxf(fmaxf(xs[a], xs[TT + a]), fmaxf(xs[2 * TT + a], xs[3 * TT + a])) * p.scale_log2;   // scale > 0
       float alpha = 1.f;
       if (mx > m_run + RESCALE_LOG2) {          // also the first tile (m_run = -inf) unless fully masked
@@ -279,6 +300,7 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       for (int x = 0; x < 16; ++x) pk[x] = pack16(sv[2 * x], sv[2 * x + 1], p.fmt);
 
       // ---- previous P.V must be complete before O is rescaled and P overwritten
+      if (threadIdx.x == 0) FTRACE(0, jt, 5);
       if (jt > 0) {
         tc::mbar_wait(o_done, (jt - 1) & 1);
         tc::tc_fence_after();
@@ -294,10 +316,12 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       // ---- P (16-bit pairs) into the TMEM A-operand of the P.V MMA: row = lane, this thread's 32
       // key columns are 16 packed columns (no shared-memory round trip for P)
+      if (threadIdx.x == 0) FTRACE(0, jt, 6);
       tc::tmem_st_32x16(tmem + TM_P + lane_base + qt * 16, pk);
       tc::tmem_st_wait();
       tc::tc_fence_before();
       tc::mbar_arrive(p_full);
+      if (threadIdx.x == 0) FTRACE(0, jt, 7);
     }
     // ---- epilogue: O / l, LSE
     float* xs = xch + (n_kt & 1) * 4 * TT;
@@ -368,7 +392,35 @@ int rga_fwd_tc(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
     attr_done = true;
   }
   dim3 grid(a.h, a.B, (a.L + TT - 1) / TT);
+  p.trace = nullptr;
+  p.trace_z = 0;
+  static const bool want_trace = getenv("MT_RGA_TRACE") != nullptr;
+  static long long* trace_dev = nullptr;
+  const size_t trace_n = 2 * 32 * 8;
+  if (want_trace) {
+    if (!trace_dev) cudaMalloc(&trace_dev, trace_n * sizeof(long long));
+    cudaMemsetAsync(trace_dev, 0, trace_n * sizeof(long long), st);
+    p.trace = trace_dev;
+    p.trace_z = atoi(getenv("MT_RGA_TRACE"));
+  }
   rga_fwd_tc_kernel<<<grid, FW_THREADS, FWD_SMEM, st>>>(tmQ, tmK, tmV, tmE, p);
+  if (want_trace) {
+    static long long host[2 * 32 * 8];
+    cudaMemcpyAsync(host, trace_dev, sizeof(host), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    long long t0 = 0;
+    for (size_t x = 0; x < trace_n; ++x) if (host[x] && (!t0 || host[x] < t0)) t0 = host[x];
+    static const char* agent[2] = {"SM", "MMA"};
+    for (int ag = 0; ag < 2; ++ag)
+      for (int n = 0; n < 32; ++n) {
+        bool any = false;
+        for (int e = 0; e < 8; ++e) any |= host[(ag * 32 + n) * 8 + e] != 0;
+        if (!any) continue;
+        fprintf(stderr, "trace fwd %-3s step %2d:", agent[ag], n);
+        for (int e = 0; e < 8; ++e) fprintf(stderr, " %8lld", host[(ag * 32 + n) * 8 + e] ? host[(ag * 32 + n) * 8 + e] - t0 : -1LL);
+        fprintf(stderr, "\n");
+      }
+  }
   return check_launch("rga_fwd_tc");
 }
 

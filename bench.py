@@ -24,8 +24,16 @@ import sys
 import threading
 import time
 
-# stdout carries exactly one JSON line: NCCL's own banner / debug lines go to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly the JSON line(s) of this script: everything else a library prints to fd 1 (NCCL's
+# version banner when NCCL_DEBUG is set in the environment, ...) is sent to stderr by pointing fd 1 at fd 2
+# for the run; emit() writes to the saved stdout.
+_STDOUT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    os.write(_STDOUT_FD, (json.dumps(obj) + "\n").encode())
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -148,7 +156,7 @@ def run_reference(args):
                                        f"{torch.get_num_threads()} threads"},
             "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline_leg(cfg_name, budget_s=20.0):
@@ -355,7 +363,7 @@ def run_ours(args):
                               "scaling": "sequences sharded over ranks, no collective"}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_leg(args.config)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -400,10 +408,10 @@ def run_sweep(args):
                     if it:
                         best = [min(best[0], t1 - t0), min(best[1], t2 - t1)]
                 U = L * L * dh * h
-                print(json.dumps({"impl": "reference", "metric": "rga_fwd_bwd_ms", "L": L, "dh": dh, "B": 1, "h": h,
+                emit(({"impl": "reference", "metric": "rga_fwd_bwd_ms", "L": L, "dh": dh, "B": 1, "h": h,
                                   "fwd_ms": 1e3 * best[0], "bwd_ms": 1e3 * best[1],
                                   "tokens_per_s": L / (best[0] + best[1]), "cores": os.cpu_count(),
-                                  "fwd_tflops": 3 * U / best[0] / 1e12, "kind": "port"}), flush=True)
+                                  "fwd_tflops": 3 * U / best[0] / 1e12, "kind": "port"}))
         return
     from musicgeneration_b200 import ops
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
@@ -436,12 +444,11 @@ def run_sweep(args):
             fwd = sum(e[0].elapsed_time(e[1]) for e in ev) / iters
             bwd = sum(e[1].elapsed_time(e[2]) for e in ev) / iters
             U = L * L * dh * B * h
-            print(json.dumps({"metric": "rga_fwd_bwd_ms", "L": L, "dh": dh, "B": B, "h": h,
+            emit(({"metric": "rga_fwd_bwd_ms", "L": L, "dh": dh, "B": B, "h": h,
                               "kernels": "tcgen05" if dh == 64 else "simt fp32 math",
                               "fwd_ms": fwd, "bwd_ms": bwd, "tokens_per_s": B * L / ((fwd + bwd) / 1e3),
                               "fwd_tflops": 3 * U / (fwd / 1e3) / 1e12, "bwd_tflops": 6 * U / (bwd / 1e3) / 1e12,
-                              "fwd_bwd_frac_of_bf16_sustained": 9 * U / ((fwd + bwd) / 1e3) / 1e12 / pk["tf_sust"]}),
-                  flush=True)
+                              "fwd_bwd_frac_of_bf16_sustained": 9 * U / ((fwd + bwd) / 1e3) / 1e12 / pk["tf_sust"]}))
 
 
 def main():

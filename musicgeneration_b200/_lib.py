@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmt_b200.so")
+LIB_PATH = os.environ.get("MT_LIB_PATH") or os.path.join(_HERE, "libmt_b200.so")     # (override: A/B timing of two builds)
 
 MT_F32, MT_BF16, MT_F16 = 0, 1, 2
 EPI_BIAS, EPI_RELU, EPI_ADD, EPI_RELU_MASK = 1, 2, 4, 8

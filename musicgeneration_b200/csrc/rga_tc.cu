@@ -105,6 +105,9 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     tc::tma_prefetch_desc(&tmK);
     tc::tma_prefetch_desc(&tmV);
     tc::tma_prefetch_desc(&tmE);
+    tc::tma_prefetch_4d(&tmQ, 0, hh, i0, b);       // the CTA's first tiles start towards L2 under the prologue
+    tc::tma_prefetch_4d(&tmK, 0, hh, 0, b);
+    tc::tma_prefetch_4d(&tmV, 0, hh, 0, b);
     tc::mbar_init(bar_q, 1);
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&kv_full[s], 1);

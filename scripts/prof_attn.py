@@ -20,7 +20,9 @@ dqkv = torch.zeros(B, L, 3, h, dh, dtype=torch.bfloat16, device=dev)
 dE = torch.zeros(max_seq, dh, device=dev)
 delta = torch.empty(B, h, L, device=dev)
 SPILL = os.environ.get("SPILL", "1") == "1"
-for it in range(3):
+ITERS = int(os.environ.get("PITER", 3))
+hist = []
+for it in range(ITERS):
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     e[0].record()
     ops.rga_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], strides, E, None, Od, ostr, lse, B, h, L, dh, max_seq, True, path=2)
@@ -29,4 +31,10 @@ for it in range(3):
                 dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], dE, B, h, L, dh, max_seq, True, path=2, spill=SPILL)
     e[2].record()
     torch.cuda.synchronize()
-    print("fwd ms", e[0].elapsed_time(e[1]), "bwd ms", e[1].elapsed_time(e[2]))
+    hist.append((e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])))
+    if ITERS <= 3:
+        print("fwd ms", hist[-1][0], "bwd ms", hist[-1][1])
+if ITERS > 3:
+    f = sorted(h[0] for h in hist[2:])
+    b = sorted(h[1] for h in hist[2:])
+    print(f"fwd ms median {f[len(f) // 2]:.4f} min {f[0]:.4f}   bwd ms median {b[len(b) // 2]:.4f} min {b[0]:.4f}")

@@ -678,17 +678,12 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int x = 0; x < 16; ++x) pk[x] = pack_bf16x2(sv[2 * x], sv[2 * x + 1]);
         if (threadIdx.x == 0) TRACE(0, n, 3);
-        if (n > 0) tc::mbar_wait(step_done, (n - 1) & 1);      // dV / dK of the previous step have read P and dS
-        if (threadIdx.x == 0) TRACE(0, n, 4);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<uint4*>(ptile + swz_chunk(a, 4 * grp + c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-        tc::fence_proxy_async();
-        tc::mbar_arrive(p_ready);
-        if (threadIdx.x == 0) TRACE(0, n, 5);
+        // dP was issued right after sg_free and has long arrived: read it BEFORE the stores of P (which wait for
+        // the previous step's dV / dK products), so that dp_free -- the go-ahead of the next step's S product --
+        // does not wait behind them
         tc::mbar_wait(dp_full, par);
         tc::tc_fence_after();
-        if (threadIdx.x == 0) TRACE(0, n, 6);
+        if (threadIdx.x == 0) TRACE(0, n, 4);
         uint32_t A16[16];
         {
           uint32_t dp[32];
@@ -704,10 +699,16 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             A16[k] = pack_bf16x2(d0, d1);
           }
         }
+        if (threadIdx.x == 0) TRACE(0, n, 5);
+        if (n > 0) tc::mbar_wait(step_done, (n - 1) & 1);      // dV / dK of the previous step have read P and dS
+        if (threadIdx.x == 0) TRACE(0, n, 6);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 4; ++c) {
+          *reinterpret_cast<uint4*>(ptile + swz_chunk(a, 4 * grp + c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
           *reinterpret_cast<uint4*>(dstile + swz_chunk(a, 4 * grp + c)) = make_uint4(A16[4 * c], A16[4 * c + 1], A16[4 * c + 2], A16[4 * c + 3]);
+        }
         tc::fence_proxy_async();
+        tc::mbar_arrive(p_ready);
         tc::mbar_arrive(ds_ready);
         if (threadIdx.x == 0) TRACE(0, n, 7);
       }

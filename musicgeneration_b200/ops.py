@@ -25,8 +25,17 @@ def _ptr(t: Optional[torch.Tensor]):
 LAUNCH_CALLS = [0]      # number of launching C-ABI calls made so far (each enqueues >= 1 kernel)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_cur_device = torch.cuda.current_device
+
+
 def _stream():
+    """cudaStream_t of torch's current stream on the current device.  (The public
+    torch.cuda.current_stream() builds a Stream object through four Python layers: 14 us per call, a
+    quarter of the host time of a train step at ~140 calls.)"""
     LAUNCH_CALLS[0] += 1
+    if _raw_stream is not None:
+        return _raw_stream(_cur_device())
     return torch.cuda.current_stream().cuda_stream
 
 

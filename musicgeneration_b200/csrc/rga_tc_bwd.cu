@@ -514,7 +514,7 @@ bool rga_bwd_tc_supported(const RgaArgs& a, int dh, int dtype) {
   if (dh != DHC || dtype != MT_BF16 || !a.causal) return false;
   if (a.sl % 8 || a.sh % 8 || a.sb % 8 || a.ol % 8 || a.oh % 8 || a.ob % 8) return false;
   if (!aligned(a.q, 16) || !aligned(a.k, 16) || !aligned(a.v, 16) || !aligned(a.E, 16) || !aligned(a.dO, 16) ||
-      !aligned(a.dq, 16) || !aligned(a.dk, 16) || !aligned(a.dv, 16))
+      !aligned(a.dq, 16) || !aligned(a.dk, 16) || !aligned(a.dv, 16) || !aligned(a.dE, 16))
     return false;
   return mt_device_ok() != 0;
 }

@@ -950,7 +950,10 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int erow = (grpA ? c0 - (TT - 1) : c0 + 1) + a;
       if (erow >= 0 && erow < p.max_seq) {
 #pragma unroll
-        for (int x = 0; x < 32; ++x) atomicAdd(p.dE + (int64_t)erow * DHC + half * 32 + x, __uint_as_float(r[x]));
+        for (int x = 0; x < 32; x += 4)      // vector reductions: every CTA of a diagonal flushes into the same rows
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.dE + (int64_t)erow * DHC + half * 32 + x),
+                       "f"(__uint_as_float(r[x])), "f"(__uint_as_float(r[x + 1])), "f"(__uint_as_float(r[x + 2])),
+                       "f"(__uint_as_float(r[x + 3])) : "memory");
       }
     } else {
       const Step2 s = step2<ROLE>(p, 0, bh0);

@@ -342,13 +342,26 @@ cast2d_kernel(const TS* __restrict__ s, TD* __restrict__ d, int64_t rows, int64_
   }
 }
 
-__global__ void colsum_fold_kernel(const float* __restrict__ part, float* __restrict__ out,
-                                   int64_t chunks, int64_t N) {
-  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (c >= N) return;
+// 256 threads = 8 warps x 32 columns: warp w sums chunks w, w+8, ... (all loads in flight: one thread walking
+// the <= 128 chunks took 11 us of serial L2 latency per launch), fixed-order fold through shared memory
+__global__ void __launch_bounds__(256) colsum_fold_kernel(const float* __restrict__ part, float* __restrict__ out,
+                                                          int64_t chunks, int64_t N) {
+  __shared__ float sh[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c = blockIdx.x * 32 + tx;
   float s = 0.f;
-  for (int64_t i = 0; i < chunks; ++i) s += part[i * N + c];
-  out[c] = s;
+  if (c < N) {
+#pragma unroll 8
+    for (int64_t i = ty; i < chunks; i += 8) s += part[i * N + c];
+  }
+  sh[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < N) {
+    float t = sh[0][tx];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t += sh[w][tx];
+    out[c] = t;
+  }
 }
 
 template <typename TS, typename TD>
@@ -432,7 +445,8 @@ smooth_ce_reduce_kernel(const float* __restrict__ row_loss, const float* __restr
   __shared__ unsigned long long sv[32], sc[32];
   double l = 0.0;
   unsigned long long nv = 0, nc = 0;
-  for (int64_t i = threadIdx.x; i < T; i += blockDim.x) {
+#pragma unroll 8
+  for (int64_t i = threadIdx.x; i < T; i += blockDim.x) {        // (loads of 8 iterations in flight; same add order)
     l += (double)row_loss[i];
     float f = row_flags[i];
     int fi = (int)f;
@@ -672,7 +686,7 @@ int mt_colsum(const void* X, int dtype, float* out, int64_t M, int64_t N, int64_
   }
   int rc = check_launch("colsum_partial");
   if (rc) return rc;
-  colsum_fold_kernel<<<(unsigned)((N + 127) / 128), 128, 0, as_stream(stream)>>>((const float*)workspace, out, chunks, N);
+  colsum_fold_kernel<<<(unsigned)((N + 31) / 32), 256, 0, as_stream(stream)>>>((const float*)workspace, out, chunks, N);
   return check_launch("colsum_fold");
 }
 

@@ -46,7 +46,10 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 template <int MT>       // MT = number of 16-row tiles (1..4)
 __global__ void __launch_bounds__(SK_THREADS)
 gemm_skinny_kernel(const SkinnyParams p) {
-  chain_prologue();
+  // Programmatic dependent launch: the successor may start launching now; the weight rows (constant during a
+  // decode) are requested BEFORE waiting for the predecessor grid -- only the activation panel depends on it --
+  // so their HBM / L2 latency runs under the predecessor's tail.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ __align__(16) uint8_t smem[];
   const int pitch = p.K + SK_PAD;                                   // elements
   __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem);       // [MT*16][pitch]
@@ -61,16 +64,17 @@ gemm_skinny_kernel(const SkinnyParams p) {
   // load-then-store loop serialised ~16 L2 round trips per thread)
   const int kvs = 31 - __clz(kv);                                   // shift instead of a division when kv is a power of two
   const bool pow2 = (kv & (kv - 1)) == 0;
+  for (int v = tid; v < SK_BN * kv; v += SK_THREADS) {
+    const int r = pow2 ? (v >> kvs) : v / kv, c = v - r * kv;
+    const int n = min(n0 + r, p.N - 1);
+    cp_async16(sW + r * pitch + c * 8, p.W + (int64_t)n * p.ldw + c * 8);
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");       // the activations come from the predecessor
   for (int v = tid; v < MT * 16 * kv; v += SK_THREADS) {
     const int r = pow2 ? (v >> kvs) : v / kv, c = v - r * kv;
     __nv_bfloat16* dst = sA + r * pitch + c * 8;
     if (r < p.M) cp_async16(dst, p.A + (int64_t)r * p.lda + c * 8);
     else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
-  }
-  for (int v = tid; v < SK_BN * kv; v += SK_THREADS) {
-    const int r = pow2 ? (v >> kvs) : v / kv, c = v - r * kv;
-    const int n = min(n0 + r, p.N - 1);
-    cp_async16(sW + r * pitch + c * 8, p.W + (int64_t)n * p.ldw + c * 8);
   }
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
   __syncthreads();

@@ -15,7 +15,7 @@ dev = torch.device("cuda:0")
 d, V, pad, layers, L, Bg = 512, 390, 388, 6, 2048, int(os.environ.get("PB", 16))
 mtb.config.pad_token = pad
 torch.manual_seed(0)
-model = mtb.MusicTransformer(embedding_dim=d, vocab_size=V, num_layer=layers, max_seq=L, dropout=0.2,
+model = mtb.MusicTransformer(embedding_dim=d, vocab_size=V, num_layer=layers, max_seq=L, dropout=float(os.environ.get("PDROP", 0.2)),
                              precision="bf16").to(dev)
 model.train()
 crit = mtb.SmoothCrossEntropyLoss(0.1, V, pad)

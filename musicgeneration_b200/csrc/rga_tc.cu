@@ -43,8 +43,8 @@ constexpr int OFF_V = OFF_K + 2 * TILE;        // 2 stages
 constexpr int OFF_E = OFF_V + 2 * TILE;        // 2 stages: the new "hi" block of each step
 constexpr int OFF_ELO = OFF_E + 2 * TILE;      // "lo" block of the first step only
 constexpr int OFF_SCR = OFF_ELO + TILE;
-constexpr int OFF_XCH = OFF_SCR + FW_SCR_BYTES;   // [2 parities][4 quarters][128] floats: row max / row sum exchange
-constexpr int OFF_BAR = OFF_XCH + 2 * 4 * TT * 4;
+constexpr int OFF_XCH = OFF_SCR + FW_SCR_BYTES;   // [2 step parities + 1 epilogue][4 quarters][128] floats: row max / row sum exchange
+constexpr int OFF_BAR = OFF_XCH + 3 * 4 * TT * 4;
 constexpr int FWD_SMEM = OFF_BAR + 256 + 1024;
 static_assert(FWD_SMEM <= 232448, "forward kernel exceeds the 227 KB shared-memory limit");
 
@@ -60,6 +60,7 @@ struct FwdParams {
   float* lse;
   const uint8_t* pad;
   int B, h, L, max_seq, causal, fmt;
+  int heads_per_cta;    // consecutive heads walked by one CTA (same batch row and query tile): halves the per-CTA fixed cost
   float scale_log2;     // log2(e) / sqrt(dh)
   long long* trace;     // MT_RGA_TRACE=z: clock64 stamps of CTA (0,0,z), [2 agents][32 steps][8 events]
   int trace_z;
@@ -90,24 +91,28 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* o_done = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
   uint8_t* spad = reinterpret_cast<uint8_t*>(bars + 10);     // [128] pad flags of the key tile
+  uint64_t* q_free = bars + 26;      // MMA -> producer: the S / G products of a head are done with Q (and ELO)
+  uint64_t* o_free = bars + 27;      // softmax -> MMA: O of the previous head has been read out
   float* xch = reinterpret_cast<float*>(smem + OFF_XCH);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // grid = (h, B, nT): the query-tile index is the slowest dimension, so over the whole launch the
-  // CTAs with the most key tiles are dispatched first
-  const int b = blockIdx.y, hh = blockIdx.x;
+  // grid = (ceil(h / heads_per_cta), B, nT): the query-tile index is the slowest dimension, so over the whole
+  // launch the CTAs with the most key tiles are dispatched first
+  const int b = blockIdx.y, hh0 = blockIdx.x * p.heads_per_cta;
+  const int n_items = min(p.heads_per_cta, p.h - hh0);
   const int i0 = (gridDim.z - 1 - blockIdx.z) * TT;
   const int L = p.L;
   const int n_kt = p.causal ? (i0 / TT + 1) : (L + TT - 1) / TT;
+  const int n_g = n_items * n_kt;            // global steps: head `item` = g / n_kt, key tile jt = g % n_kt
 
   if (warp == FW_MATH_WARPS && lane == 0) {
     tc::tma_prefetch_desc(&tmQ);
     tc::tma_prefetch_desc(&tmK);
     tc::tma_prefetch_desc(&tmV);
     tc::tma_prefetch_desc(&tmE);
-    tc::tma_prefetch_4d(&tmQ, 0, hh, i0, b);       // the CTA's first tiles start towards L2 under the prologue
-    tc::tma_prefetch_4d(&tmK, 0, hh, 0, b);
-    tc::tma_prefetch_4d(&tmV, 0, hh, 0, b);
+    tc::tma_prefetch_4d(&tmQ, 0, hh0, i0, b);      // the CTA's first tiles start towards L2 under the prologue
+    tc::tma_prefetch_4d(&tmK, 0, hh0, 0, b);
+    tc::tma_prefetch_4d(&tmV, 0, hh0, 0, b);
     tc::mbar_init(bar_q, 1);
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&kv_full[s], 1);
@@ -117,6 +122,8 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     tc::mbar_init(s_consumed, FW_MATH_THREADS);
     tc::mbar_init(p_full, FW_MATH_THREADS);
     tc::mbar_init(o_done, 1);
+    tc::mbar_init(q_free, 1);
+    tc::mbar_init(o_free, FW_MATH_THREADS);
     tc::fence_barrier_init();
   }
   if (warp == FW_MATH_WARPS + 1) tc::tmem_alloc(tmem_slot, 512);
@@ -128,18 +135,25 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   if (warp == FW_MATH_WARPS) {
     // ================================ TMA producer ==========================================
     if (lane == 0) {
-      tc::mbar_arrive_expect_tx(bar_q, TILE);
-      tc::tma_load_4d(smem + OFF_Q, &tmQ, bar_q, 0, hh, i0, b);
-      for (int jt = 0; jt < n_kt; ++jt) {
-        const int s = jt & 1;
+      int item = 0, jt = 0;
+      for (int g = 0; g < n_g; ++g) {
+        const int hh = hh0 + item;
+        if (jt == 0) {
+          // Q (and the ELO block) of the previous head: its S / G products must be done with them
+          if (item > 0) tc::mbar_wait(q_free, (item - 1) & 1);
+          tc::mbar_arrive_expect_tx(bar_q, TILE);
+          tc::tma_load_4d(smem + OFF_Q, &tmQ, bar_q, 0, hh, i0, b);
+        }
+        const int s = g & 1;
         const int j0 = jt * TT;
         const int c0 = p.max_seq - 1 - (i0 - j0);
-        tc::mbar_wait(&kv_empty[s], ((jt >> 1) & 1) ^ 1);
+        tc::mbar_wait(&kv_empty[s], ((g >> 1) & 1) ^ 1);
         tc::mbar_arrive_expect_tx(&kv_full[s], (jt == 0 ? 4 : 3) * TILE);
         tc::tma_load_4d(smem + OFF_K + s * TILE, &tmK, &kv_full[s], 0, hh, j0, b);
         tc::tma_load_2d(smem + OFF_E + s * TILE, &tmE, &kv_full[s], 0, c0 + 1);
         if (jt == 0) tc::tma_load_2d(smem + OFF_ELO, &tmE, &kv_full[s], 0, c0 - (TT - 1));
         tc::tma_load_4d(smem + OFF_V + s * TILE, &tmV, &kv_full[s], 0, hh, j0, b);
+        if (++jt == n_kt) { jt = 0; ++item; }
       }
     }
   } else if (warp == FW_MATH_WARPS + 1) {
@@ -153,8 +167,10 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const uint64_t ed0 = tc::make_sdesc(tc::smem_u32(smem + OFF_E), 16, 1024);
       const uint64_t elod = tc::make_sdesc(tc::smem_u32(smem + OFF_ELO), 16, 1024);
       const uint64_t vd0 = tc::make_sdesc(tc::smem_u32(smem + OFF_V), 1024, 1024);
-      auto issue_s = [&](int jt) {
-        const uint64_t so = (uint64_t)(jt & 1) * (TILE >> 4);
+      // S and the new G block of global step g (key tile jt of its head); the first step of a head also
+      // computes the lo block from ELO
+      auto issue_s = [&](int g, int jt, bool last_of_head) {
+        const uint64_t so = (uint64_t)(g & 1) * (TILE >> 4);
         const uint32_t g_hi = tmem + (((jt + 1) & 1) ? TM_G1 : TM_G0);
 #pragma unroll
         for (int k4 = 0; k4 < DHC / 16; ++k4) {
@@ -167,31 +183,37 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             tc::umma_f16(tmem + TM_G0, qd0 + 2 * k4, elod + 2 * k4, idesc_s, k4 != 0);
         }
         tc::umma_commit(s_full);
+        if (last_of_head) tc::umma_commit(q_free);        // Q / ELO may take the next head's tiles
       };
       tc::mbar_wait(bar_q, 0);
       tc::mbar_wait(&kv_full[0], 0);
       tc::tc_fence_after();
-      issue_s(0);
-      for (int jt = 0; jt < n_kt; ++jt) {
-        if (jt + 1 < n_kt) {
-          tc::mbar_wait(s_consumed, jt & 1);
-          FTRACE(1, jt, 0);
-          tc::mbar_wait(&kv_full[(jt + 1) & 1], ((jt + 1) >> 1) & 1);
+      issue_s(0, 0, n_kt == 1);
+      int item = 0, jt = 0;
+      for (int g = 0; g < n_g; ++g) {
+        if (g + 1 < n_g) {
+          const int jn = (jt + 1 == n_kt) ? 0 : jt + 1;
+          tc::mbar_wait(s_consumed, g & 1);
+          FTRACE(1, g, 0);
+          if (jn == 0) tc::mbar_wait(bar_q, (item + 1) & 1);       // the next head's Q
+          tc::mbar_wait(&kv_full[(g + 1) & 1], ((g + 1) >> 1) & 1);
           tc::tc_fence_after();
-          FTRACE(1, jt, 1);
-          issue_s(jt + 1);
-          FTRACE(1, jt, 2);
+          FTRACE(1, g, 1);
+          issue_s(g + 1, jn, jn + 1 == n_kt);
+          FTRACE(1, g, 2);
         }
-        tc::mbar_wait(p_full, jt & 1);
+        tc::mbar_wait(p_full, g & 1);
+        if (jt == 0 && item > 0) tc::mbar_wait(o_free, (item - 1) & 1);   // O of the previous head has been read out
         tc::tc_fence_after();
-        FTRACE(1, jt, 3);
-        const uint64_t vd = vd0 + (uint64_t)(jt & 1) * (TILE >> 4);
+        FTRACE(1, g, 3);
+        const uint64_t vd = vd0 + (uint64_t)(g & 1) * (TILE >> 4);
 #pragma unroll
         for (int k8 = 0; k8 < TT / 16; ++k8)     // P stays in TMEM (A operand): 16 keys = 8 columns; V: 16 key rows = 2048 B
           tc::umma_f16_ts(tmem + TM_O, tmem + TM_P + 8 * k8, vd + 128 * k8, idesc_o, (jt | k8) != 0);
-        tc::umma_commit(&kv_empty[jt & 1]);
+        tc::umma_commit(&kv_empty[g & 1]);
         tc::umma_commit(o_done);
-        FTRACE(1, jt, 4);
+        FTRACE(1, g, 4);
+        if (++jt == n_kt) { jt = 0; ++item; }
       }
     }
   } else {
@@ -214,17 +236,18 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
     float m_run = -INFINITY, l_part = 0.f;             // l_part: this thread's quarter of the row sum
 
-    for (int jt = 0; jt < n_kt; ++jt) {
+    int item = 0, jt = 0;
+    for (int g = 0; g < n_g; ++g) {
       const int j0 = jt * TT;
       if (padrow) {          // stage the key tile's pad flags (overlaps the MMA)
         tc::named_bar_sync(1, FW_MATH_THREADS);
         if (qt == 0) spad[a] = (j0 + a < L) ? padrow[j0 + a] : 1;
         tc::named_bar_sync(1, FW_MATH_THREADS);
       }
-      if (threadIdx.x == 0) FTRACE(0, jt, 0);
-      tc::mbar_wait(s_full, jt & 1);
+      if (threadIdx.x == 0) FTRACE(0, g, 0);
+      tc::mbar_wait(s_full, g & 1);
       tc::tc_fence_after();
-      if (threadIdx.x == 0) FTRACE(0, jt, 1);
+      if (threadIdx.x == 0) FTRACE(0, g, 1);
       const uint32_t g_lo = tmem + ((jt & 1) ? TM_G1 : TM_G0);
       const uint32_t g_hi = tmem + (((jt + 1) & 1) ? TM_G1 : TM_G0);
 
@@ -241,7 +264,7 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       // S / G fully read: the MMA warp may overwrite them with the next key tile
       tc::tc_fence_before();
       tc::mbar_arrive(s_consumed);
-      if (threadIdx.x == 0) FTRACE(0, jt, 2);
+      if (threadIdx.x == 0) FTRACE(0, g, 2);
       skew_fetch_add_32(sv, scr, lane);
 
       // ---- mask (only on the diagonal / ragged / padded tiles) + online softmax (log2 domain)
@@ -275,11 +298,11 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       // exchange the quarter-row maxima with the three partner threads (other quarters, same row);
       // the slots alternate with the step parity, so a slot is rewritten only after its readers
       // passed the following step's barrier
-      float* xs = xch + (jt & 1) * 4 * TT;
+      float* xs = xch + (g & 1) * 4 * TT;
       xs[qt * TT + a] = mx;
-      if (threadIdx.x == 0) FTRACE(0, jt, 3);
+      if (threadIdx.x == 0) FTRACE(0, g, 3);
       tc::named_bar_sync(rowbar, 128);
-      if (threadIdx.x == 0) FTRACE(0, jt, 4);
+      if (threadIdx.x == 0) FTRACE(0, g, 4);
       mx = fmaxf(fmaxf(xs[a], xs[TT + a]), fmaxf(xs[2 * TT + a], xs[3 * TT + a])) * p.scale_log2;   // scale > 0
       float alpha = 1.f;
       if (mx > m_run + RESCALE_LOG2) {          // also the first tile (m_run = -inf) unless fully masked
@@ -303,9 +326,9 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       for (int x = 0; x < 16; ++x) pk[x] = pack16(sv[2 * x], sv[2 * x + 1], p.fmt);
 
       // ---- previous P.V must be complete before O is rescaled and P overwritten
-      if (threadIdx.x == 0) FTRACE(0, jt, 5);
+      if (threadIdx.x == 0) FTRACE(0, g, 5);
       if (jt > 0) {
-        tc::mbar_wait(o_done, (jt - 1) & 1);
+        tc::mbar_wait(o_done, (g - 1) & 1);
         tc::tc_fence_after();
         if (__any_sync(0xffffffffu, alpha != 1.f)) {       // each quarter rescales 16 of O's 64 columns
           uint32_t r[16];
@@ -319,38 +342,52 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       // ---- P (16-bit pairs) into the TMEM A-operand of the P.V MMA: row = lane, this thread's 32
       // key columns are 16 packed columns (no shared-memory round trip for P)
-      if (threadIdx.x == 0) FTRACE(0, jt, 6);
+      if (threadIdx.x == 0) FTRACE(0, g, 6);
       tc::tmem_st_32x16(tmem + TM_P + lane_base + qt * 16, pk);
       tc::tmem_st_wait();
       tc::tc_fence_before();
       tc::mbar_arrive(p_full);
-      if (threadIdx.x == 0) FTRACE(0, jt, 7);
-    }
-    // ---- epilogue: O / l, LSE
-    float* xs = xch + (n_kt & 1) * 4 * TT;
-    xs[qt * TT + a] = l_part;
-    tc::named_bar_sync(rowbar, 128);
-    const float l_run = (xs[a] + xs[TT + a]) + (xs[2 * TT + a] + xs[3 * TT + a]);
-    tc::mbar_wait(o_done, (n_kt - 1) & 1);
-    tc::tc_fence_after();
-    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-    uint32_t packed[8];
-    {
-      uint32_t r[16];
-      tc::tmem_ld_32x16(tmem + TM_O + lane_base + qt * 16, r);
-      tc::tmem_ld_wait();
+      if (threadIdx.x == 0) FTRACE(0, g, 7);
+      if (++jt < n_kt) continue;
+
+      // ---- end of a head: O / l, LSE (the row sums are exchanged through their own slot: the step slots
+      // may already be rewritten by a warp that is ahead)
+      {
+        const int hh = hh0 + item;
+        float* xe = xch + 2 * 4 * TT;
+        xe[qt * TT + a] = l_part;
+        tc::named_bar_sync(rowbar, 128);
+        const float l_run = (xe[a] + xe[TT + a]) + (xe[2 * TT + a] + xe[3 * TT + a]);
+        tc::mbar_wait(o_done, g & 1);
+        tc::tc_fence_after();
+        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+        uint32_t packed[8];
+        {
+          uint32_t r[16];
+          tc::tmem_ld_32x16(tmem + TM_O + lane_base + qt * 16, r);
+          tc::tmem_ld_wait();
 #pragma unroll
-      for (int x = 0; x < 16; x += 2)
-        packed[x / 2] = pack16(__uint_as_float(r[x]) * inv, __uint_as_float(r[x + 1]) * inv, p.fmt);
-    }
-    if (i < L) {
-      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.O) + (int64_t)b * p.ob + (int64_t)i * p.ol +
-                                            (int64_t)hh * p.oh + qt * 16);
-      dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-      dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-      // natural-log LSE of the scaled logits (what the backward and rga_weights consume)
-      if (qt == 0)
-        p.lse[((int64_t)b * p.h + hh) * L + i] = l_run > 0.f ? (m_run + log2f(l_run)) * 0.6931471805599453f : 0.f;
+          for (int x = 0; x < 16; x += 2)
+            packed[x / 2] = pack16(__uint_as_float(r[x]) * inv, __uint_as_float(r[x + 1]) * inv, p.fmt);
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive(o_free);               // the next head's first P.V product may overwrite O
+        if (i < L) {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.O) + (int64_t)b * p.ob + (int64_t)i * p.ol +
+                                                (int64_t)hh * p.oh + qt * 16);
+          dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+          // natural-log LSE of the scaled logits (what the backward and rga_weights consume)
+          if (qt == 0)
+            p.lse[((int64_t)b * p.h + hh) * L + i] = l_run > 0.f ? (m_run + log2f(l_run)) * 0.6931471805599453f : 0.f;
+        }
+        // the partner warps must have read the row sums before this warp's next epilogue rewrites them: the
+        // row barriers of the next head's steps lie in between
+        m_run = -INFINITY;
+        l_part = 0.f;
+        jt = 0;
+        ++item;
+      }
     }
     tc::tc_fence_before();
   }
@@ -394,7 +431,18 @@ int rga_fwd_tc(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
     if (e != cudaSuccess) { set_error("rga_fwd_tc: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_done = true;
   }
-  dim3 grid(a.h, a.B, (a.L + TT - 1) / TT);
+  // consecutive heads of one (batch row, query tile) share a CTA: same number of key tiles, same E blocks; the
+  // per-CTA fixed cost (launch, TMEM allocation, barrier set-up, pipeline fill) is paid once per pair
+  // (measured at config B, 2048 tile rows: 1 head per CTA 0.304 ms, 2 heads 0.287 ms, 4 heads 0.282 ms); as many
+  // as leave at least three CTAs per SM
+  static const int hpc_env = getenv("MT_FWD_HPC") ? atoi(getenv("MT_FWD_HPC")) : 0;
+  const int nT = (a.L + TT - 1) / TT;
+  int hpc = 1;
+  for (int c = 4; c > 1; c >>= 1)
+    if ((int64_t)((a.h + c - 1) / c) * a.B * nT >= 3 * (int64_t)sm_count()) { hpc = c; break; }
+  if (hpc_env > 0) hpc = hpc_env;
+  p.heads_per_cta = hpc > a.h ? a.h : hpc;
+  dim3 grid((a.h + p.heads_per_cta - 1) / p.heads_per_cta, a.B, nT);
   p.trace = nullptr;
   p.trace_z = 0;
   static const bool want_trace = getenv("MT_RGA_TRACE") != nullptr;

@@ -52,10 +52,11 @@ template <> struct Lay3<L_DE> {      // Q x 2; dG x 2
   static constexpr uint32_t TMEM_COLS = 128;       // dE_lo | dE_hi
 };
 constexpr uint32_t TM3_DS = 64;          // dQ role: dS slot s at columns 64 + 64*s
+constexpr uint32_t TM3_ACC1 = 192;       // dQ role: second dQ accumulator (heads alternate between columns 0 and 192)
 template <int ROLE> constexpr int smem3_bytes() { return Lay3<ROLE>::BAR + 256; }
 static_assert(smem3_bytes<L_DQ>() <= 232448 && smem3_bytes<L_DE>() <= 232448, "shared memory budget");
 
-enum { B3_XF = 0, B3_XE = 2, B3_DGR = 4, B3_DGF = 6, B3_DONE = 8, B3_TMEM = 9 };
+enum { B3_XF = 0, B3_XE = 2, B3_DGR = 4, B3_DGF = 6, B3_DONE = 8, B3_TMEM = 10 };     // B3_DONE: [2] (dQ role: one per accumulator)
 
 struct Bwd3Params {
   const uint8_t* ws;                     // dS tiles: [(b*h+hh)][it*(it+1)/2 + jt][32 KB]
@@ -63,6 +64,7 @@ struct Bwd3Params {
   float* dE;
   int B, h, L, max_seq, nT, nTri;
   int bh_per_cta;                        // dE role
+  int heads_per_cta;                     // dQ role: consecutive heads of one (batch row, query tile) walked by one CTA
   long long* trace;                      // MT_RGA_TRACE=z: clock64 stamps of CTA (0,0,z), [2 agents][32 steps][4 events]
   int trace_z;
 };
@@ -79,7 +81,10 @@ struct Step3 { int it, jt, b, hh; };
 template <int ROLE>
 __device__ __forceinline__ int num_steps3(const Bwd3Params& p, int& bh0) {
   bh0 = 0;
-  if (ROLE == L_DQ) return p.nT - (int)blockIdx.z;             // it = nT-1-blockIdx.z: longest first
+  if (ROLE == L_DQ) {                                          // it = nT-1-blockIdx.z: longest first
+    const int items = min(p.heads_per_cta, p.h - (int)blockIdx.x * p.heads_per_cta);
+    return items * (p.nT - (int)blockIdx.z);
+  }
   bh0 = (int)blockIdx.x * p.bh_per_cta;
   const int nbh = min(p.bh_per_cta, p.B * p.h - bh0);
   return nbh > 0 ? nbh * (p.nT - (int)blockIdx.z) : 0;
@@ -87,13 +92,16 @@ __device__ __forceinline__ int num_steps3(const Bwd3Params& p, int& bh0) {
 template <int ROLE>
 __device__ __forceinline__ Step3 step3_first(const Bwd3Params& p, int bh0) {
   Step3 s;
-  if (ROLE == L_DQ) { s.it = p.nT - 1 - (int)blockIdx.z; s.jt = 0; s.hh = blockIdx.x; s.b = blockIdx.y; }
+  if (ROLE == L_DQ) { s.it = p.nT - 1 - (int)blockIdx.z; s.jt = 0; s.hh = blockIdx.x * p.heads_per_cta; s.b = blockIdx.y; }
   else { s.it = (int)blockIdx.z; s.jt = 0; s.b = bh0 / p.h; s.hh = bh0 % p.h; }
   return s;
 }
 template <int ROLE>
 __device__ __forceinline__ void step3_advance(const Bwd3Params& p, Step3& s) {
-  if (ROLE == L_DQ) { ++s.jt; return; }
+  if (ROLE == L_DQ) {                                    // next key tile, or the first one of the next head
+    if (s.jt < s.it) ++s.jt; else { s.jt = 0; ++s.hh; }
+    return;
+  }
   if (s.it + 1 < p.nT) { ++s.it; ++s.jt; return; }       // next tile down the diagonal
   s.it = (int)blockIdx.z; s.jt = 0;                      // next (batch, head) of the slice
   if (++s.hh == p.h) { s.hh = 0; ++s.b; }
@@ -130,7 +138,8 @@ rga_bwd3_kernel(const __grid_constant__ CUtensorMap tmX,      // K (dQ role) or 
       tc::mbar_init(&dg_ready[s], CV_THREADS / 32);
       tc::mbar_init(&dg_free[s], 1);
     }
-    tc::mbar_init(acc_done, 1);
+    tc::mbar_init(&acc_done[0], 1);
+    tc::mbar_init(&acc_done[1], 1);
     tc::fence_barrier_init();
   }
   if (warp == W_MMA) tc::tmem_alloc(tmem_slot, LY::TMEM_COLS);
@@ -156,10 +165,13 @@ rga_bwd3_kernel(const __grid_constant__ CUtensorMap tmX,      // K (dQ role) or 
         tc::mbar_wait(&x_empty[st], ((n >> 1) & 1) ^ 1);
         if (ROLE == L_DQ) {
           const int c0 = p.max_seq - 1 - (s.it - s.jt) * TT;
-          tc::mbar_arrive_expect_tx(&x_full[st], (n == 0 ? 3 : 2) * TILE);
+          const bool first = (s.jt == 0);             // first key tile of a head: its lo block is loaded too
+          // ... into the slot that holds the hi block of the previous head's last step: wait for that step as well
+          if (first && n > 0) tc::mbar_wait(&x_empty[(n - 1) & 1], ((n - 1) >> 1) & 1);
+          tc::mbar_arrive_expect_tx(&x_full[st], (first ? 3 : 2) * TILE);
           tc::tma_load_4d(smem + LY::X0 + st * TILE, &tmX, &x_full[st], 0, s.hh, s.jt * TT, s.b);
           tc::tma_load_2d(smem + LY::E0 + eslot(n) * TILE, &tmE, &x_full[st], 0, c0 + 1);
-          if (n == 0) tc::tma_load_2d(smem + LY::E0 + eslot(-1) * TILE, &tmE, &x_full[st], 0, c0 - (TT - 1));
+          if (first) tc::tma_load_2d(smem + LY::E0 + eslot(n - 1) * TILE, &tmE, &x_full[st], 0, c0 - (TT - 1));
         } else {
           tc::mbar_arrive_expect_tx(&x_full[st], TILE);
           tc::tma_load_4d(smem + LY::X0 + st * TILE, &tmX, &x_full[st], 0, s.hh, s.it * TT, s.b);
@@ -180,9 +192,12 @@ rga_bwd3_kernel(const __grid_constant__ CUtensorMap tmX,      // K (dQ role) or 
         const uint64_t kd_mn0 = tc::make_sdesc(tc::smem_u32(smem + LY::X0), 1024, 1024);
         const uint64_t ed_mn0 = tc::make_sdesc(tc::smem_u32(smem + LY::E0), 1024, 1024);
         const uint64_t dgd0 = tc::make_sdesc(tc::smem_u32(smem + LY::DG), 16, 1024);
+        const int per = p.nT - (int)blockIdx.z;           // key tiles (steps) per head
+        int jt = 0, item = 0;
         for (int n = 0; n < nsteps; ++n) {
           const uint64_t st = n & 1;
           const uint32_t par = (n >> 1) & 1;
+          const uint32_t acc = tmem + ((item & 1) ? TM3_ACC1 : 0u);      // heads alternate between two accumulators
           tc::mbar_wait(&x_full[st], par);
           TRACE3(1, n, 0);
           tc::mbar_wait(&dg_ready[st], par);
@@ -190,16 +205,17 @@ rga_bwd3_kernel(const __grid_constant__ CUtensorMap tmX,      // K (dQ role) or 
           TRACE3(1, n, 1);
 #pragma unroll
           for (int k16 = 0; k16 < TT / 16; ++k16)         // dQ += dS . K_j : dS is the TMEM A operand (8 columns per 16 keys)
-            tc::umma_f16_ts(tmem, tmem + TM3_DS + 64 * (uint32_t)st + 8 * k16, kd_mn0 + st * TS16 + 128 * k16, id_kmn,
-                            (n | k16) != 0);
+            tc::umma_f16_ts(acc, tmem + TM3_DS + 64 * (uint32_t)st + 8 * k16, kd_mn0 + st * TS16 + 128 * k16, id_kmn,
+                            (jt | k16) != 0);
           const uint64_t elo = (uint64_t)eslot(n - 1) * TS16, ehi = (uint64_t)eslot(n) * TS16;
           const uint64_t dgd = dgd0 + st * 4 * TS16;
 #pragma unroll
           for (int k16 = 0; k16 < 2 * TT / 16; ++k16)     // dQ += dG . [E_lo; E_hi] (contraction over the band)
-            tc::umma_f16(tmem, dgd + (uint64_t)(k16 >> 2) * TS16 + 2 * (k16 & 3),
+            tc::umma_f16(acc, dgd + (uint64_t)(k16 >> 2) * TS16 + 2 * (k16 & 3),
                          ed_mn0 + (k16 < 8 ? elo + 128 * k16 : ehi + 128 * (k16 - 8)), id_kmn, 1);
           tc::umma_commit(&dg_free[st]);
           tc::umma_commit(&x_empty[st]);
+          if (++jt == per) { tc::umma_commit(&acc_done[item & 1]); jt = 0; ++item; }
           TRACE3(1, n, 2);
         }
       } else {
@@ -225,7 +241,7 @@ rga_bwd3_kernel(const __grid_constant__ CUtensorMap tmX,      // K (dQ role) or 
           TRACE3(1, n, 2);
         }
       }
-      tc::umma_commit(acc_done);
+      if (ROLE == L_DE) tc::umma_commit(&acc_done[0]);
     }
   } else {
     // ================================ converters: dS tile -> registers -> band dG (+ TMEM dS) =====
@@ -288,28 +304,22 @@ rga_bwd3_kernel(const __grid_constant__ CUtensorMap tmX,      // K (dQ role) or 
       tc::mbar_arrive_warp(&dg_ready[st]);
       if (threadIdx.x == 0) TRACE3(0, n, 3);
     };
-    uint32_t R0[16], R1[16], R2[16];
-    fetch(R0);
-    fetch(R1);
-    for (int n = 0; n < nsteps; n += 3) {
-      fetch(R2);
-      process(R0, n);
-      if (n + 1 < nsteps) { fetch(R0); process(R1, n + 1); }
-      if (n + 2 < nsteps) { fetch(R1); process(R2, n + 2); }
-    }
-
-    // ---- epilogue
-    tc::mbar_wait(acc_done, 0);
-    tc::tc_fence_after();
-    if (ROLE == L_DQ) {           // 64 accumulator columns: this thread takes 16 of row a
+    // dQ role: the accumulator of head `item` (columns 0 or TM3_ACC1) -> dq.  Called one step into the next head
+    // (the products of the head's last step have finished by then; the accumulators alternate, so the next
+    // head's products do not touch it) and once after the loop.
+    const int per = (ROLE == L_DQ) ? p.nT - (int)blockIdx.z : 1;
+    auto store_dq = [&](int item) {
+      tc::mbar_wait(&acc_done[item & 1], (item >> 1) & 1);
+      tc::tc_fence_after();
       uint32_t r[16];
-      tc::tmem_ld_32x16(tmem + lane_base + q4 * 16, r);
+      tc::tmem_ld_32x16(tmem + ((item & 1) ? TM3_ACC1 : 0u) + lane_base + q4 * 16, r);
       tc::tmem_ld_wait();
+      tc::tc_fence_before();
       const Step3 s = step3_first<ROLE>(p, bh0);
       const int row = s.it * TT + a;
       if (row < p.L) {
         uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dq) + (int64_t)s.b * p.sb +
-                                              (int64_t)row * p.sl + (int64_t)s.hh * p.sh + q4 * 16);
+                                              (int64_t)row * p.sl + (int64_t)(s.hh + item) * p.sh + q4 * 16);
 #pragma unroll
         for (int x = 0; x < 2; ++x)
           dst[x] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * x]), __uint_as_float(r[8 * x + 1])),
@@ -317,6 +327,31 @@ rga_bwd3_kernel(const __grid_constant__ CUtensorMap tmX,      // K (dQ role) or 
                               pack_bf16x2(__uint_as_float(r[8 * x + 4]), __uint_as_float(r[8 * x + 5])),
                               pack_bf16x2(__uint_as_float(r[8 * x + 6]), __uint_as_float(r[8 * x + 7])));
       }
+    };
+    int cjt = 0, citem = 0;                // converter-side position inside the head
+    auto after = [&]() {
+      if (ROLE != L_DQ) return;
+      if (cjt == 0 && citem > 0) store_dq(citem - 1);     // first step of a new head is converted: flush the previous one
+      if (++cjt == per) { cjt = 0; ++citem; }
+    };
+    uint32_t R0[16], R1[16], R2[16];
+    fetch(R0);
+    fetch(R1);
+    for (int n = 0; n < nsteps; n += 3) {
+      fetch(R2);
+      process(R0, n); after();
+      if (n + 1 < nsteps) { fetch(R0); process(R1, n + 1); after(); }
+      if (n + 2 < nsteps) { fetch(R1); process(R2, n + 2); after(); }
+    }
+
+    // ---- epilogue
+    if (ROLE == L_DQ) {
+      store_dq(citem - 1);        // (the loop ends on the last step of a head: citem = number of heads walked)
+    } else {
+      tc::mbar_wait(&acc_done[0], 0);
+      tc::tc_fence_after();
+    }
+    if (ROLE == L_DQ) {
     } else {                      // two blocks of 128 E rows x 64: quarters 0,1 the lo block, 2,3 the hi block
       const int c0 = p.max_seq - 1 - (int)blockIdx.z * TT;
       const int erow = ((q4 >> 1) == 0 ? c0 - (TT - 1) : c0 + 1) + a;
@@ -391,6 +426,7 @@ Bwd3Params make_params3(const RgaArgs& a, const void* ws) {
   p.nT = (a.L + TT - 1) / TT;
   p.nTri = p.nT * (p.nT + 1) / 2;
   p.bh_per_cta = 1;
+  p.heads_per_cta = 1;
   p.trace = nullptr;
   p.trace_z = 0;
   return p;
@@ -406,7 +442,15 @@ size_t rga_bwd3_workspace_bytes(int64_t B, int64_t h, int64_t L) {
 // dQ from the spilled dS tiles (query-tile owner walks the key tiles at or left of it)
 int rga_bwd3_dq(const RgaArgs& a, const void* ws, const CUtensorMap& tmK, const CUtensorMap& tmE, cudaStream_t st) {
   Bwd3Params p = make_params3(a, ws);
-  return launch_role3<L_DQ>(tmK, tmE, p, dim3(a.h, a.B, p.nT), st);
+  // consecutive heads of one (batch row, query tile) share a CTA (same number of key tiles, same E blocks, two
+  // alternating accumulators): as many as leave at least three CTAs per SM
+  static const int hpc_env = getenv("MT_DQ_HPC") ? atoi(getenv("MT_DQ_HPC")) : 0;
+  int hpc = 1;
+  for (int c = 4; c > 1; c >>= 1)
+    if ((int64_t)((a.h + c - 1) / c) * a.B * p.nT >= 3 * (int64_t)sm_count()) { hpc = c; break; }
+  if (hpc_env > 0) hpc = hpc_env;
+  p.heads_per_cta = hpc > a.h ? a.h : hpc;
+  return launch_role3<L_DQ>(tmK, tmE, p, dim3((a.h + p.heads_per_cta - 1) / p.heads_per_cta, a.B, p.nT), st);
 }
 
 // dE from the spilled dS tiles (tile-diagonal owner walks down the diagonal over a slice of (batch, head))

@@ -93,6 +93,7 @@ struct Bwd2Params {
   int B, h, L, max_seq, nT;
   int bh_per_cta;                        // DE role
   uint8_t* ds_ws; int nTri;              // DKV role: spill every dS tile image here (rga_tc_bwd3.cu consumes them)
+  int heads_per_cta;                     // DKV role: consecutive heads of one (batch row, key tile) walked by one CTA
   float scale, scale_log2;
   long long* trace;                      // MT_RGA_TRACE=z: clock64 stamps of CTA (0,0,z), [4 agents][32 steps][8 events]
   int trace_z;
@@ -112,7 +113,7 @@ __device__ __forceinline__ int num_steps2(const Bwd2Params& p, int& bh0) {
   // grid = (h, B, nT) [DKV] or (slices, 1, nT) [DE]: the tile / diagonal index is the SLOWEST grid
   // dimension, so CTAs are dispatched longest-first over the whole launch
   bh0 = 0;
-  if (ROLE == R_DKV) return p.nT - (int)blockIdx.z;
+  if (ROLE == R_DKV) return min(p.heads_per_cta, p.h - (int)blockIdx.x * p.heads_per_cta) * (p.nT - (int)blockIdx.z);
   if (ROLE == R_DQ) return p.nT - (int)blockIdx.z;             // it = nT-1-blockIdx.z  ->  it+1 key tiles
   bh0 = (int)blockIdx.x * p.bh_per_cta;
   int nbh = min(p.bh_per_cta, p.B * p.h - bh0);
@@ -121,7 +122,10 @@ __device__ __forceinline__ int num_steps2(const Bwd2Params& p, int& bh0) {
 template <int ROLE>
 __device__ __forceinline__ Step2 step2(const Bwd2Params& p, int n, int bh0) {
   Step2 s;
-  if (ROLE == R_DKV) { s.jt = blockIdx.z; s.it = s.jt + n; s.hh = blockIdx.x; s.b = blockIdx.y; }
+  if (ROLE == R_DKV) {
+    const int per = p.nT - (int)blockIdx.z;       // query tiles (steps) per head
+    s.jt = blockIdx.z; s.it = s.jt + n % per; s.hh = (int)blockIdx.x * p.heads_per_cta + n / per; s.b = blockIdx.y;
+  }
   else if (ROLE == R_DQ) { s.it = p.nT - 1 - (int)blockIdx.z; s.jt = n; s.hh = blockIdx.x; s.b = blockIdx.y; }
   else {
     const int per = p.nT - (int)blockIdx.z;
@@ -134,7 +138,10 @@ __device__ __forceinline__ Step2 step2(const Bwd2Params& p, int n, int bh0) {
 // step n+1 from step n without the integer divisions of step2 (they sat in every agent's per-step chain)
 template <int ROLE>
 __device__ __forceinline__ void step_advance(const Bwd2Params& p, Step2& s) {
-  if (ROLE == R_DKV) { ++s.it; return; }
+  if (ROLE == R_DKV) {                                   // next query tile, or the first one of the next head
+    if (s.it + 1 < p.nT) ++s.it; else { s.it = (int)blockIdx.z; ++s.hh; }
+    return;
+  }
   if (ROLE == R_DQ) { ++s.jt; return; }
   if (s.it + 1 < p.nT) { ++s.it; ++s.jt; return; }       // next tile down the diagonal
   s.it = (int)blockIdx.z; s.jt = 0;                      // next (batch, head) of the slice
@@ -256,12 +263,9 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ================================ TMA producer ==========================================
     if (lane == 0) {
       if (ROLE == R_DKV) {
-        const Step2 s0 = step2<ROLE>(p, 0, bh0);
-        tc::mbar_arrive_expect_tx(bar_res, 2 * TILE);
-        tc::tma_load_4d(buf_k(), &tmK, bar_res, 0, s0.hh, s0.jt * TT, s0.b);
-        tc::tma_load_4d(buf_v(), &tmV, bar_res, 0, s0.hh, s0.jt * TT, s0.b);
-        Step2 s = s0;
+        Step2 s = step2<ROLE>(p, 0, bh0);
         for (int n = 0; n < nsteps; ++n, step_advance<ROLE>(p, s)) {
+          const bool head_start = (s.it == (int)blockIdx.z);
           // {Q, dO} slot n % 3: last read by the dV / dK products of step n-3 -- these loads run two steps ahead
           const int q3 = n % 3;
           tc::mbar_wait(&qd_empty[q3], ((n / 3) & 1) ^ 1);
@@ -269,15 +273,32 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tc::tma_load_4d(buf_q(n), &tmQ, &qd_full[q3], 0, s.hh, s.it * TT, s.b);
           tc::tma_load_4d(buf_do(n), &tmDO, &qd_full[q3], 0, s.hh, s.it * TT, s.b);
           if (n + 3 < nsteps) {       // pull the tiles of step n+3 into L2
-            tc::tma_prefetch_4d(&tmQ, 0, s.hh, (s.it + 3) * TT, s.b);
-            tc::tma_prefetch_4d(&tmDO, 0, s.hh, (s.it + 3) * TT, s.b);
+            Step2 t = s;
+            step_advance<ROLE>(p, t); step_advance<ROLE>(p, t); step_advance<ROLE>(p, t);
+            tc::tma_prefetch_4d(&tmQ, 0, t.hh, t.it * TT, t.b);
+            tc::tma_prefetch_4d(&tmDO, 0, t.hh, t.it * TT, t.b);
+            if (t.it == (int)blockIdx.z) {      // ... and the K / V tiles of a head that starts there
+              tc::tma_prefetch_4d(&tmK, 0, t.hh, t.jt * TT, t.b);
+              tc::tma_prefetch_4d(&tmV, 0, t.hh, t.jt * TT, t.b);
+            }
+          }
+          if (head_start) {
+            // the head's resident K / V tiles: the S and dP products of the previous head's last step must be done
+            // with the old ones (dp_full is committed after both)
+            // (this thread runs up to two steps ahead: dp_full may still be in phase n-2, where a parity-only wait
+            // for phase n-1 would pass at once -- so phase n-2 first; phase n-3 is known complete from s_full(n-2))
+            if (n > 1) tc::mbar_wait(dp_full, (n - 2) & 1);
+            if (n > 0) tc::mbar_wait(dp_full, (n - 1) & 1);
+            tc::mbar_arrive_expect_tx(bar_res, 2 * TILE);
+            tc::tma_load_4d(buf_k(), &tmK, bar_res, 0, s.hh, s.jt * TT, s.b);
+            tc::tma_load_4d(buf_v(), &tmV, bar_res, 0, s.hh, s.jt * TT, s.b);
           }
           // E slot n & 1 held the hi block of step n-1: free once G(n-1) is computed, which s_full(n-1) covers
           if (n >= 1) tc::mbar_wait(s_full, (n - 1) & 1);
           const int c0 = p.max_seq - 1 - (s.it - s.jt) * TT;
-          tc::mbar_arrive_expect_tx(&e_full[n & 1], (n == 0 ? 2 : 1) * TILE);
+          tc::mbar_arrive_expect_tx(&e_full[n & 1], (head_start ? 2 : 1) * TILE);
           tc::tma_load_2d(buf_elo(n), &tmE, &e_full[n & 1], 0, c0 - (TT - 1));
-          if (n == 0) tc::tma_load_2d(buf_ehi(0), &tmE, &e_full[0], 0, c0 + 1);
+          if (head_start) tc::tma_load_2d(buf_ehi(n), &tmE, &e_full[n & 1], 0, c0 + 1);
         }
       } else if (ROLE == R_DQ) {
         Step2 s = step2<ROLE>(p, 0, bh0);
@@ -364,6 +385,8 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc::tc_fence_after();
         issue_g(0);
         issue_s(0);
+        const int per = p.nT - (int)blockIdx.z;   // steps per head
+        int k = 0, item = 0;
         for (int n = 0; n < nsteps; ++n) {
           const uint32_t par = n & 1;
           tc::mbar_wait(sg_free, par);            // every math warp has S and G of the step in registers
@@ -375,7 +398,9 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tc::umma_f16(tmem + TM_S, dod + 2 * k4, vd + 2 * k4, id_kk, k4 != 0);
           tc::umma_commit(dp_full);
           TRACE(3, n, 1);
+          if (++k == per) { k = 0; ++item; }
           if (n + 1 < nsteps) {
+            if (k == 0) tc::mbar_wait(bar_res, item & 1);          // K / V of the head that starts with step n+1
             tc::mbar_wait(&qd_full[(n + 1) % 3], ((n + 1) / 3) & 1);
             tc::mbar_wait(&e_full[(n + 1) & 1], ((n + 1) >> 1) & 1);
             tc::tc_fence_after();
@@ -573,6 +598,8 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint64_t dod_mn0 = tc::make_sdesc(tc::smem_u32(smem + Lay2<R_DKV>::DO0), 1024, 1024);
       const uint64_t opd0 = tc::make_sdesc(tc::smem_u32(smem + Lay2<R_DKV>::P), TILE, 1024);
       const uint64_t opd1 = tc::make_sdesc(tc::smem_u32(smem + Lay2<R_DKV>::DS), TILE, 1024);
+      const int per = p.nT - (int)blockIdx.z;     // steps per head
+      int k = 0, hh = (int)blockIdx.x * p.heads_per_cta;
       for (int n = 0; n < nsteps; ++n) {
         const uint32_t par = n & 1;
         const uint64_t dod_mn = dod_mn0 + (uint64_t)(n % 3) * STR, qd_mn = qd_mn0 + (uint64_t)(n % 3) * STR;
@@ -580,20 +607,21 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc::mbar_wait(ds_ready, par);
         tc::tc_fence_after();
         if (p.ds_ws) {        // the dS operand image (32 KB, swizzled) goes to the workspace as it is
-          const int it = (int)blockIdx.z + n, jt = (int)blockIdx.z;
-          uint8_t* dst = p.ds_ws + (((int64_t)blockIdx.y * p.h + blockIdx.x) * p.nTri + (it * (it + 1) / 2 + jt)) *
+          const int it = (int)blockIdx.z + k, jt = (int)blockIdx.z;
+          uint8_t* dst = p.ds_ws + (((int64_t)blockIdx.y * p.h + hh) * p.nTri + (it * (it + 1) / 2 + jt)) *
                                        (int64_t)(2 * TILE);
           tc::bulk_store_1d(dst, smem + Lay2<R_DKV>::DS, 2 * TILE);
           tc::bulk_commit();
         }
 #pragma unroll
         for (int k16 = 0; k16 < TT / 16; ++k16) {      // contraction over the 128 query rows
-          tc::umma_f16(tmem + TM_ACC1, opd0 + 128 * k16, dod_mn + 128 * k16, id_mnmn, (n | k16) != 0);   // dV += P^T dO
-          tc::umma_f16(tmem + TM_ACC0, opd1 + 128 * k16, qd_mn + 128 * k16, id_mnmn, (n | k16) != 0);    // dK += dS^T Q
+          tc::umma_f16(tmem + TM_ACC1, opd0 + 128 * k16, dod_mn + 128 * k16, id_mnmn, (k | k16) != 0);   // dV += P^T dO
+          tc::umma_f16(tmem + TM_ACC0, opd1 + 128 * k16, qd_mn + 128 * k16, id_mnmn, (k | k16) != 0);    // dK += dS^T Q
         }
         if (p.ds_ws) tc::bulk_wait_read0();            // the math warps overwrite dS once step_done is signalled
         tc::umma_commit(&qd_empty[n % 3]);
         tc::umma_commit(step_done);
+        if (++k == per) { k = 0; ++hh; }               // (the first products of the next head restart the accumulators)
       }
       if (p.ds_ws) tc::bulk_wait0();
     }
@@ -623,6 +651,24 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float lse_next = row_stat(p.lse, s), d_next = row_stat(p.delta, s);
       uint8_t* const ptile = pbuf + half * TILE;
       uint8_t* const dstile = smem + Lay2<R_DKV>::DS + half * TILE;
+      // dK (warps 0-7, ACC0) / dV (warps 8-15, ACC1) of head hh -> global; each thread 32 of the 64 columns of key row a
+      auto store_acc = [&](int hh) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32(tmem + (grp ? TM_ACC1 : TM_ACC0) + lane_base + half * 32, r);
+        tc::tmem_ld_wait();
+        tc::tc_fence_before();
+        const int row = (int)blockIdx.z * TT + a;
+        if (row < p.L) {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(grp ? p.dv : p.dk) + (int64_t)blockIdx.y * p.sb +
+                                                (int64_t)row * p.sl + (int64_t)hh * p.sh + half * 32);
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+            dst[x] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * x]), __uint_as_float(r[8 * x + 1])),
+                                pack_bf16x2(__uint_as_float(r[8 * x + 2]), __uint_as_float(r[8 * x + 3])),
+                                pack_bf16x2(__uint_as_float(r[8 * x + 4]), __uint_as_float(r[8 * x + 5])),
+                                pack_bf16x2(__uint_as_float(r[8 * x + 6]), __uint_as_float(r[8 * x + 7])));
+        }
+      };
       for (int n = 0; n < nsteps; ++n, s = snext) {
         const uint32_t par = n & 1;
         const int i0 = s.it * TT, j0 = s.jt * TT;
@@ -702,6 +748,13 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (threadIdx.x == 0) TRACE(0, n, 5);
         if (n > 0) tc::mbar_wait(step_done, (n - 1) & 1);      // dV / dK of the previous step have read P and dS
         if (threadIdx.x == 0) TRACE(0, n, 6);
+        if (n > 0 && i0 == j0) {
+          // first step of a new head: the previous head's dK / dV are complete (step_done above) and must leave
+          // TMEM before this step's products -- issued once every thread has arrived on p_ready / ds_ready
+          // below -- restart the accumulators
+          tc::tc_fence_after();
+          store_acc(s.hh - 1);
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           *reinterpret_cast<uint4*>(ptile + swz_chunk(a, 4 * grp + c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
@@ -712,6 +765,10 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc::mbar_arrive(ds_ready);
         if (threadIdx.x == 0) TRACE(0, n, 7);
       }
+      // the last head (s is one step past it: s.hh has already advanced)
+      tc::mbar_wait(step_done, (nsteps - 1) & 1);
+      tc::tc_fence_after();
+      store_acc(s.hh - 1);
     } else if (grpA) {
       // ================================ group A: S + skew -> P ================================
       uint32_t* scr = reinterpret_cast<uint32_t*>(smem + LY::SCR) + threadIdx.x * SCRB_WORDS;
@@ -927,6 +984,7 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
     // ---- epilogue: accumulators out of TMEM; group A takes ACC0, group B ACC1; each thread 32 of
     // the 64 columns of its row
+    if (!(ROLE == R_DKV && MT_DKV_FUSED16)) {
     tc::mbar_wait(step_done, (nsteps - 1) & 1);
     tc::tc_fence_after();
     uint32_t r[32];
@@ -970,6 +1028,7 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           dst[x] = make_uint4(packed[4 * x], packed[4 * x + 1], packed[4 * x + 2], packed[4 * x + 3]);
       }
     }
+    }   // (!DKV)
     tc::tc_fence_before();
   }
   __syncthreads();
@@ -1030,6 +1089,7 @@ Bwd2Params make_params2(const RgaArgs& a) {
   p.scale_log2 = LOG2E / a.inv_scale_div;
   p.bh_per_cta = 1;
   p.ds_ws = nullptr;
+  p.heads_per_cta = 1;
   p.nTri = p.nT * (p.nT + 1) / 2;
   p.trace = nullptr;
   p.trace_z = 0;
@@ -1043,7 +1103,15 @@ int rga_bwd2_dkv(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tm
                  const CUtensorMap& tmDO, const CUtensorMap& tmE, void* ds_ws, cudaStream_t st) {
   Bwd2Params p = make_params2(a);
   p.ds_ws = static_cast<uint8_t*>(ds_ws);
-  return launch_role2<R_DKV>(tmQ, tmK, tmV, tmDO, tmE, p, dim3(a.h, a.B, p.nT), st);
+  // consecutive heads of one (batch row, key tile) share a CTA (same walk over the query tiles; the resident K / V
+  // tiles are reloaded and dK / dV flushed at the head boundary): as many as leave at least three CTAs per SM
+  static const int hpc_env = getenv("MT_DKV_HPC") ? atoi(getenv("MT_DKV_HPC")) : 0;
+  int hpc = 1;
+  for (int c = 4; c > 1; c >>= 1)
+    if ((int64_t)((a.h + c - 1) / c) * a.B * p.nT >= 3 * (int64_t)sm_count()) { hpc = c; break; }
+  if (hpc_env > 0) hpc = hpc_env;
+  p.heads_per_cta = hpc > a.h ? a.h : hpc;
+  return launch_role2<R_DKV>(tmQ, tmK, tmV, tmDO, tmE, p, dim3((a.h + p.heads_per_cta - 1) / p.heads_per_cta, a.B, p.nT), st);
 }
 
 // dQ (query-tile owner walks the key tiles at or left of it; P / dS stay in TMEM)

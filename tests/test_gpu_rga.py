@@ -208,9 +208,11 @@ def test_rga_tcgen05_long_context_against_oracle():
     assert max(r["dq"], r["dk"], r["dv"]) < 1.2e-2 and r["dE"] < 1.2e-2, r
 
 
-@pytest.mark.parametrize("B,h,L", [(1, 12, 4096), (1, 2, 8192)])
+@pytest.mark.parametrize("B,h,L", [(1, 12, 4096), (1, 2, 8192), (16, 8, 2048), (16, 6, 2048), (16, 8, 1024)])
 def test_rga_tcgen05_long_context_matches_simt(B, h, L):
-    """Config C's attention shape (12 heads, L = 4096) and the top of the microbench sweep (L = 8192):
+    """Config C's attention shape (12 heads, L = 4096), the top of the microbench sweep (L = 8192) and config B's
+    full per-layer shape (16 x 8 heads x 2048): the last three are large enough for the launchers to put several
+    heads on one CTA (4 + 4, 4 + 2 with a remainder, 2 per CTA) -- the small cases elsewhere never do.
     the tensor-core kernels (dS-spill backward) against the fp32-math SIMT kernels on the same bf16
     inputs (the fp64 oracle would need several L x L fp64 matrices per head on the host)."""
     from musicgeneration_b200 import ops

@@ -337,10 +337,10 @@ def run_ours(args):
                          "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                          "frac": ach / pk["tf_sust"],
                          # dram__bytes_read+write of the four kernels of one call, ncu --set full capture of the
-                         # config-B layer shape (profiles/r1d_ncu_attention_kernels.summary.txt); algorithmic
+                         # config-B layer shape (profiles/r1e_ncu_attention_kernels.summary.txt); algorithmic
                          # operand bytes (q,k,v,O,dO,dq,dk,dv once) are 0.27 GB -- the rest is the dS workspace
-                         "traffic": 2.48e9 if (args.config == "B" and Bg == 16) else None,
-                         "traffic_source": "profiles/r1d_ncu_attention_kernels.summary.txt",
+                         "traffic": 2.23e9 if (args.config == "B" and Bg == 16) else None,
+                         "traffic_source": "profiles/r1e_ncu_attention_kernels.summary.txt",
                          "peak_source": pk["src"] + " sustained",
                          "ms_per_launch": bwd_ms, "flops_per_launch": bwd_flops,
                          "fwd_ms_per_launch": fwd_ms,

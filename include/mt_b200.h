@@ -210,6 +210,26 @@ int mt_decode_advance(int32_t* t_dev, void* stream);
  * outside a decode step. */
 int mt_decode_chain(int enable);
 
+/* ---- data feed: HBM-resident token arena ------------------------------------
+ * Replaces Data.batch / slide_seq2seq_batch / seq2seq_batch (MT/data.py:41-67) + the numpy int16 ->
+ * device int32 conversion of MT/train.py:258-260.  All `.data` files are concatenated once into one
+ * uint8 / uint16 arena on the device; file f is arena[file_off[f] .. file_off[f+1]).
+ *
+ * mt_window_gather: x[b, t] = arena[starts[b] + t] (t < L);  y[b, t] = arena[starts[b] + y_shift + t]
+ * (t < y_len; y may be NULL).  slide_seq2seq_batch: y_len = L, y_shift = 1; seq2seq_batch: y_len = L,
+ * y_shift = L.  `starts` is a device array of B arena offsets (drawn by the host with the reference's
+ * `random` call sequence, or by mt_window_sample).  Bit-exact integer copy, one launch, no sync. */
+int mt_window_gather(const void* arena, int token_bytes, const int64_t* starts, int32_t* x, int32_t* y,
+                     int64_t B, int64_t L, int64_t y_len, int64_t y_shift, void* stream);
+/* mt_window_sample: on-device counterpart of random.sample(files, B) + random.randrange(0, len - need)
+ * (MT/data.py:42,100): row b takes file eligible[perm(b)] (perm = keyed bijection of [0, n_eligible),
+ * i.e. without replacement) and a uniform window start in [0, len_f - need); every eligible file must
+ * be longer than `need`.  Deterministic in (seed, step); writes arena offsets to starts[B] and, if
+ * files != NULL, the chosen file indices.  Not the Mersenne-Twister stream of the reference: same
+ * distribution, different draws (the host-drawn path is the bit-exact one). */
+int mt_window_sample(const int64_t* file_off, const int64_t* eligible, int64_t n_eligible, int64_t need,
+                     uint64_t seed, uint64_t step, int64_t* starts, int64_t* files, int64_t B, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

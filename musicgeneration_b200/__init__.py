@@ -5,7 +5,7 @@ utils / config); all arithmetic runs in hand-written sm_100a CUDA kernels behind
 ``include/mt_b200.h`` (``libmt_b200.so``, bound with ctypes in ``_lib.py``).  CUDA only: there
 is no CPU fallback, and a missing extension raises at first use.
 """
-from . import (_lib, config, criterion, engine, layers, metrics, network, ops, optim,  # noqa: F401
+from . import (_lib, config, criterion, data, engine, layers, metrics, network, ops, optim,  # noqa: F401
                parallel, utils)
 from .criterion import CustomSchedule, SmoothCrossEntropyLoss  # noqa: F401
 from .engine import Mask  # noqa: F401

@@ -59,6 +59,8 @@ SIGNATURES = {
     "mt_decode_sample": (_int, [_p, _p, _p, _i64, _p, _i32, _i64, _i64, _f, _i32, _int, _p]),
     "mt_decode_advance": (_int, [_p, _p]),
     "mt_decode_chain": (_int, [_int]),
+    "mt_window_gather": (_int, [_p, _int, _p, _p, _p, _i64, _i64, _i64, _i64, _p]),
+    "mt_window_sample": (_int, [_p, _p, _i64, _i64, _u64, _u64, _p, _p, _i64, _p]),
 }
 
 _lib = None

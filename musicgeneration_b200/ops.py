@@ -277,3 +277,20 @@ def decode_chain(enable: bool):
 
 def decode_advance(t_dev):
     L.check(L.load().mt_decode_advance(_ptr(t_dev), _stream()), "decode_advance")
+
+
+def window_gather(arena, starts, x, y=None, y_shift=0):
+    """x[b, :] = arena[starts[b] : +L], y[b, :] = arena[starts[b] + y_shift : +y_len] (int32 outputs)."""
+    _need_cuda(arena, starts, x, y)
+    if arena.dtype not in (torch.uint8, torch.uint16) or starts.dtype != torch.int64 or x.dtype != torch.int32:
+        raise RuntimeError("window_gather: arena uint8/uint16, starts int64, outputs int32")
+    B, Lx = x.shape
+    L.check(L.load().mt_window_gather(_ptr(arena), arena.element_size(), _ptr(starts), _ptr(x), _ptr(y), B, Lx,
+                                      0 if y is None else y.shape[1], y_shift, _stream()), "window_gather")
+
+
+def window_sample(file_off, eligible, need, seed, step, starts, files=None):
+    """On-device draw of B distinct eligible files and one window start per file (arena offsets)."""
+    _need_cuda(file_off, eligible, starts, files)
+    L.check(L.load().mt_window_sample(_ptr(file_off), _ptr(eligible), eligible.numel(), need, seed, step,
+                                      _ptr(starts), _ptr(files), starts.numel(), _stream()), "window_sample")

@@ -173,10 +173,84 @@ def golden_config_a(R):
     print("config A loss", float(loss))
 
 
+def data_feed_script(D, record):
+    """The call sequence both the golden generator and the tests replay (same ``random`` seeds)."""
+    import random
+
+    def retry(fn, *a):
+        """The train loop's own policy for IndexError (MT/train.py:261-262: skip the batch); ValueError
+        (randrange(0, 0)) is treated the same here.  Deterministic: every failed draw consumes the same
+        random numbers in the reference, the oracle and the CUDA-backed class."""
+        fails = 0
+        while True:
+            try:
+                return fn(*a), fails
+            except (IndexError, ValueError):
+                fails += 1
+
+    random.seed(11)
+    for name, fn, args in [("slide", D.slide_seq2seq_batch, (4, 64)),
+                           ("slide_valid", D.slide_seq2seq_batch, (2, 48, 'valid')),
+                           ("s2s", D.seq2seq_batch, (3, 40)),
+                           ("small", D.smallest_encoder_batch, (2, 130)),
+                           ("batch", D.batch, (5, 50, 'train'))]:
+        res, fails = retry(fn, *args)
+        record(name, *(res if isinstance(res, tuple) else (res,)), np.array(fails))
+    random.seed(12)
+    record("randseq", np.array(D.random_sequential_batch(6, 20)))
+    record("seq0", np.array(D.sequential_batch(7, 25)))
+    record("seq1", np.array(D.sequential_batch(400, 25)))     # runs past the first file (cursor reset)
+    record("seq2", np.array(D.sequential_batch(3, 25)))
+    random.seed(13)
+    errs = []
+    for _ in range(12):                                       # 65-token pieces: randrange(0, 0)
+        try:
+            D.slide_seq2seq_batch(8, 64)
+            errs.append(0)
+        except ValueError:
+            errs.append(1)
+        except IndexError:
+            errs.append(2)
+    record("errs", np.array(errs))
+
+
+def golden_data(R):
+    """MT/data.py run UNMODIFIED over a synthetic ``.data`` corpus (oracle.restate.write_token_corpus).
+    torch >= 2.6 defaults ``torch.load`` to weights_only=True, which rejects the pickled numpy arrays the
+    reference's own preprocessing writes; the generator flips that default around the reference calls."""
+    import functools
+    import tempfile
+    from oracle.restate import write_token_corpus
+    out = {}
+
+    def record(name, *arrs):
+        for i, a in enumerate(arrs):
+            out[f"{name}:{i}"] = np.asarray(a)
+
+    orig = torch.load
+    torch.load = functools.partial(orig, weights_only=False)
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            write_token_corpus(tmp)
+            D = R.data.Data(tmp, 30)
+            out["files"] = np.array([os.path.relpath(f, tmp) for f in D.files])
+            for k in ("train", "valid", "test"):
+                out["split:" + k] = np.array([os.path.relpath(f, tmp) for f in D.file_dict[k]])
+            data_feed_script(D, record)
+    finally:
+        torch.load = orig
+    np.savez(os.path.join(OUT, "data_feed.npz"), **out)
+    print("data feed golden:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     R = load_reference()
+    if "--data-only" in sys.argv:
+        golden_data(R)
+        sys.exit(0)
+    golden_data(R)
     golden_train(R)
     golden_rga(R)
     golden_decode(R)

@@ -63,7 +63,7 @@ _CACHE: dict | None = None
 
 def load_reference() -> types.SimpleNamespace:
     """Return a namespace with the reference modules: layers, network, criterion, utils,
-    config, metrics.  Raises FileNotFoundError when the reference tree is absent."""
+    config, metrics, data.  Raises FileNotFoundError when the reference tree is absent."""
     global _CACHE
     if _CACHE is not None:
         return _CACHE
@@ -75,7 +75,7 @@ def load_reference() -> types.SimpleNamespace:
     # import under the bare names (that is what the files themselves do) but snapshot and
     # restore any modules of ours that share those names.
     bare = ["sequence", "utils", "config", "layers", "criterion", "parallel", "metrics",
-            "network"]
+            "network", "data"]
     saved = {n: sys.modules.pop(n) for n in bare if n in sys.modules}
     sys.path.insert(0, d)
     try:

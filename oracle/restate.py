@@ -313,3 +313,106 @@ def init_params(d: int, vocab: int, layers: int, max_seq: int, seed: int = 0) ->
             p[pre + n + ".bias"] = torch.zeros(d)
     lin("fc", vocab, d)
     return p
+
+
+# ----------------------------------------------------------------------------------------
+# MT/data.py:10-107  Data (batch builders) -- host restatement that re-reads the files
+# ----------------------------------------------------------------------------------------
+def write_token_corpus(root: str, n_files: int = 24, seed: int = 5, lo: int = 70, hi: int = 420,
+                       vocab: int = 388, dtype=np.uint16) -> List[str]:
+    """Synthetic corpus in the reference's on-disk format: one ``torch.save(np.ndarray)`` per piece,
+    named ``*.data`` (REF/mg/model/utils/preprocess_MIDI_like.py:21-41).  Deterministic in ``seed``;
+    a few pieces sit exactly at lengths the tests use as window sizes (boundary cases of
+    ``_get_seq``).  Returns the file names in creation order."""
+    import os as _os
+    rng = np.random.RandomState(seed)
+    names = []
+    for i in range(n_files):
+        n = int(rng.randint(lo, hi))
+        if i % 7 == 3:
+            n = 65            # == 64 + 1: random.randrange(0, 0) -> ValueError for slide batches of 64
+        if i % 11 == 5:
+            n = 40            # passes a max_length = 30 filter, too short for most windows -> IndexError
+        arr = rng.randint(0, vocab, size=n).astype(dtype)
+        sub = _os.path.join(root, f"d{i % 3}")
+        _os.makedirs(sub, exist_ok=True)
+        name = _os.path.join(sub, f"piece{i:03d}-{rng.randint(0, 1 << 30):08x}.data")
+        torch.save(arr, name)
+        names.append(name)
+    return names
+
+
+class DataOracle:
+    """MT/data.py:10-107 restated on the host with numpy: same ``random`` call sequence (one
+    ``random.sample`` per batch, one ``random.randrange`` per drawn file), same split, same errors.
+    ``files`` may be given to fix the listing order (the reference takes ``os.walk`` order)."""
+
+    def __init__(self, dir_path, max_length, files=None):
+        import os as _os
+        if files is None:
+            files = []
+            for path, _, names in _os.walk(dir_path):                       # MT/utils.py:19-22
+                files += [_os.path.join(path, n) for n in names if n.lower().endswith('.data')]
+        self.files = list(files)
+        self._data = {f: np.asarray(torch.load(f, weights_only=False)) for f in self.files}
+        n = len(self.files)
+        keep = lambda fs: [f for f in fs if max_length <= len(self._data[f])]   # MT/data.py:33-40
+        self.file_dict = {'train': keep(self.files[:int(n * 0.8)]),
+                          'valid': keep(self.files[int(n * 0.8):int(n * 0.9)]),
+                          'test': keep(self.files[int(n * 0.9):])}
+        self._seq_file_name_idx = 0
+        self._seq_idx = 0
+
+    def _get_seq(self, fname, max_length=None):                             # MT/data.py:96-107
+        import random as _random
+        data = self._data[fname]
+        if max_length is not None:
+            if max_length <= len(data):
+                start = _random.randrange(0, len(data) - max_length)
+                data = data[start:start + max_length]
+            else:
+                raise IndexError
+        return data
+
+    def batch(self, batch_size, length, mode='train'):                      # MT/data.py:41-48
+        import random as _random
+        batch_files = _random.sample(self.file_dict[mode], k=batch_size)
+        return np.array([self._get_seq(f, length) for f in batch_files], dtype=np.int16)
+
+    def seq2seq_batch(self, batch_size, length, mode='train'):              # MT/data.py:50-54
+        data = self.batch(batch_size, length * 2, mode)
+        return data[:, :length], data[:, length:]
+
+    def smallest_encoder_batch(self, batch_size, length, mode='train'):     # MT/data.py:56-60
+        data = self.batch(batch_size, length * 2, mode)
+        return data[:, :length // 100], data[:, length // 100:length // 100 + length]
+
+    def slide_seq2seq_batch(self, batch_size, length, mode='train'):        # MT/data.py:62-66
+        data = self.batch(batch_size, length + 1, mode)
+        return data[:, :-1], data[:, 1:]
+
+    def random_sequential_batch(self, batch_size, length):                  # MT/data.py:68-76
+        import random as _random
+        batch_files = _random.sample(self.files, k=batch_size)
+        out = []
+        for i in range(batch_size):
+            data = self._get_seq(batch_files[i])
+            for j in range(len(data) - length):
+                out.append(data[j:j + length])
+                if len(out) == batch_size:
+                    return out
+        return None
+
+    def sequential_batch(self, batch_size, length):                         # MT/data.py:78-94
+        out = []
+        data = self._get_seq(self.files[self._seq_file_name_idx])
+        while len(out) < batch_size:
+            while self._seq_idx < len(data) - length:
+                out.append(data[self._seq_idx:self._seq_idx + length])
+                self._seq_idx += 1
+                if len(out) == batch_size:
+                    return out
+            self._seq_idx = 0
+            self._seq_file_name_idx += 1
+            if self._seq_file_name_idx == len(self.files):
+                self._seq_file_name_idx = 0

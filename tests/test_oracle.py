@@ -143,3 +143,46 @@ def test_live_reference_matches_oracle():
     assert (ref - ours).abs().max() < 2e-5
     l_ref = R.criterion.SmoothCrossEntropyLoss(0.1, 72, 70)(ref, y)
     assert abs(float(l_ref) - float(O.smooth_ce(ours, y, 0.1, 72, 70))) < 2e-6
+
+
+# ---- data feed (MT/data.py) ---------------------------------------------------------------
+def _replay(D):
+    from oracle.make_golden import data_feed_script
+    out = {}
+
+    def record(name, *arrs):
+        for i, a in enumerate(arrs):
+            out[f"{name}:{i}"] = np.asarray(a)
+
+    data_feed_script(D, record)
+    return out
+
+
+def test_data_oracle_matches_reference_golden(tmp_path):
+    """DataOracle replays the call script the UNMODIFIED MT/data.py ran in the build container: same
+    split, same windows, same failed draws, bit for bit."""
+    z = load("data_feed.npz")
+    names = O.write_token_corpus(str(tmp_path))
+    assert sorted(os.path.relpath(n, tmp_path) for n in names) == sorted(z["files"].tolist())
+    D = O.DataOracle(str(tmp_path), 30, files=[os.path.join(tmp_path, f) for f in z["files"].tolist()])
+    for k in ("train", "valid", "test"):
+        assert [os.path.relpath(f, tmp_path) for f in D.file_dict[k]] == z["split:" + k].tolist()
+    got = _replay(D)
+    for k, v in got.items():
+        assert v.dtype == z[k].dtype and v.shape == z[k].shape, k
+        assert (v == z[k]).all(), k
+
+
+@pytest.mark.skipif(reference_dir() is None, reason="reference tree not present")
+def test_data_oracle_matches_live_reference(tmp_path, monkeypatch):
+    import functools
+    from oracle.ref_import import load_reference
+    R = load_reference()
+    O.write_token_corpus(str(tmp_path), n_files=31, seed=9)
+    monkeypatch.setattr(torch, "load", functools.partial(torch.load, weights_only=False))
+    ref = R.data.Data(str(tmp_path), 30)
+    got_ref = _replay(ref)
+    got = _replay(O.DataOracle(str(tmp_path), 30, files=ref.files))
+    assert got.keys() == got_ref.keys()
+    for k in got:
+        assert (got[k] == got_ref[k]).all(), k

@@ -47,3 +47,46 @@ def materialize(mask: Mask, L: int) -> torch.Tensor:
     if mask.pad_keys is not None:
         m = m | mask.pad_keys.bool()[:, None, None, :]
     return m
+
+
+class ScalarReadback:
+    """Device -> host read of per-step scalars (loss, accuracy) without stalling the launch queue.
+
+    MT/train.py:267-283 reads ``metrics['loss']`` with an implicit synchronise every iteration, which
+    drains the GPU before the host starts enqueueing the next step.  Here ``push(t)`` enqueues an async
+    copy of the 0-d tensor into a pinned slot and records an event; ``pop()`` returns the OLDEST pushed
+    value as a Python float, waiting only for that copy's event.  Calling ``pop()`` once ``depth - 1``
+    steps later (depth 2: right after the next step has been enqueued) keeps every step's value read on
+    the host while the device never idles; ``drain()`` returns what is still in flight."""
+
+    def __init__(self, depth: int = 2, dtype=torch.float32):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ScalarReadback needs a CUDA device")
+        self.depth = max(1, depth)
+        self._slots = torch.empty(self.depth, dtype=dtype).pin_memory()
+        self._events = [torch.cuda.Event() for _ in range(self.depth)]
+        self._head = 0      # next slot to fill
+        self._n = 0         # values in flight
+
+    def push(self, t: torch.Tensor):
+        if self._n == self.depth:
+            raise RuntimeError("ScalarReadback: pop() before pushing more than `depth` values")
+        i = self._head
+        self._slots[i:i + 1].copy_(t.detach().reshape(1), non_blocking=True)
+        self._events[i].record()
+        self._head = (i + 1) % self.depth
+        self._n += 1
+
+    def __len__(self):
+        return self._n
+
+    def pop(self) -> float:
+        if self._n == 0:
+            raise RuntimeError("ScalarReadback: nothing in flight")
+        i = (self._head - self._n) % self.depth
+        self._events[i].synchronize()
+        self._n -= 1
+        return float(self._slots[i])
+
+    def drain(self):
+        return [self.pop() for _ in range(self._n)]

@@ -353,3 +353,23 @@ def test_gemm_skinny_decode_shapes(dev, M, N, K, out_bf16):
     C2 = torch.empty((M, N), dtype=odt, device=dev)
     ops.gemm(Ad, Wd, C2, M, N, K, K, K, N, False, True, bias=bias.to(dev), relu=True)
     assert rel(C2.float().cpu(), torch.relu(ref)) < (4e-3 if out_bf16 else 2e-6)
+
+
+@pytest.mark.gpu
+def test_scalar_readback_order_and_values():
+    """utils.ScalarReadback returns every pushed value, in order, lagging by at most depth - 1."""
+    from musicgeneration_b200.utils import ScalarReadback
+    rb = ScalarReadback(depth=2)
+    got = []
+    for i in range(7):
+        rb.push(torch.full((), float(i) * 1.5, device="cuda"))
+        if len(rb) == 2:
+            got.append(rb.pop())
+    got += rb.drain()
+    assert got == [i * 1.5 for i in range(7)]
+    with pytest.raises(RuntimeError):
+        rb.pop()
+    rb.push(torch.zeros((), device="cuda"))
+    rb.push(torch.zeros((), device="cuda"))
+    with pytest.raises(RuntimeError):
+        rb.push(torch.zeros((), device="cuda"))

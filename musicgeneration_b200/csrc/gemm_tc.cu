@@ -525,14 +525,30 @@ __global__ void __launch_bounds__(256) tc_splitk_fold_kernel(TcGemmParams p) {
   else reinterpret_cast<float*>(p.C)[m * p.ldc + n] = s;
 }
 
-int tc_splits(int64_t M, int64_t N, int64_t K) {
-  int64_t tiles = ((M + BM - 1) / BM) * ((N + 127) / 128);
+// Split-K factor of a launch with few output tiles and a long K (the weight gradients: K = tokens).
+// Two CTAs are resident per SM, so tiles * splits is kept AT OR BELOW 2 * SMs: one more CTA than
+// that is a second wave of the whole K range (measured: 336 CTAs of K/7 took 65.9 us for the QKV
+// gradient of config B -- two waves -- where 288 CTAs of K/6 fit one).
+int tc_splits(int64_t M, int64_t N, int64_t K, int bn) {
+  int64_t tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
   if (tiles >= sm_count() || K < 2048) return 1;
-  int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;
+  int64_t want = (2 * (int64_t)sm_count()) / tiles;
   int64_t maxs = K / 512;
   if (want > maxs) want = maxs;
   if (want > 32) want = 32;
   return want < 1 ? 1 : (int)want;
+}
+
+// 128 x 256 tiles for the MN-major-A (weight gradient) products (87 instead of 64 FLOP per byte fetched
+// from L2) are available with MT_WGRAD_BN=256 but measured SLOWER on B200 at config B's shapes (QKV
+// gradient 59.3 vs 56.4 us, fc 34.9 vs 26.9 us incl. the fold): the 2-stage ring of the wide shape hides
+// less of the L2 latency than the 3-stage ring of the 128 x 128 one.  Default: 128 x 128.
+bool wgrad_wide() {
+  static const bool wide = [] {
+    const char* e = getenv("MT_WGRAD_BN");
+    return e && atoi(e) == 256;
+  }();
+  return wide;
 }
 
 }  // namespace
@@ -636,7 +652,7 @@ bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb
 }
 
 size_t gemm_tc_workspace_bytes(int64_t M, int64_t N, int64_t K) {
-  int s = tc_splits(M, N, K);
+  int s = max(tc_splits(M, N, K, 128), tc_splits(M, N, K, 256));
   return s > 1 ? (size_t)s * M * N * sizeof(float) : 0;
 }
 
@@ -652,8 +668,8 @@ int gemm_tc(const void* A, const void* B, void* C, const float* bias, const floa
   else rc = tc::make_tmap_2d(&tmA, A, M, K, lda, BK, BM);
   if (rc) return rc;
   // 128 x 256 tiles when the output is at least 256 columns wide and a plain (no split-K) product
-  const int splits0 = tc_splits(M, N, K);
-  const bool wide = (N % 256 == 0) && splits0 == 1 && !a_mn;
+  const bool wide = a_mn ? ((N % 256 == 0) && b_mn && wgrad_wide())
+                         : ((N % 256 == 0) && tc_splits(M, N, K, 128) == 1);
   const int BN = wide ? 256 : 128;
   if (b_mn) rc = tc::make_tmap_2d(&tmB, B, K, N, ldb, 64, BK);
   else rc = tc::make_tmap_2d(&tmB, B, N, K, ldb, BK, BN);
@@ -666,7 +682,7 @@ int gemm_tc(const void* A, const void* B, void* C, const float* bias, const floa
   const int oes = p.out_bf16 ? 2 : 4;
   p.vec_ok = (ldc % 4 == 0) && aligned(C, 4 * oes) && (!(epilogue & MT_EPI_BIAS) || aligned(bias, 16)) &&
              (!(epilogue & MT_EPI_ADD) || aligned(addend, 16)) && (!(epilogue & MT_EPI_RELU_MASK) || aligned(aux, 8));
-  p.splits = tc_splits(M, N, K);
+  p.splits = tc_splits(M, N, K, BN);
   if (p.splits > 1 && (!workspace || workspace_bytes < (size_t)p.splits * M * N * sizeof(float))) p.splits = 1;
   p.add_inplace = (epilogue & MT_EPI_ADD) && addend == C && !p.out_bf16 && p.vec_ok &&
                   !(epilogue & (MT_EPI_RELU | MT_EPI_RELU_MASK)) && (N % 4 == 0);
@@ -714,7 +730,7 @@ int gemm_tc(const void* A, const void* B, void* C, const float* bias, const floa
   }
   if (!a_mn && !b_mn) { if (wide) MT_TC_LAUNCH(0, 0, 256) else MT_TC_LAUNCH(0, 0, 128) }
   else if (!a_mn && b_mn) { if (wide) MT_TC_LAUNCH(0, 1, 256) else MT_TC_LAUNCH(0, 1, 128) }
-  else if (a_mn && b_mn) MT_TC_LAUNCH(1, 1, 128)
+  else if (a_mn && b_mn) { if (wide) MT_TC_LAUNCH(1, 1, 256) else MT_TC_LAUNCH(1, 1, 128) }
   else { set_error("gemm_tc: unsupported operand majors"); return MT_E_UNSUPPORTED; }
 #undef MT_TC_LAUNCH
   if (e != cudaSuccess) { set_error("gemm_tc: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }

@@ -525,6 +525,31 @@ __global__ void __launch_bounds__(256) tc_splitk_fold_kernel(TcGemmParams p) {
   else reinterpret_cast<float*>(p.C)[m * p.ldc + n] = s;
 }
 
+// The weight-gradient case (fp32 output, no epilogue, N % 4 == 0): one quad per thread, the partial
+// loads of eight splits in flight at a time; same ascending-z summation order as the scalar kernel.
+__global__ void __launch_bounds__(256) tc_splitk_fold_vec_kernel(TcGemmParams p) {
+  const int64_t quads = p.M * p.N / 4;
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= quads) return;
+  const int64_t e = idx * 4;
+  const int64_t m = e / p.N, n = e - m * p.N;
+  const float4* src = reinterpret_cast<const float4*>(p.part) + idx;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  int z = 0;
+  for (; z + 8 <= p.splits; z += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (int64_t)(z + u) * quads);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+  }
+  for (; z < p.splits; ++z) {
+    const float4 v = __ldcg(src + (int64_t)z * quads);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + m * p.ldc + n) = s;
+}
+
 // Split-K factor of a launch with few output tiles and a long K (the weight gradients: K = tokens).
 // Two CTAs are resident per SM, so tiles * splits is kept AT OR BELOW 2 * SMs: one more CTA than
 // that is a second wave of the whole K range (measured: 336 CTAs of K/7 took 65.9 us for the QKV
@@ -532,7 +557,8 @@ __global__ void __launch_bounds__(256) tc_splitk_fold_kernel(TcGemmParams p) {
 int tc_splits(int64_t M, int64_t N, int64_t K, int bn) {
   int64_t tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
   if (tiles >= sm_count() || K < 2048) return 1;
-  int64_t want = (2 * (int64_t)sm_count()) / tiles;
+  static const int per_sm = [] { const char* e = getenv("MT_SPLITK_PER_SM"); int v = e ? atoi(e) : 2; return v == 1 ? 1 : 2; }();
+  int64_t want = (per_sm * (int64_t)sm_count()) / tiles;
   int64_t maxs = K / 512;
   if (want > maxs) want = maxs;
   if (want > 32) want = 32;
@@ -738,7 +764,10 @@ int gemm_tc(const void* A, const void* B, void* C, const float* bias, const floa
   if (rc) return rc;
   if (p.splits > 1) {
     int64_t n = M * N;
-    tc_splitk_fold_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p);
+    if (epilogue == 0 && !p.out_bf16 && (N % 4 == 0) && (ldc % 4 == 0) && aligned(C, 16) && aligned(workspace, 16))
+      tc_splitk_fold_vec_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, stream>>>(p);
+    else
+      tc_splitk_fold_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p);
     rc = check_launch("gemm_tc_fold");
   }
   return rc;

@@ -104,7 +104,7 @@ def linear_wgrad(dy, x, dW, db, cfg: StackCfg, ldy=None, n=None):
 def rga_block_fwd(xq, xk, xv, W: LayerWeights, cfg: StackCfg, B: int, Lq: int, mask: Optional[Mask],
                   need_weights: bool):
     """xq/xk/xv: [T, d] act dtype (the same tensor for self-attention).  Returns
-    (a [T,d] f32 = fc output incl. bias, saved dict, P or None)."""
+    (a [T,d] act dtype = fc output incl. bias, saved dict, P or None)."""
     d, h, dh = cfg.d, cfg.h, cfg.dh
     T = B * Lq
     qkv = _empty((T, 3 * d), cfg.act, xq)
@@ -128,7 +128,9 @@ def rga_block_fwd(xq, xk, xv, W: LayerWeights, cfg: StackCfg, B: int, Lq: int, m
     if need_weights:
         P = _empty((B, h, Lq, Lq), torch.float32, xq)
         ops.rga_weights(q, k, strides, W.E, pad, lse, P, B, h, Lq, dh, cfg.max_seq, causal)
-    a = _empty((T, d), torch.float32, xq)
+    # sublayer output in the activation dtype (bf16 mode: what a bf16 nn.Linear returns; it is read twice more,
+    # by the residual+LayerNorm forward and backward, so the narrower type saves 3 x T x d x 2 bytes per sublayer)
+    a = _empty((T, d), cfg.act, xq)
     linear_fwd(O, W.Wfc, W.bfc, a, cfg)
     saved = dict(xq=xq, xk=xk, xv=xv, same=same, qkv=qkv, O=O, lse=lse, causal=causal, pad=pad,
                  strides=strides, ostrides=ostrides, B=B, L=Lq)
@@ -206,7 +208,7 @@ def layer_fwd(x_f32, x_lp, W: LayerWeights, cfg: StackCfg, B: int, Lq: int, mask
     o1 = out1_lp if lp else out1
     hmid = _empty((T, d // 2), cfg.act, x_f32)
     linear_fwd(o1, W.Wpre, W.bpre, hmid, cfg, relu=True)
-    f = _empty((T, d), torch.float32, x_f32)
+    f = _empty((T, d), cfg.act, x_f32)
     linear_fwd(hmid, W.Wsuf, W.bsuf, f, cfg)
     out2 = _empty((T, d), torch.float32, x_f32)
     out2_lp = _empty((T, d), cfg.act, x_f32) if lp else None

@@ -244,6 +244,10 @@ class _RGAFunction(torch.autograd.Function):
         ctx.shape = (B, Lq, d)
         if P is not None:
             ctx.mark_non_differentiable(P)
+        if a.dtype != torch.float32:         # the module surface returns fp32 (MT/layers.py:108); the stack consumes `a` as is
+            a32 = torch.empty((B * Lq, d), dtype=torch.float32, device=a.device)
+            ops.cast(a, a32)
+            a = a32
         return a.view(B, Lq, d), P
 
     @staticmethod

@@ -57,6 +57,7 @@ class FlatAdam:
         for p in model.parameters():
             add(p)
         self.params = order
+        self._model_order = [p for p in model.parameters() if p.requires_grad]
         dev = order[0].device
         if dev.type != "cuda":
             raise RuntimeError("FlatAdam needs the model on a CUDA device (no CPU fallback)")
@@ -109,11 +110,63 @@ class FlatAdam:
         ops.adam_step(self.flat_p, self.flat_g, self.m, self.v, None, lr, self.betas[0], self.betas[1],
                       self.eps, self.step_count, 1.0 / (world * self.grad_accum))
 
+    # ---- checkpoint compatibility (MT/train.py:143,151,203: torch.optim.Adam state_dict under 'optimizer') ----
+    def _slots(self):
+        """(flat offset, numel, shape) of every trainable parameter in ``model.parameters()`` order -- the
+        order torch.optim.Adam(model.parameters()) numbers its state entries in."""
+        base = self.flat_p.data_ptr()
+        return [((p.data_ptr() - base) // 4, p.numel(), tuple(p.shape)) for p in self._model_order]
+
     def state_dict(self):
-        return {"step": self.step_count, "m": self.m, "v": self.v, "lr": self.param_groups[0]["lr"]}
+        """The dict ``torch.optim.Adam(model.parameters(), ...).state_dict()`` would hold at this point:
+        ``state[i] = {step, exp_avg, exp_avg_sq}`` per parameter index (empty before the first step) and one
+        param group; a reference checkpoint written from it loads into the reference's optimizer and back."""
+        group = torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], lr=float(self.param_groups[0]["lr"]),
+                                 betas=tuple(self.betas), eps=self.eps).state_dict()["param_groups"][0]
+        slots = self._slots()
+        group["params"] = list(range(len(slots)))
+        state = {}
+        if self.step_count > 0:
+            for i, (off, n, shape) in enumerate(slots):
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.m[off:off + n].view(shape).clone(),
+                            "exp_avg_sq": self.v[off:off + n].view(shape).clone()}
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd):
-        self.step_count = int(sd["step"])
-        self.m.copy_(sd["m"])
-        self.v.copy_(sd["v"])
-        self.param_groups[0]["lr"] = sd["lr"]
+        """Accepts a torch.optim.Adam state_dict (a reference checkpoint's 'optimizer' entry, or our own
+        ``state_dict()``) and the flat {'step','m','v','lr'} form earlier versions of this class wrote."""
+        if "param_groups" not in sd:
+            self.step_count = int(sd["step"])
+            self.m.copy_(sd["m"])
+            self.v.copy_(sd["v"])
+            self.param_groups[0]["lr"] = sd["lr"]
+            return
+        groups = sd["param_groups"]
+        slots = self._slots()
+        index = [i for g in groups for i in g["params"]]
+        if len(index) != len(slots):
+            raise ValueError("loaded state dict contains a parameter group that doesn't match the size of "
+                             "optimizer's group")
+        g0 = groups[0]
+        self.param_groups[0]["lr"] = g0["lr"]
+        self.betas = tuple(g0.get("betas", self.betas))
+        self.eps = g0.get("eps", self.eps)
+        if g0.get("weight_decay", 0) or g0.get("amsgrad", False):
+            raise ValueError("FlatAdam implements plain Adam (weight_decay=0, amsgrad=False), as MT/train.py:143 uses it")
+        self.m.zero_()
+        self.v.zero_()
+        steps = set()
+        for pos, key in enumerate(index):
+            st = sd["state"].get(key)
+            if st is None:
+                continue
+            off, n, shape = slots[pos]
+            if tuple(st["exp_avg"].shape) != shape:
+                raise ValueError(f"optimizer state {key}: shape {tuple(st['exp_avg'].shape)} != parameter shape {shape}")
+            self.m[off:off + n].view(shape).copy_(st["exp_avg"])
+            self.v[off:off + n].view(shape).copy_(st["exp_avg_sq"])
+            steps.add(int(st["step"]))
+        if len(steps) > 1:
+            raise ValueError("FlatAdam keeps one step counter; the loaded state has per-parameter steps " + str(sorted(steps)))
+        self.step_count = steps.pop() if steps else 0

@@ -257,3 +257,74 @@ def test_causality_and_batch_independence_property():
         other = m(x2)
     assert torch.equal(base[0, :300], other[0, :300])
     assert not torch.equal(base[0, 300:], other[0, 300:])
+
+
+@pytest.mark.gpu
+def test_flat_adam_checkpoint_round_trip_with_torch_adam(tmp_path):
+    """the {'net','optimizer','epoch'} checkpoint of MT/train.py:201-207 is interchangeable.
+    FlatAdam.state_dict() loads into torch.optim.Adam(model.parameters()) and the other way round; after
+    the exchange one more step with identical gradients gives the same parameters (fp32, 1e-6)."""
+    import copy
+    import musicgeneration_b200 as mtb
+    from musicgeneration_b200.optim import FlatAdam
+    torch.manual_seed(3)
+    d, V, layers, L, B = 128, 96, 2, 64, 2
+    mtb.config.pad_token = 94
+    m = mtb.MusicTransformer(embedding_dim=d, vocab_size=V, num_layer=layers, max_seq=L, dropout=0.0,
+                             precision="fp32").cuda()
+    twin = copy.deepcopy(m).cpu()                       # plain torch parameters for the reference optimizer
+    opt = FlatAdam(m, lr=0.0, betas=(0.9, 0.98), eps=1e-9)
+    sched = mtb.CustomSchedule(d, optimizer=opt)
+    ref_opt = torch.optim.Adam(twin.parameters(), lr=0, betas=(0.9, 0.98), eps=1e-9)
+    ref_sched = mtb.CustomSchedule(d, optimizer=ref_opt)
+    crit = mtb.SmoothCrossEntropyLoss(0.1, V, 94)
+    x, y = O.synthetic_ids(B, L, 94)
+
+    def step_both():
+        opt.zero_grad()
+        crit(m(x.cuda()), y.cuda()).backward()
+        for p, q in zip(m.parameters(), twin.parameters()):
+            q.grad = p.grad.detach().cpu().clone()
+        sched.step()
+        ref_sched.step()
+
+    assert opt.state_dict()["state"] == {}
+    for _ in range(3):
+        step_both()
+    for p, q in zip(m.parameters(), twin.parameters()):
+        assert (p.detach().cpu() - q.detach()).abs().max() <= 1e-6 + 1e-5 * q.detach().abs().max()
+    # ours -> file -> torch.optim.Adam
+    ck = {"net": m.state_dict(), "optimizer": sched.optimizer.state_dict(), "epoch": 7}
+    torch.save(ck, tmp_path / "train-7-0.0.pth")
+    ck = torch.load(tmp_path / "train-7-0.0.pth", map_location="cpu")
+    twin2 = copy.deepcopy(twin)
+    twin2.load_state_dict(ck["net"])
+    ref2 = torch.optim.Adam(twin2.parameters(), lr=0, betas=(0.9, 0.98), eps=1e-9)
+    ref2.load_state_dict(ck["optimizer"])
+    sd_ref, sd2 = ref_opt.state_dict(), ref2.state_dict()
+    assert sd2["param_groups"][0]["params"] == sd_ref["param_groups"][0]["params"]
+    for i in sd_ref["state"]:
+        assert float(sd2["state"][i]["step"]) == float(sd_ref["state"][i]["step"]) == 3.0
+        for k in ("exp_avg", "exp_avg_sq"):
+            a, b = sd2["state"][i][k], sd_ref["state"][i][k]
+            assert (a - b).abs().max() <= 1e-7 + 1e-5 * b.abs().max(), (i, k)
+    # torch.optim.Adam -> FlatAdam on a fresh model
+    m3 = mtb.MusicTransformer(embedding_dim=d, vocab_size=V, num_layer=layers, max_seq=L, dropout=0.0,
+                              precision="fp32").cuda()
+    m3.load_state_dict(twin.state_dict())
+    opt3 = FlatAdam(m3, lr=0.0, betas=(0.9, 0.98), eps=1e-9)
+    opt3.load_state_dict(ref_opt.state_dict())
+    assert opt3.step_count == 3
+    sched3 = mtb.CustomSchedule(d, optimizer=opt3)
+    sched3._step = ref_sched._step
+    opt3.zero_grad()
+    crit(m3(x.cuda()), y.cuda()).backward()
+    for p, q in zip(m3.parameters(), twin.parameters()):
+        q.grad = p.grad.detach().cpu().clone()
+    sched3.step()
+    ref_sched.step()
+    for (n, p), q in zip(m3.named_parameters(), twin.parameters()):
+        assert (p.detach().cpu() - q.detach()).abs().max() <= 1e-6 + 1e-5 * q.detach().abs().max(), n
+    # the flat form older checkpoints of this class used still loads
+    opt3.load_state_dict({"step": 5, "m": opt3.m.clone(), "v": opt3.v.clone(), "lr": 0.1})
+    assert opt3.step_count == 5

@@ -85,6 +85,14 @@ int mt_gemm(const void* A, const void* B, void* C, const float* bias, const floa
             const void* aux, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
             int64_t ldc, int transA, int transB, int in_dtype, int out_dtype, int epilogue,
             int path, void* workspace, size_t workspace_bytes, void* stream);
+/* nn.Linear backward in one pass over dy: dW[M,N] = dy[K,M]^T . x[K,N] (fp32) and db[M] = sum_k dy[k,m].
+ * The column sums ride along as one extra 128 x 16 x 16 tensor-core product per k-step against a tile of
+ * ones in the CTAs that own the first tile column (no second read of dy, no extra launch).  tcgen05 path
+ * only (bf16 / f16 operands, N % 128 == 0): MT_E_UNSUPPORTED otherwise -- callers then use mt_gemm +
+ * mt_colsum.  Workspace: mt_gemm_workspace_bytes(M, N, K, in_dtype, 0). */
+int mt_wgrad_bias(const void* dy, const void* x, float* dW, float* db, int64_t M, int64_t N, int64_t K,
+                  int64_t lddy, int64_t ldx, int64_t lddw, int in_dtype, void* workspace, size_t workspace_bytes,
+                  void* stream);
 /* out[n] = sum_m X[m,n]  (bias gradients) */
 size_t mt_colsum_workspace_bytes(int64_t M, int64_t N);
 int mt_colsum(const void* X, int dtype, float* out, int64_t M, int64_t N, int64_t ldx,

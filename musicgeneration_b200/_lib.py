@@ -36,6 +36,7 @@ SIGNATURES = {
     "mt_ln_param_grad": (_int, [_p, _p, _p, _p, _i64, _i64, _p]),
     "mt_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64, _int, _int]),
     "mt_gemm": (_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _int, _int, _p, _sz, _p]),
+    "mt_wgrad_bias": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _sz, _p]),
     "mt_colsum_workspace_bytes": (_sz, [_i64, _i64]),
     "mt_colsum": (_int, [_p, _int, _p, _i64, _i64, _i64, _p, _sz, _p]),
     "mt_cast": (_int, [_p, _int, _p, _int, _i64, _p]),

@@ -38,6 +38,19 @@ int mt_gemm(const void* A, const void* B, void* C, const float* bias, const floa
   return gemm_simt(A, B, C, bias, addend, aux, M, N, K, lda, ldb, ldc, transA, transB, in_dtype, out_dtype, epilogue, workspace, workspace_bytes, as_stream(stream));
 }
 
+int mt_wgrad_bias(const void* dy, const void* x, float* dW, float* db, int64_t M, int64_t N, int64_t K,
+                  int64_t lddy, int64_t ldx, int64_t lddw, int in_dtype, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  MT_REQUIRE(dy && x && dW && db, "wgrad_bias: null pointer");
+  MT_REQUIRE(M > 0 && N > 0 && K > 0 && lddy >= M && ldx >= N && lddw >= N, "wgrad_bias: bad shape");
+  if (N % 128 != 0 || !gemm_tc_supported(M, N, K, lddy, ldx, lddw, 1, 0, in_dtype, MT_F32, 0, dy, x, dW)) {
+    set_error("wgrad_bias: tcgen05 weight-gradient form only (16-bit operands, N %% 128 == 0); use mt_gemm + mt_colsum");
+    return MT_E_UNSUPPORTED;
+  }
+  return gemm_tc(dy, x, dW, nullptr, nullptr, nullptr, M, N, K, lddy, ldx, lddw, 1, 0, in_dtype, MT_F32, 0, workspace,
+                 workspace_bytes, as_stream(stream), db);
+}
+
 static int fill_rga(RgaArgs& a, const void* q, const void* k, const void* v, int64_t sb, int64_t sl,
                     int64_t sh, const void* E, const uint8_t* pad, int64_t B, int64_t h, int64_t L,
                     int64_t dh, int64_t max_seq, int causal, int dtype) {

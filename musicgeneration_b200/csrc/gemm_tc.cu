@@ -33,7 +33,8 @@ template <int BN_> struct Shape {
   static constexpr int STAGES = (BN_ == 128) ? 3 : 2;
   static constexpr int TILE_B = BN_ * BK * 2;
   static constexpr int RING = STAGES * (TILE_BYTES + TILE_B);
-  static constexpr size_t SMEM = RING + 256 + 1024;
+  static constexpr int ONES = RING + 1024;            // 2 KB of bf16 1.0 (the B operand of the column-sum product), 1 KB aligned
+  static constexpr size_t SMEM = RING + 1024 + 2048 + 1024;
   static_assert(BM * EPI_PITCH * 4 <= RING, "epilogue staging aliases the operand ring");
 };
 
@@ -48,6 +49,11 @@ struct TcGemmParams {
   int splits;
   int64_t k_per_split;
   float* part;
+  // weight-gradient launches only (A MN-major): cs_out[m] = sum_k A[k, m] -- the bias gradient -- from one extra
+  // N = 16 product per k-step against a tile of ones in the CTAs of the first tile column; split-K partials
+  // in cs_part[z][M], folded with the rest
+  float* cs_out;
+  float* cs_part;
 };
 
 // One quad (row, n .. n+3) of the output tile: bias / residual add / ReLU / ReLU-mask, then store.
@@ -139,15 +145,23 @@ __device__ __forceinline__ void epilogue_quad_pre(const TcGemmParams& p, int64_t
   else store4<float>(reinterpret_cast<float*>(p.C) + off, r);
 }
 
-template <int A_MN, int B_MN, int BN>
+template <int A_MN, int B_MN, int BN, bool CS = false>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcGemmParams p, const int fmt) {
   constexpr int STAGES = Shape<BN>::STAGES;
   constexpr int TILE_B = Shape<BN>::TILE_B;
-  constexpr int TMEM_COLS = BN;
+  constexpr bool CS_OK = CS && (A_MN == 1 && BN == 128);    // the column-sum accumulator takes TMEM columns BN .. BN+15
+  constexpr int TMEM_COLS = CS_OK ? 256 : BN;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((tc::smem_u32(smem) & 1023u) != 0) __trap();
+  const bool do_cs = CS_OK && p.cs_out != nullptr && blockIdx.x == 0;
+  if (do_cs) {
+    for (int i = threadIdx.x; i < 2048 / 16; i += TC_THREADS)
+      reinterpret_cast<uint4*>(smem + Shape<BN>::ONES)[i] = (fmt == 1) ? make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u)
+                                                                      : make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    tc::fence_proxy_async();            // generic-proxy stores -> visible to the tensor core's shared-memory reads
+  }
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * TILE_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * TILE_B);
@@ -207,6 +221,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t idesc = tc::make_idesc(BM, BN, fmt, fmt, A_MN, B_MN);
       const uint64_t ad_k = tc::make_sdesc(tc::smem_u32(sA), 16, 1024), ad_mn = tc::make_sdesc(tc::smem_u32(sA), TILE_BYTES / 2, 1024);
       const uint64_t bd_k = tc::make_sdesc(tc::smem_u32(sB), 16, 1024), bd_mn = tc::make_sdesc(tc::smem_u32(sB), TILE_BYTES / 2, 1024);
+      const uint32_t idesc_cs = tc::make_idesc(BM, 16, fmt, fmt, A_MN, 0);
+      const uint64_t ones_d = tc::make_sdesc(tc::smem_u32(smem + Shape<BN>::ONES), 16, 1024);     // K-major, 16 rows: every element is 1
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -220,6 +236,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int k4 = 0; k4 < BK / 16; ++k4)
           tc::umma_f16(tmem_base, ad0 + (A_MN ? 128 : 2) * k4, bd0 + (B_MN ? 128 : 2) * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+        if (do_cs) {      // D2[m, 0..15] += sum over the 16 k of A[k, m] * 1
+#pragma unroll
+          for (int k4 = 0; k4 < BK / 16; ++k4)
+            tc::umma_f16(tmem_base + BN, ad0 + 128 * k4, ones_d, idesc_cs, (kb | k4) != 0 ? 1u : 0u);
+        }
         tc::umma_commit(&empty[s]);
       }
       tc::umma_commit(tmem_full);
@@ -261,6 +282,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float4 acc = *reinterpret_cast<const float4*>(stage + r * EPI_PITCH + col);
         float o[4] = {acc.x, acc.y, acc.z, acc.w};
         epilogue_quad(p, row, n, o);
+      }
+    }
+    if (do_cs) {                                  // column BN of row (q * 32 + lane) = this CTA's share of the column sum
+      uint32_t r[32];
+      tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)BN, r);
+      tc::tmem_ld_wait();
+      const int64_t row = (int64_t)m0 + q * 32 + lane;
+      if (row < p.M) {
+        if (p.splits > 1) p.cs_part[(int64_t)blockIdx.z * p.M + row] = __uint_as_float(r[0]);
+        else p.cs_out[row] = __uint_as_float(r[0]);
       }
     }
   }
@@ -509,7 +540,20 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
 }
 
+// blocks past the output's own fold the column-sum partials (ascending z, like everything else here)
+__device__ __forceinline__ bool fold_colsum_blocks(const TcGemmParams& p, int64_t main_blocks) {
+  if ((int64_t)blockIdx.x < main_blocks) return false;
+  const int64_t m = ((int64_t)blockIdx.x - main_blocks) * blockDim.x + threadIdx.x;
+  if (p.cs_out != nullptr && m < p.M) {
+    float s = 0.f;
+    for (int z = 0; z < p.splits; ++z) s += p.cs_part[(int64_t)z * p.M + m];
+    p.cs_out[m] = s;
+  }
+  return true;
+}
+
 __global__ void __launch_bounds__(256) tc_splitk_fold_kernel(TcGemmParams p) {
+  if (fold_colsum_blocks(p, (p.M * p.N + 255) / 256)) return;
   int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (idx >= p.M * p.N) return;
   int64_t m = idx / p.N, n = idx - m * p.N;
@@ -529,6 +573,7 @@ __global__ void __launch_bounds__(256) tc_splitk_fold_kernel(TcGemmParams p) {
 // loads of eight splits in flight at a time; same ascending-z summation order as the scalar kernel.
 __global__ void __launch_bounds__(256) tc_splitk_fold_vec_kernel(TcGemmParams p) {
   const int64_t quads = p.M * p.N / 4;
+  if (fold_colsum_blocks(p, (quads + 255) / 256)) return;
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (idx >= quads) return;
   const int64_t e = idx * 4;
@@ -679,13 +724,14 @@ bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb
 
 size_t gemm_tc_workspace_bytes(int64_t M, int64_t N, int64_t K) {
   int s = max(tc_splits(M, N, K, 128), tc_splits(M, N, K, 256));
+  if (s > 1) return (size_t)s * (M * N + M) * sizeof(float);      // + the column-sum partials of mt_wgrad_bias
   return s > 1 ? (size_t)s * M * N * sizeof(float) : 0;
 }
 
 int gemm_tc(const void* A, const void* B, void* C, const float* bias, const float* addend, const void* aux,
             int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int transA, int transB,
             int in_dtype, int out_dtype, int epilogue, void* workspace, size_t workspace_bytes,
-            cudaStream_t stream) {
+            cudaStream_t stream, float* colsum_out) {
   CUtensorMap tmA, tmB;
   int rc;
   const int a_mn = transA ? 1 : 0;        // stored [K, M]: M contiguous
@@ -719,6 +765,17 @@ int gemm_tc(const void* A, const void* B, void* C, const float* bias, const floa
     p.splits = (int)((K + kps - 1) / kps);            // every split owns at least one k-block
   }
   p.part = reinterpret_cast<float*>(workspace);
+  p.cs_out = nullptr;
+  p.cs_part = nullptr;
+  if (colsum_out) {
+    if (!(a_mn && b_mn && BN == 128)) { set_error("gemm_tc: column sums come with the weight-gradient form only"); return MT_E_UNSUPPORTED; }
+    if (p.splits > 1 && workspace_bytes < (size_t)p.splits * (M * N + M) * sizeof(float)) {
+      set_error("gemm_tc: workspace too small for the column-sum partials");
+      return MT_E_WORKSPACE;
+    }
+    p.cs_out = colsum_out;
+    p.cs_part = p.part + (int64_t)p.splits * M * N;
+  }
   const int fmt = (in_dtype == MT_BF16) ? 1 : 0;
 
   cudaError_t e = cudaSuccess;
@@ -756,7 +813,17 @@ int gemm_tc(const void* A, const void* B, void* C, const float* bias, const floa
   }
   if (!a_mn && !b_mn) { if (wide) MT_TC_LAUNCH(0, 0, 256) else MT_TC_LAUNCH(0, 0, 128) }
   else if (!a_mn && b_mn) { if (wide) MT_TC_LAUNCH(0, 1, 256) else MT_TC_LAUNCH(0, 1, 128) }
-  else if (a_mn && b_mn) { if (wide) MT_TC_LAUNCH(1, 1, 256) else MT_TC_LAUNCH(1, 1, 128) }
+  else if (a_mn && b_mn) {
+    if (p.cs_out) {
+      auto kern = gemm_tc_kernel<1, 1, 128, true>;
+      static bool attr_done = false;
+      if (!attr_done) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape<128>::SMEM);
+        attr_done = (e == cudaSuccess);
+      }
+      if (e == cudaSuccess) kern<<<grid, TC_THREADS, Shape<128>::SMEM, stream>>>(tmA, tmB, p, fmt);
+    } else if (wide) MT_TC_LAUNCH(1, 1, 256) else MT_TC_LAUNCH(1, 1, 128)
+  }
   else { set_error("gemm_tc: unsupported operand majors"); return MT_E_UNSUPPORTED; }
 #undef MT_TC_LAUNCH
   if (e != cudaSuccess) { set_error("gemm_tc: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
@@ -764,10 +831,11 @@ int gemm_tc(const void* A, const void* B, void* C, const float* bias, const floa
   if (rc) return rc;
   if (p.splits > 1) {
     int64_t n = M * N;
+    const unsigned cs_blocks = p.cs_out ? (unsigned)((M + 255) / 256) : 0u;
     if (epilogue == 0 && !p.out_bf16 && (N % 4 == 0) && (ldc % 4 == 0) && aligned(C, 16) && aligned(workspace, 16))
-      tc_splitk_fold_vec_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, stream>>>(p);
+      tc_splitk_fold_vec_kernel<<<(unsigned)((n / 4 + 255) / 256) + cs_blocks, 256, 0, stream>>>(p);
     else
-      tc_splitk_fold_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p);
+      tc_splitk_fold_kernel<<<(unsigned)((n + 255) / 256) + cs_blocks, 256, 0, stream>>>(p);
     rc = check_launch("gemm_tc_fold");
   }
   return rc;

@@ -34,7 +34,7 @@ size_t gemm_tc_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int gemm_tc(const void* A, const void* B, void* C, const float* bias, const float* addend,
             const void* aux, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
             int64_t ldc, int transA, int transB, int in_dtype, int out_dtype, int epilogue,
-            void* workspace, size_t workspace_bytes, cudaStream_t stream);
+            void* workspace, size_t workspace_bytes, cudaStream_t stream, float* colsum_out = nullptr);
 // gemm_skinny.cu (decode-sized M: mma.sync strip kernel)
 bool gemm_skinny_supported(int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int transA, int transB,
                            int in_dtype, int out_dtype, int epilogue, const void* A, const void* B);

@@ -93,6 +93,9 @@ def linear_wgrad(dy, x, dW, db, cfg: StackCfg, ldy=None, n=None):
     T, K = x.shape
     N = n or dy.shape[1]
     ld = ldy or dy.stride(0)
+    if db is not None and ops.wgrad_bias_supported(dy, x, N, K, cfg.gemm_path):
+        ops.wgrad_bias(dy, x, dW, db, N, K, T, ld, x.stride(0), dW.stride(0))      # column sums ride along in the GEMM
+        return
     ops.gemm(dy, x, dW, N, K, T, ld, x.stride(0), dW.stride(0), True, False, path=cfg.gemm_path)
     if db is not None:
         ops.colsum(dy, db, T, N, ld)

@@ -122,6 +122,22 @@ def gemm(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, bias=None, addend=None
                         ws.numel() if ws is not None else 0, _stream()), "gemm")
 
 
+def wgrad_bias_supported(dy, x, M, N, path=L.PATH_AUTO) -> bool:
+    """Whether mt_wgrad_bias takes dW[M,N] = dy^T x with db = colsum(dy) (tcgen05 weight-gradient form)."""
+    return (path != L.PATH_SIMT and dy.dtype in (torch.bfloat16, torch.float16) and x.dtype == dy.dtype
+            and N % 128 == 0 and M >= 64 and dy.stride(0) % 8 == 0 and x.stride(0) % 8 == 0)
+
+
+def wgrad_bias(dy, x, dW, db, M, N, K, lddy, ldx, lddw):
+    """dW[M,N] = dy[K,M]^T . x[K,N], db[M] = colsum(dy): one pass over dy (see include/mt_b200.h)."""
+    _need_cuda(dy, x, dW, db)
+    lib = L.load()
+    nws = lib.mt_gemm_workspace_bytes(M, N, K, dt(dy), L.PATH_AUTO)
+    ws = workspace(nws, dy.device)
+    L.check(lib.mt_wgrad_bias(_ptr(dy), _ptr(x), _ptr(dW), _ptr(db), M, N, K, lddy, ldx, lddw, dt(dy), _ptr(ws),
+                              ws.numel() if ws is not None else 0, _stream()), "wgrad_bias")
+
+
 def colsum(X, out, M, N, ldx):
     _need_cuda(X, out)
     lib = L.load()

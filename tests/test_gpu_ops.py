@@ -373,3 +373,33 @@ def test_scalar_readback_order_and_values():
     rb.push(torch.zeros((), device="cuda"))
     with pytest.raises(RuntimeError):
         rb.push(torch.zeros((), device="cuda"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K,ldm", [(1536, 512, 32768, 1536), (256, 512, 4096, 256), (390, 512, 2048, 392),
+                                       (128, 128, 512, 128), (512, 256, 8192, 512), (200, 384, 3000, 208)])
+def test_wgrad_bias_one_pass(dev, M, N, K, ldm):
+    """mt_wgrad_bias: dW = dy^T x and db = colsum(dy) from one pass (extra N = 16 product against a ones tile).
+    Reference: fp32 matmul / column sum of the same bf16-rounded operands; fp32 accumulation, so 1e-5 of the
+    largest magnitude (the summation order differs)."""
+    from musicgeneration_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    dy = torch.zeros(K, ldm, dtype=torch.bfloat16)
+    dy[:, :M] = torch.randn(K, M, generator=g).to(torch.bfloat16)
+    x = torch.randn(K, N, generator=g).to(torch.bfloat16)
+    dyd, xd = dy.to(dev), x.to(dev)
+    assert ops.wgrad_bias_supported(dyd, xd, M, N)
+    dW = torch.full((M, N), float("nan"), device=dev)
+    db = torch.full((M,), float("nan"), device=dev)
+    ops.wgrad_bias(dyd, xd, dW, db, M, N, K, ldm, N, N)
+    ref_W = dy[:, :M].double().t() @ x.double()
+    ref_b = dy[:, :M].double().sum(0)
+    assert (dW.double().cpu() - ref_W).abs().max() <= 1e-5 * ref_W.abs().max() + 1e-4
+    assert (db.double().cpu() - ref_b).abs().max() <= 1e-5 * ref_b.abs().max() + 1e-4
+    # and against the two-launch path it replaces
+    dW2 = torch.empty((M, N), device=dev)
+    db2 = torch.empty((M,), device=dev)
+    ops.gemm(dyd, xd, dW2, M, N, K, ldm, N, N, True, False)
+    ops.colsum(dyd, db2, K, M, ldm)
+    assert torch.equal(dW, dW2)
+    assert (db - db2).abs().max() <= 1e-5 * db2.abs().max() + 1e-4

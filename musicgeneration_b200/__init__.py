@@ -6,7 +6,7 @@ utils / config); all arithmetic runs in hand-written sm_100a CUDA kernels behind
 is no CPU fallback, and a missing extension raises at first use.
 """
 from . import (_lib, config, criterion, data, engine, layers, metrics, network, ops, optim,  # noqa: F401
-               parallel, utils)
+               parallel, sequence, utils)
 from .criterion import CustomSchedule, SmoothCrossEntropyLoss  # noqa: F401
 from .engine import Mask  # noqa: F401
 from .layers import (DynamicPositionEmbedding, Encoder, EncoderLayer,  # noqa: F401

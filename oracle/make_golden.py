@@ -214,6 +214,25 @@ def data_feed_script(D, record):
     record("errs", np.array(errs))
 
 
+def golden_notes(R):
+    """Event ids -> notes through the UNMODIFIED MT/sequence.py + the velocity rescaling of MT/utils.py:25-31
+    (pretty_midi.Note stubbed by a plain record, oracle/ref_import.py): random ids over the whole model
+    vocabulary (pad / eos ids included), a hand-written phrase with overlapping and unterminated notes."""
+    rng = np.random.RandomState(21)
+    seqs = {"random": rng.randint(0, 390, size=3000),
+            "dense": rng.choice(np.r_[0:176, 176:208, 208:230], size=2000),
+            "phrase": np.array([180, 39, 250, 127, 200, 39, 43, 258, 131, 39, 307, 46, 215, 134, 50])}
+    out = {}
+    for name, ids in seqs.items():
+        ns = R.sequence.EventSeq.from_array(ids).to_note_seq()
+        for note in ns.notes:
+            note.velocity = int((note.velocity - 64) * 0.8 + 64)
+        out["ids:" + name] = ids.astype(np.int64)
+        out["notes:" + name] = np.array([[n.velocity, n.pitch, n.start, n.end] for n in ns.notes], dtype=np.float64).reshape(-1, 4)
+    np.savez(os.path.join(OUT, "notes.npz"), **out)
+    print("notes golden:", {k: v.shape for k, v in out.items()})
+
+
 def golden_data(R):
     """MT/data.py run UNMODIFIED over a synthetic ``.data`` corpus (oracle.restate.write_token_corpus).
     torch >= 2.6 defaults ``torch.load`` to weights_only=True, which rejects the pickled numpy arrays the
@@ -249,7 +268,9 @@ if __name__ == "__main__":
     R = load_reference()
     if "--data-only" in sys.argv:
         golden_data(R)
+        golden_notes(R)
         sys.exit(0)
+    golden_notes(R)
     golden_data(R)
     golden_train(R)
     golden_rga(R)

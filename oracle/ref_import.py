@@ -34,8 +34,14 @@ def reference_dir() -> str | None:
 def _install_stubs() -> None:
     if "pretty_midi" not in sys.modules:
         m = types.ModuleType("pretty_midi")
-        for n in ("PrettyMIDI", "Note", "Instrument", "ControlChange"):
+        for n in ("PrettyMIDI", "Instrument", "ControlChange"):
             setattr(m, n, type(n, (), {"__init__": lambda self, *a, **k: None}))
+
+        class Note:                 # the four fields MT/sequence.py reads and writes (pretty_midi.Note's signature)
+            def __init__(self, velocity, pitch, start, end):
+                self.velocity, self.pitch, self.start, self.end = velocity, pitch, start, end
+
+        m.Note = Note
         sys.modules["pretty_midi"] = m
     if "tensorboardX" not in sys.modules:
         m = types.ModuleType("tensorboardX")

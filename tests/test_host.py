@@ -121,3 +121,79 @@ def test_custom_schedule_drives_optimizer():
     sched.step()
     assert opt.param_groups[0]["lr"] == pytest.approx(O.noam_rate(1, 256, 10))
     assert float(p[0]) < 1.0
+
+
+# ---- events -> notes -> MIDI file ------------------------------------------------
+def _parse_smf(data: bytes):
+    """Minimal Standard MIDI File reader for the round-trip check: returns (division, tempo_us, program,
+    note-ons [(pitch, velocity, tick)], note-offs [(pitch, tick)]) -- overlapping notes of one pitch (which the
+    reference's decoder produces: a re-struck open note keeps its default length) make on/off PAIRING ambiguous in
+    a MIDI stream, so the two event multisets are compared instead."""
+    import struct
+    assert data[:4] == b"MThd"
+    hlen, fmt, ntrk, div = struct.unpack(">IHHH", data[4:14])
+    pos, tracks = 8 + hlen, []
+    for _ in range(ntrk):
+        assert data[pos:pos + 4] == b"MTrk"
+        n = struct.unpack(">I", data[pos + 4:pos + 8])[0]
+        tracks.append(data[pos + 8:pos + 8 + n])
+        pos += 8 + n
+    assert pos == len(data) and fmt == 1 and ntrk == 2
+    tempo, program, ons, offs = None, None, [], []
+    for trk in tracks:
+        i, t = 0, 0
+        while i < len(trk):
+            d = 0
+            while True:
+                b = trk[i]; i += 1
+                d = (d << 7) | (b & 0x7F)
+                if not b & 0x80:
+                    break
+            t += d
+            st = trk[i]
+            if st == 0xFF:
+                typ, ln = trk[i + 1], trk[i + 2]
+                if typ == 0x51:
+                    tempo = int.from_bytes(trk[i + 3:i + 3 + ln], "big")
+                i += 3 + ln
+            elif st & 0xF0 == 0xC0:
+                program = trk[i + 1]; i += 2
+            elif st & 0xF0 == 0x90:
+                pitch, vel = trk[i + 1], trk[i + 2]; i += 3
+                if vel:
+                    ons.append((pitch, vel, t))
+                else:
+                    offs.append((pitch, t))
+            else:
+                raise AssertionError(hex(st))
+    return div, tempo, program, ons, offs
+
+
+def test_events_to_notes_match_reference_golden():
+    """musicgeneration_b200.sequence.events_to_notes == EventSeq.from_array(ids).to_note_seq() + the velocity
+    rescaling of MT/utils.py:25-31, run UNMODIFIED in the build container (tests/golden/notes.npz): velocities
+    and pitches equal, start / end times bit-identical (same float64 accumulation order)."""
+    from musicgeneration_b200 import sequence as S
+    z = np.load(os.path.join(ROOT, "tests", "golden", "notes.npz"))
+    for name in ("random", "dense", "phrase"):
+        got = S.events_to_notes(z["ids:" + name], velocity_scale=0.8)
+        ref = z["notes:" + name]
+        assert len(got) == len(ref) > 0, name
+        arr = np.array([[n.velocity, n.pitch, n.start, n.end] for n in got], dtype=np.float64)
+        assert (arr == ref).all(), name
+    assert S.EVENT_DIM == 308 and S.events_to_notes([388, 389, 400, -1]) == []
+
+
+def test_midi_file_round_trip(tmp_path):
+    from musicgeneration_b200 import sequence as S
+    z = np.load(os.path.join(ROOT, "tests", "golden", "notes.npz"))
+    path = tmp_path / "out.mid"
+    n = S.event_indeces_to_midi_file(z["ids:dense"], str(path))
+    notes = S.events_to_notes(z["ids:dense"], 0.8)
+    assert n == len(notes) == len(z["notes:dense"])
+    div, tempo, program, ons, offs = _parse_smf(path.read_bytes())
+    assert (div, tempo, program) == (220, 500000, 1)
+    tick = lambda t: int(round(t * 220 * 2))
+    assert sorted(ons) == sorted((m.pitch, m.velocity, tick(m.start)) for m in notes)
+    assert sorted(offs) == sorted((m.pitch, tick(m.end)) for m in notes)
+    assert S.decode_midi is S.event_indeces_to_midi_file

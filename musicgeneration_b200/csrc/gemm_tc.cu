@@ -437,6 +437,8 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         float4 pa[8], pa_next[8];
         uint2 px[8], px_next[8];
         prefetch(m0, n0, 0, pa, px);
+        const bool mask_fast = pre_aux && !pre_add && p.out_bf16 && !(p.epi & (MT_EPI_BIAS | MT_EPI_RELU | MT_EPI_ADD)) &&
+                               m0 + BM <= p.M && n0 + BN <= p.N;
         tc::mbar_wait(&acc_full[buf], (i >> 1) & 1);
         tc::tc_fence_after();
         const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + chalf * CPW);
@@ -455,6 +457,25 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<uint4*>(stage + lane * PS_STG_WORDS + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
           __syncwarp();
+          if (mask_fast) {
+            // interior tile of a ReLU-masked bf16 product (the FFN_suf dgrad): 8 independent LDS -> mask -> STG
+            // chains per thread, no per-quad bounds or flag tests (28.4 us against 16.7 us for the unmasked product)
+            float4 acc[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              acc[it] = *reinterpret_cast<const float4*>(stage + (it * 4 + rsub) * PS_STG_WORDS + piece * 4);
+            const int64_t off0 = ((int64_t)m0 + q * 32 + rsub) * p.ldc + (int64_t)n0 + chalf * CPW + c * 32 + piece * 4;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              float4 v = acc[it];
+              const uint2 a = px[it];
+              if (!(__uint_as_float(a.x << 16) > 0.f)) v.x = 0.f;
+              if (!(__uint_as_float(a.x & 0xffff0000u) > 0.f)) v.y = 0.f;
+              if (!(__uint_as_float(a.y << 16) > 0.f)) v.z = 0.f;
+              if (!(__uint_as_float(a.y & 0xffff0000u) > 0.f)) v.w = 0.f;
+              store4<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.C) + off0 + (int64_t)(it * 4) * p.ldc, v);
+            }
+          } else {
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rr = it * 4 + rsub;
@@ -465,6 +486,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             float o[4] = {acc.x, acc.y, acc.z, acc.w};
             if (n + 3 < p.N) epilogue_quad_pre(p, row, n, o, pa[it], px[it], pre_add, pre_aux);
             else epilogue_quad(p, row, n, o);
+          }
           }
 #pragma unroll
           for (int it = 0; it < 8; ++it) { pa[it] = pa_next[it]; px[it] = px_next[it]; }

@@ -17,6 +17,10 @@
  *     cudaError_t; mt_last_error() returns a thread-local message; nothing throws or exits;
  *   - dtype codes: MT_F32 = 0, MT_BF16 = 1, MT_F16 = 2.  "lp" = the low-precision activation
  *     type of the bf16 mode; in fp32 mode lp pointers are NULL or dtype is MT_F32.
+ *     MT_F16_BF16 = 3 is accepted by mt_rga_fwd / mt_rga_bwd_ws (tcgen05 path) only: q, k, v and E are
+ *     f16 (11-bit mantissa), every other 16-bit tensor of the call (O, dO, dq, dk, dv) is bf16 -- the
+ *     mode of the FIRST encoder layer, whose input is the un-normalised embedding (MT/layers.py:226-229:
+ *     |logit| ~ 1e3, a bf16 operand moves the near-one-hot softmax).
  *   - tensors are row-major and dense unless strides are passed (strides are in ELEMENTS).
  */
 #ifndef MT_B200_H_
@@ -32,6 +36,7 @@ extern "C" {
 #define MT_F32 0
 #define MT_BF16 1
 #define MT_F16 2
+#define MT_F16_BF16 3
 
 #define MT_E_ARG (-1)      /* bad pointer / shape / alignment                */
 #define MT_E_UNSUPPORTED (-2) /* combination not built (e.g. dh not in {32,64,128}) */

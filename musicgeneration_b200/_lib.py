@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MT_LIB_PATH") or os.path.join(_HERE, "libmt_b200.so")     # (override: A/B timing of two builds)
 
 MT_F32, MT_BF16, MT_F16 = 0, 1, 2
+MT_F16_BF16 = 3        # mt_rga_fwd / mt_rga_bwd_ws only: f16 q/k/v/E, bf16 O/dO/dq/dk/dv (include/mt_b200.h)
 EPI_BIAS, EPI_RELU, EPI_ADD, EPI_RELU_MASK = 1, 2, 4, 8
 PATH_AUTO, PATH_SIMT, PATH_TC = 0, 1, 2
 

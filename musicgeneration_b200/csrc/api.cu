@@ -32,7 +32,7 @@ int mt_gemm(const void* A, const void* B, void* C, const float* bias, const floa
   }
   // decode-sized problems (a few dozen activation rows): weight-streaming strip kernel
   if (path == 0 && gemm_skinny_supported(M, N, K, lda, ldb, transA, transB, in_dtype, out_dtype, epilogue, A, B))
-    return gemm_skinny(A, B, C, bias, M, N, K, lda, ldb, ldc, out_dtype, epilogue, as_stream(stream));
+    return gemm_skinny(A, B, C, bias, M, N, K, lda, ldb, ldc, in_dtype, out_dtype, epilogue, as_stream(stream));
   if (path == 2 || (path == 0 && tc_ok))
     return gemm_tc(A, B, C, bias, addend, aux, M, N, K, lda, ldb, ldc, transA, transB, in_dtype, out_dtype, epilogue, workspace, workspace_bytes, as_stream(stream));
   return gemm_simt(A, B, C, bias, addend, aux, M, N, K, lda, ldb, ldc, transA, transB, in_dtype, out_dtype, epilogue, workspace, workspace_bytes, as_stream(stream));
@@ -80,6 +80,7 @@ int mt_rga_fwd(const void* q, const void* k, const void* v, int64_t sb, int64_t 
   bool tc_ok = rga_tc_supported(a, (int)dh, dtype, false);
   if (path == 2 && !tc_ok) { set_error("rga_fwd: tcgen05 path does not take this problem"); return MT_E_UNSUPPORTED; }
   if (path == 2 || (path == 0 && tc_ok)) return rga_fwd_tc(a, (int)dh, dtype, as_stream(stream));
+  if (dtype == MT_F16_BF16) { set_error("rga_fwd: the mixed f16/bf16 mode exists on the tcgen05 path only"); return MT_E_UNSUPPORTED; }
   return rga_fwd_simt(a, (int)dh, dtype, as_stream(stream));
 }
 
@@ -97,7 +98,7 @@ int mt_rga_weights(const void* q, const void* k, int64_t sb, int64_t sl, int64_t
 }
 
 size_t mt_rga_bwd_workspace_bytes(int64_t B, int64_t h, int64_t L, int64_t dh, int dtype) {
-  if (dh != 64 || dtype != MT_BF16 || B <= 0 || h <= 0 || L <= 0) return 0;
+  if (dh != 64 || (dtype != MT_BF16 && dtype != MT_F16_BF16) || B <= 0 || h <= 0 || L <= 0) return 0;
   return rga_bwd3_workspace_bytes(B, h, L);
 }
 
@@ -126,6 +127,7 @@ int mt_rga_bwd_ws(const void* q, const void* k, const void* v, int64_t sb, int64
   bool tc_ok = rga_tc_supported(a, (int)dh, dtype, true);
   if (path == 2 && !tc_ok) { set_error("rga_bwd: tcgen05 path does not take this problem"); return MT_E_UNSUPPORTED; }
   if (path == 2 || (path == 0 && tc_ok)) return rga_bwd_tc(a, (int)dh, dtype, workspace, workspace_bytes, as_stream(stream));
+  if (dtype == MT_F16_BF16) { set_error("rga_bwd: the mixed f16/bf16 mode exists on the tcgen05 path only"); return MT_E_UNSUPPORTED; }
   return rga_bwd_simt(a, (int)dh, dtype, as_stream(stream));
 }
 

@@ -100,6 +100,20 @@ template <> struct Raw8<__nv_bfloat16> {
     for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
   }
 };
+template <> struct Raw8<__half> {
+  uint4 r;
+  __device__ __forceinline__ void load(const __half* p) { r = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void zero() { r = make_uint4(0, 0, 0, 0); }
+  __device__ __forceinline__ void store(__half* p) const { *reinterpret_cast<uint4*>(p) = r; }
+  __device__ __forceinline__ void to_float(float (&f)[8]) const {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = v.x; f[2 * i + 1] = v.y;
+    }
+  }
+};
 template <> struct Raw8<float> {
   float4 a, b;
   __device__ __forceinline__ void load(const float* p) {
@@ -123,6 +137,12 @@ template <> __device__ __forceinline__ void load8f<__nv_bfloat16>(const __nv_bfl
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+
+template <> __device__ __forceinline__ void load8f<__half>(const __half* p, float (&f)[8]) {
+  Raw8<__half> r;
+  r.load(p);
+  r.to_float(f);
 }
 
 template <typename T, int DH>
@@ -412,7 +432,7 @@ static int rga_decode_impl(const void* q, int64_t q_stride_b, const void* kcache
     if (smem > 48 * 1024) ae = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     kern<<<grid, 128, smem, as_stream(stream)>>>((const T*)q, (const T*)kcache, (const T*)vcache, (const T*)E, pad_keys, (T*)out, q_stride_b, (int)h, (int)max_seq, (int)t, t_dev, sqrtf((float)dh)); \
   }
-  MT_DISPATCH_F32_BF16(dtype, T, {
+  MT_DISPATCH_DTYPE(dtype, T, {
     if (dh == 32) MT_LAUNCH_DEC(T, 32)
     else if (dh == 64) MT_LAUNCH_DEC(T, 64)
     else if (dh == 128) MT_LAUNCH_DEC(T, 128)
@@ -436,7 +456,7 @@ static int kv_append_impl(const void* qkv, void* kcache, void* vcache, int64_t B
   MT_REQUIRE(B > 0 && h > 0 && dh > 0 && t >= 0 && t < max_seq, "kv_append: bad shape");
   MT_REQUIRE(!pad_bits || ids, "kv_append: pad_bits needs the id matrix");
   int64_t n = B * h * dh;
-  MT_DISPATCH_F32_BF16(dtype, T,
+  MT_DISPATCH_DTYPE(dtype, T,
       (kv_append_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>((const T*)qkv, (T*)kcache, (T*)vcache, (int)B, (int)h, (int)dh, (int)max_seq, (int)t, t_dev, ids, ld_ids, pad_token, pad_bits)));
   return check_launch("kv_append");
 }
@@ -473,7 +493,7 @@ int mt_decode_embed(const int32_t* ids, int64_t ld_ids, const int32_t* t_dev, co
   MT_REQUIRE(ids && t_dev && emb && pe && out_f32 && B > 0 && d > 0 && d % 4 == 0 && V > 0, "decode_embed: bad args");
   if (!out_lp) lp_dtype = MT_F32;
   int64_t n4 = B * (d / 4);
-  MT_DISPATCH_F32_BF16(lp_dtype, TL,
+  MT_DISPATCH_DTYPE(lp_dtype, TL,
       (launch_chain(decode_embed_kernel<TL>, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, as_stream(stream), ids, ld_ids, t_dev, emb, pe, out_f32, (TL*)out_lp, (int)B, (int)(d / 4), (int)V, scale, pad_token, pad_bits, max_seq)));
   return check_launch("decode_embed");
 }
@@ -511,7 +531,7 @@ int mt_decode_attend(const void* q, int64_t q_stride_b, void* kcache, void* vcac
   const float isd = 1.f / sqrtf((float)dh);
 #define MT_LAUNCH_DECS(T, DHC) \
   launch_chain(rga_decode_split_kernel<T, DHC>, grid, dim3(128), 0, as_stream(stream), (const T*)q, (T*)kcache, (T*)vcache, (const T*)E, pad_bits, (T*)out, q_stride_b, (int)h, (int)max_seq, t_dev, isd, counters, part, nsplit, append);
-  MT_DISPATCH_F32_BF16(dtype, T, {
+  MT_DISPATCH_DTYPE(dtype, T, {
     if (dh == 32) { MT_LAUNCH_DECS(T, 32) }
     else if (dh == 64) { MT_LAUNCH_DECS(T, 64) }
     else if (dh == 128) { MT_LAUNCH_DECS(T, 128) }

@@ -578,7 +578,7 @@ int mt_embed_pos_fwd(const int32_t* ids, const float* emb, const float* pe, floa
   float inv_keep = 1.f / (1.f - p_drop);
   int grid = grid_for(T * (d / 4), 256);
   if (!out_lp) lp_dtype = MT_F32;
-  MT_DISPATCH_F32_BF16(lp_dtype, TL,
+  MT_DISPATCH_DTYPE(lp_dtype, TL,
       (embed_pos_fwd_kernel<TL><<<grid, 256, 0, as_stream(stream)>>>(ids, emb, pe, out_f32, (TL*)out_lp, T, L, (int)(d / 4), V, pos0, scale, p_drop, inv_keep, seed, site)));
   return check_launch("embed_pos_fwd");
 }

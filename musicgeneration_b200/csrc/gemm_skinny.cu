@@ -23,7 +23,8 @@ struct SkinnyParams {
   const __nv_bfloat16* A; const __nv_bfloat16* W; void* C; const float* bias;
   int M, N, K;
   int64_t lda, ldw, ldc;
-  int epi, out_bf16;
+  int epi, out_bf16;                // out_bf16: 16-bit output (bf16, or f16 when out_f16)
+  int in_f16, out_f16;              // f16 operands / output: the first encoder layer of the bf16 mode
   int mtiles;                       // ceil(M / 16)
 };
 
@@ -39,6 +40,13 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void mma_f16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -95,7 +103,8 @@ gemm_skinny_kernel(const SkinnyParams p) {
     for (int m = 0; m < MT; ++m) {
       uint32_t a[4];
       ldmatrix_x4(a, sA_u + (uint32_t)(((m * 16 + lrow) * pitch + k0 + lcol) * 2));
-      mma_bf16_16816(acc[m], a, b0, b1);
+      if (p.in_f16) mma_f16_16816(acc[m], a, b0, b1);
+      else mma_bf16_16816(acc[m], a, b0, b1);
     }
   }
   // ---- fold the four K quarters; C fragment: c0,c1 -> row lane/4, cols 2*(lane%4)+{0,1}; c2,c3 -> row + 8
@@ -116,7 +125,8 @@ gemm_skinny_kernel(const SkinnyParams p) {
     for (int w = 0; w < SK_WARPS; ++w) s += red[w * MT * 16 * 8 + e];
     if (p.epi & MT_EPI_BIAS) s += p.bias[n];
     if (p.epi & MT_EPI_RELU) s = fmaxf(s, 0.f);
-    if (p.out_bf16) reinterpret_cast<__nv_bfloat16*>(p.C)[(int64_t)r * p.ldc + n] = __float2bfloat16_rn(s);
+    if (p.out_f16) reinterpret_cast<__half*>(p.C)[(int64_t)r * p.ldc + n] = __float2half_rn(s);
+    else if (p.out_bf16) reinterpret_cast<__nv_bfloat16*>(p.C)[(int64_t)r * p.ldc + n] = __float2bfloat16_rn(s);
     else reinterpret_cast<float*>(p.C)[(int64_t)r * p.ldc + n] = s;
   }
 }
@@ -129,7 +139,8 @@ size_t skinny_smem(int mtiles, int K) {
 
 bool gemm_skinny_supported(int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int transA, int transB,
                            int in_dtype, int out_dtype, int epilogue, const void* A, const void* B) {
-  if (in_dtype != MT_BF16 || (out_dtype != MT_F32 && out_dtype != MT_BF16)) return false;
+  if (in_dtype != MT_BF16 && in_dtype != MT_F16) return false;
+  if (out_dtype != MT_F32 && out_dtype != MT_BF16 && out_dtype != MT_F16) return false;
   if (transA || !transB) return false;                               // x . W^T only
   if (M > 64 || K % 64 || K > 2048 || N < 1) return false;
   if (epilogue & ~(MT_EPI_BIAS | MT_EPI_RELU)) return false;
@@ -138,11 +149,12 @@ bool gemm_skinny_supported(int64_t M, int64_t N, int64_t K, int64_t lda, int64_t
 }
 
 int gemm_skinny(const void* A, const void* B, void* C, const float* bias, int64_t M, int64_t N, int64_t K,
-                int64_t lda, int64_t ldb, int64_t ldc, int out_dtype, int epilogue, cudaStream_t st) {
+                int64_t lda, int64_t ldb, int64_t ldc, int in_dtype, int out_dtype, int epilogue, cudaStream_t st) {
   SkinnyParams p;
   p.A = reinterpret_cast<const __nv_bfloat16*>(A); p.W = reinterpret_cast<const __nv_bfloat16*>(B);
   p.C = C; p.bias = bias; p.M = (int)M; p.N = (int)N; p.K = (int)K;
-  p.lda = lda; p.ldw = ldb; p.ldc = ldc; p.epi = epilogue; p.out_bf16 = (out_dtype == MT_BF16);
+  p.lda = lda; p.ldw = ldb; p.ldc = ldc; p.epi = epilogue; p.out_bf16 = (out_dtype != MT_F32);
+  p.in_f16 = (in_dtype == MT_F16); p.out_f16 = (out_dtype == MT_F16);
   p.mtiles = (int)((M + 15) / 16);
   const size_t smem = skinny_smem(p.mtiles, (int)K);
   const unsigned grid = (unsigned)((N + SK_BN - 1) / SK_BN);

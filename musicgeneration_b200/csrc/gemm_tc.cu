@@ -44,7 +44,8 @@ struct TcGemmParams {
   const float* addend;
   const void* aux;
   int64_t M, N, K, ldc;
-  int epi, out_bf16, vec_ok;
+  int epi, out_bf16, vec_ok;     // out_bf16: the output is 16-bit (bf16, or f16 when out_f16 is set)
+  int out_f16;
   int add_inplace;          // EPI_ADD with addend == C (fp32, no ReLU / mask): accumulate with red.global.add.v4.f32
   int splits;
   int64_t k_per_split;
@@ -55,6 +56,16 @@ struct TcGemmParams {
   float* cs_out;
   float* cs_part;
 };
+
+// 16-bit output: bf16, or f16 (the first encoder layer's QKV projection in the mixed mode)
+__device__ __forceinline__ void store4_lp(const TcGemmParams& p, int64_t off, const float4& r) {
+  if (p.out_f16) store4<__half>(reinterpret_cast<__half*>(p.C) + off, r);
+  else store4<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.C) + off, r);
+}
+__device__ __forceinline__ void store1_lp(const TcGemmParams& p, int64_t off, float x) {
+  if (p.out_f16) reinterpret_cast<__half*>(p.C)[off] = __float2half_rn(x);
+  else reinterpret_cast<__nv_bfloat16*>(p.C)[off] = __float2bfloat16_rn(x);
+}
 
 // One quad (row, n .. n+3) of the output tile: bias / residual add / ReLU / ReLU-mask, then store.
 __device__ __forceinline__ void epilogue_quad(const TcGemmParams& p, int64_t row, int64_t n, float (&o)[4]) {
@@ -99,7 +110,7 @@ __device__ __forceinline__ void epilogue_quad(const TcGemmParams& p, int64_t row
       if (!(m.w > 0.f)) o[3] = 0.f;
     }
     float4 r = make_float4(o[0], o[1], o[2], o[3]);
-    if (p.out_bf16) store4<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.C) + off, r);
+    if (p.out_bf16) store4_lp(p, off, r);
     else store4<float>(reinterpret_cast<float*>(p.C) + off, r);
   } else {
 #pragma unroll
@@ -113,7 +124,7 @@ __device__ __forceinline__ void epilogue_quad(const TcGemmParams& p, int64_t row
       if (p.epi & MT_EPI_RELU_MASK) {
         if (!(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.aux)[off + t]) > 0.f)) x = 0.f;
       }
-      if (p.out_bf16) reinterpret_cast<__nv_bfloat16*>(p.C)[off + t] = __float2bfloat16_rn(x);
+      if (p.out_bf16) store1_lp(p, off + t, x);
       else reinterpret_cast<float*>(p.C)[off + t] = x;
     }
   }
@@ -141,7 +152,7 @@ __device__ __forceinline__ void epilogue_quad_pre(const TcGemmParams& p, int64_t
     if (!(m3 > 0.f)) o[3] = 0.f;
   }
   float4 r = make_float4(o[0], o[1], o[2], o[3]);
-  if (p.out_bf16) store4<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.C) + off, r);
+  if (p.out_bf16) store4_lp(p, off, r);
   else store4<float>(reinterpret_cast<float*>(p.C) + off, r);
 }
 
@@ -437,7 +448,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         float4 pa[8], pa_next[8];
         uint2 px[8], px_next[8];
         prefetch(m0, n0, 0, pa, px);
-        const bool mask_fast = pre_aux && !pre_add && p.out_bf16 && !(p.epi & (MT_EPI_BIAS | MT_EPI_RELU | MT_EPI_ADD)) &&
+        const bool mask_fast = pre_aux && !pre_add && p.out_bf16 && !p.out_f16 && !(p.epi & (MT_EPI_BIAS | MT_EPI_RELU | MT_EPI_ADD)) &&
                                m0 + BM <= p.M && n0 + BN <= p.N;
         tc::mbar_wait(&acc_full[buf], (i >> 1) & 1);
         tc::tc_fence_after();
@@ -536,7 +547,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               if (p.add_inplace)
                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(reinterpret_cast<float*>(p.C) + off),
                              "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-              else if (p.out_bf16) store4<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.C) + off, v);
+              else if (p.out_bf16) store4_lp(p, off, v);
               else store4<float>(reinterpret_cast<float*>(p.C) + off, v);
             }
           } else {
@@ -587,7 +598,7 @@ __global__ void __launch_bounds__(256) tc_splitk_fold_kernel(TcGemmParams p) {
   if (p.epi & MT_EPI_RELU_MASK) {
     if (!(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.aux)[m * p.ldc + n]) > 0.f)) s = 0.f;
   }
-  if (p.out_bf16) reinterpret_cast<__nv_bfloat16*>(p.C)[m * p.ldc + n] = __float2bfloat16_rn(s);
+  if (p.out_bf16) store1_lp(p, m * p.ldc + n, s);
   else reinterpret_cast<float*>(p.C)[m * p.ldc + n] = s;
 }
 
@@ -734,7 +745,7 @@ bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb
                        const void* C) {
   (void)epilogue; (void)C;
   if (in_dtype != MT_BF16 && in_dtype != MT_F16) return false;
-  if (out_dtype != MT_F32 && out_dtype != MT_BF16) return false;
+  if (out_dtype != MT_F32 && out_dtype != MT_BF16 && out_dtype != MT_F16) return false;
   if (transA && !(transA && !transB)) return false;                 // TN only (wgrad form)
   if (!aligned(A, 16) || !aligned(B, 16)) return false;
   if (lda % 8 || ldb % 8) return false;
@@ -772,7 +783,8 @@ int gemm_tc(const void* A, const void* B, void* C, const float* bias, const floa
   TcGemmParams p;
   p.C = C; p.bias = bias; p.addend = addend; p.aux = aux;
   p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.epi = epilogue;
-  p.out_bf16 = (out_dtype == MT_BF16);
+  p.out_bf16 = (out_dtype != MT_F32);
+  p.out_f16 = (out_dtype == MT_F16);
   const int oes = p.out_bf16 ? 2 : 4;
   p.vec_ok = (ldc % 4 == 0) && aligned(C, 4 * oes) && (!(epilogue & MT_EPI_BIAS) || aligned(bias, 16)) &&
              (!(epilogue & MT_EPI_ADD) || aligned(addend, 16)) && (!(epilogue & MT_EPI_RELU_MASK) || aligned(aux, 8));

@@ -39,7 +39,7 @@ int gemm_tc(const void* A, const void* B, void* C, const float* bias, const floa
 bool gemm_skinny_supported(int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int transA, int transB,
                            int in_dtype, int out_dtype, int epilogue, const void* A, const void* B);
 int gemm_skinny(const void* A, const void* B, void* C, const float* bias, int64_t M, int64_t N, int64_t K,
-                int64_t lda, int64_t ldb, int64_t ldc, int out_dtype, int epilogue, cudaStream_t st);
+                int64_t lda, int64_t ldb, int64_t ldc, int in_dtype, int out_dtype, int epilogue, cudaStream_t st);
 bool rga_tc_supported(const RgaArgs& a, int dh, int dtype, bool backward);
 int rga_fwd_tc(const RgaArgs& a, int dh, int dtype, cudaStream_t st);
 int rga_bwd_tc(const RgaArgs& a, int dh, int dtype, void* ws, size_t ws_bytes, cudaStream_t st);

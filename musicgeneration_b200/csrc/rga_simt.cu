@@ -512,7 +512,7 @@ int rga_fwd_simt(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
 
 int rga_weights_simt(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
   int rc = 0;
-  MT_DISPATCH_F32_BF16(dtype, T, MT_DISPATCH_DH(dh, DHC, {
+  MT_DISPATCH_DTYPE(dtype, T, MT_DISPATCH_DH(dh, DHC, {
     size_t smem = ((2 * RT + 2 * RT - 1) * (DHC + 1)) * sizeof(float);
     auto kern = rga_weights_kernel<T, DHC>;
     if ((rc = set_smem(kern, smem))) return rc;

@@ -60,6 +60,7 @@ struct FwdParams {
   float* lse;
   const uint8_t* pad;
   int B, h, L, max_seq, causal, fmt;
+  int ofmt;             // 16-bit format of O (1 = bf16, 0 = f16); differs from fmt in the mixed mode (f16 q/k/v/E, bf16 O)
   int heads_per_cta;    // consecutive heads walked by one CTA (same batch row and query tile): halves the per-CTA fixed cost
   float scale_log2;     // log2(e) / sqrt(dh)
   long long* trace;     // MT_RGA_TRACE=z: clock64 stamps of CTA (0,0,z), [2 agents][32 steps][8 events]
@@ -368,7 +369,7 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           tc::tmem_ld_wait();
 #pragma unroll
           for (int x = 0; x < 16; x += 2)
-            packed[x / 2] = pack16(__uint_as_float(r[x]) * inv, __uint_as_float(r[x + 1]) * inv, p.fmt);
+            packed[x / 2] = pack16(__uint_as_float(r[x]) * inv, __uint_as_float(r[x + 1]) * inv, p.ofmt);
         }
         tc::tc_fence_before();
         tc::mbar_arrive(o_free);               // the next head's first P.V product may overwrite O
@@ -405,7 +406,7 @@ bool rga_bwd_tc_supported(const RgaArgs& a, int dh, int dtype);   // rga_tc_bwd.
 bool rga_tc_supported(const RgaArgs& a, int dh, int dtype, bool backward) {
   if (backward) return rga_bwd_tc_supported(a, dh, dtype);
   if (dh != DHC) return false;
-  if (dtype != MT_BF16 && dtype != MT_F16) return false;
+  if (dtype != MT_BF16 && dtype != MT_F16 && dtype != MT_F16_BF16) return false;
   if (a.sl % 8 || a.sh % 8 || a.sb % 8) return false;
   if (!aligned(a.q, 16) || !aligned(a.k, 16) || !aligned(a.v, 16) || !aligned(a.E, 16)) return false;
   if (a.O && (a.ol % 8 || a.oh % 8 || a.ob % 8 || !aligned(a.O, 16))) return false;
@@ -424,6 +425,7 @@ int rga_fwd_tc(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
   p.O = a.O; p.ob = a.ob; p.ol = a.ol; p.oh = a.oh; p.lse = a.lse; p.pad = a.pad;
   p.B = a.B; p.h = a.h; p.L = a.L; p.max_seq = a.max_seq; p.causal = a.causal;
   p.fmt = (dtype == MT_BF16) ? 1 : 0;
+  p.ofmt = (dtype == MT_F16) ? 0 : 1;
   p.scale_log2 = LOG2E / a.inv_scale_div;
   static bool attr_done = false;
   if (!attr_done) {

@@ -94,6 +94,7 @@ struct Bwd2Params {
   int bh_per_cta;                        // DE role
   uint8_t* ds_ws; int nTri;              // DKV role: spill every dS tile image here (rga_tc_bwd3.cu consumes them)
   int heads_per_cta;                     // DKV role: consecutive heads of one (batch row, key tile) walked by one CTA
+  int qk_fmt;                            // DKV role: 16-bit format of q / k / v / E (1 = bf16, 0 = f16: mixed mode); dO, P, dS, dq/dk/dv are bf16
   float scale, scale_log2;
   long long* trace;                      // MT_RGA_TRACE=z: clock64 stamps of CTA (0,0,z), [4 agents][32 steps][8 events]
   int trace_z;
@@ -356,7 +357,8 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ================================ MMA issuer ============================================
     if (ROLE == R_DKV) {
       if (lane == 0) {         // S, G, dP products (dV / dK: second issuer, warp 18)
-        const uint32_t id_kk = tc::make_idesc(TT, TT, 1, 1, 0, 0);      // K-major x K-major, N = 128
+        const uint32_t id_kk = tc::make_idesc(TT, TT, p.qk_fmt, p.qk_fmt, 0, 0);      // S, G: K-major x K-major, N = 128
+        const uint32_t id_dp = tc::make_idesc(TT, TT, 1, p.qk_fmt, 0, 0);             // dP: A = dO (bf16), B = V
         constexpr uint64_t TS16 = TILE >> 4;
         const uint64_t kd = tc::make_sdesc(tc::smem_u32(buf_k()), 16, 1024);
         const uint64_t vd = tc::make_sdesc(tc::smem_u32(buf_v()), 16, 1024);
@@ -395,7 +397,7 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const uint64_t dod = dod0 + (uint64_t)(n % 3) * TS16;
 #pragma unroll
           for (int k4 = 0; k4 < DHC / 16; ++k4)   // dP = dO V^T into the S columns
-            tc::umma_f16(tmem + TM_S, dod + 2 * k4, vd + 2 * k4, id_kk, k4 != 0);
+            tc::umma_f16(tmem + TM_S, dod + 2 * k4, vd + 2 * k4, id_dp, k4 != 0);
           tc::umma_commit(dp_full);
           TRACE(3, n, 1);
           if (++k == per) { k = 0; ++item; }
@@ -593,6 +595,7 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // products touch disjoint TMEM columns and shared-memory stages, so they are issued by two threads.
     if (ROLE == R_DKV && MT_DKV_FUSED16 && lane == 0) {
       const uint32_t id_mnmn = tc::make_idesc(TT, DHC, 1, 1, 1, 1);   // A MN-major (P / dS), B MN-major (dO / Q), N = 64
+      const uint32_t id_dk = tc::make_idesc(TT, DHC, 1, p.qk_fmt, 1, 1);   // dK: B = Q in its own 16-bit format
       constexpr uint64_t STR = TILE >> 4;
       const uint64_t qd_mn0 = tc::make_sdesc(tc::smem_u32(smem + Lay2<R_DKV>::Q0), 1024, 1024);
       const uint64_t dod_mn0 = tc::make_sdesc(tc::smem_u32(smem + Lay2<R_DKV>::DO0), 1024, 1024);
@@ -616,7 +619,7 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int k16 = 0; k16 < TT / 16; ++k16) {      // contraction over the 128 query rows
           tc::umma_f16(tmem + TM_ACC1, opd0 + 128 * k16, dod_mn + 128 * k16, id_mnmn, (k | k16) != 0);   // dV += P^T dO
-          tc::umma_f16(tmem + TM_ACC0, opd1 + 128 * k16, qd_mn + 128 * k16, id_mnmn, (k | k16) != 0);    // dK += dS^T Q
+          tc::umma_f16(tmem + TM_ACC0, opd1 + 128 * k16, qd_mn + 128 * k16, id_dk, (k | k16) != 0);      // dK += dS^T Q
         }
         if (p.ds_ws) tc::bulk_wait_read0();            // the math warps overwrite dS once step_done is signalled
         tc::umma_commit(&qd_empty[n % 3]);
@@ -1090,6 +1093,7 @@ Bwd2Params make_params2(const RgaArgs& a) {
   p.bh_per_cta = 1;
   p.ds_ws = nullptr;
   p.heads_per_cta = 1;
+  p.qk_fmt = 1;
   p.nTri = p.nT * (p.nT + 1) / 2;
   p.trace = nullptr;
   p.trace_z = 0;
@@ -1100,9 +1104,10 @@ Bwd2Params make_params2(const RgaArgs& a) {
 
 // dK, dV (key-tile owner walks the query tiles at or below it); ds_ws != NULL: also spill the dS tiles
 int rga_bwd2_dkv(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
-                 const CUtensorMap& tmDO, const CUtensorMap& tmE, void* ds_ws, cudaStream_t st) {
+                 const CUtensorMap& tmDO, const CUtensorMap& tmE, void* ds_ws, int qk_fmt, cudaStream_t st) {
   Bwd2Params p = make_params2(a);
   p.ds_ws = static_cast<uint8_t*>(ds_ws);
+  p.qk_fmt = qk_fmt;
   // consecutive heads of one (batch row, key tile) share a CTA (same walk over the query tiles; the resident K / V
   // tiles are reloaded and dK / dV flushed at the head boundary): as many as leave at least three CTAs per SM
   static const int hpc_env = getenv("MT_DKV_HPC") ? atoi(getenv("MT_DKV_HPC")) : 0;

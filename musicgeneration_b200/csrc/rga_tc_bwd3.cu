@@ -65,6 +65,7 @@ struct Bwd3Params {
   int B, h, L, max_seq, nT, nTri;
   int bh_per_cta;                        // dE role
   int heads_per_cta;                     // dQ role: consecutive heads of one (batch row, query tile) walked by one CTA
+  int qk_fmt;                            // 16-bit format of the K / Q / E operands (1 = bf16, 0 = f16: mixed mode); dS / dG are bf16
   long long* trace;                      // MT_RGA_TRACE=z: clock64 stamps of CTA (0,0,z), [2 agents][32 steps][4 events]
   int trace_z;
 };
@@ -188,7 +189,7 @@ rga_bwd3_kernel(const __grid_constant__ CUtensorMap tmX,      // K (dQ role) or 
     // ================================ MMA issuer ============================================
     if (lane == 0) {
       if (ROLE == L_DQ) {
-        const uint32_t id_kmn = tc::make_idesc(TT, DHC, 1, 1, 0, 1);    // A K-major (TMEM dS / smem dG), B MN-major (K / E), N = 64
+        const uint32_t id_kmn = tc::make_idesc(TT, DHC, 1, p.qk_fmt, 0, 1);    // A K-major (TMEM dS / smem dG, bf16), B MN-major (K / E), N = 64
         const uint64_t kd_mn0 = tc::make_sdesc(tc::smem_u32(smem + LY::X0), 1024, 1024);
         const uint64_t ed_mn0 = tc::make_sdesc(tc::smem_u32(smem + LY::E0), 1024, 1024);
         const uint64_t dgd0 = tc::make_sdesc(tc::smem_u32(smem + LY::DG), 16, 1024);
@@ -219,7 +220,7 @@ rga_bwd3_kernel(const __grid_constant__ CUtensorMap tmX,      // K (dQ role) or 
           TRACE3(1, n, 2);
         }
       } else {
-        const uint32_t id_mnmn = tc::make_idesc(TT, DHC, 1, 1, 1, 1);   // A MN-major (dG block), B MN-major (Q), N = 64
+        const uint32_t id_mnmn = tc::make_idesc(TT, DHC, 1, p.qk_fmt, 1, 1);   // A MN-major (dG block, bf16), B MN-major (Q), N = 64
         const uint64_t qd_mn0 = tc::make_sdesc(tc::smem_u32(smem + LY::X0), 1024, 1024);
         const uint64_t dg_lo0 = tc::make_sdesc(tc::smem_u32(smem + LY::DG), TILE, 1024);
         const uint64_t dg_hi0 = tc::make_sdesc(tc::smem_u32(smem + LY::DG + 2 * TILE), TILE, 1024);
@@ -427,6 +428,7 @@ Bwd3Params make_params3(const RgaArgs& a, const void* ws) {
   p.nTri = p.nT * (p.nT + 1) / 2;
   p.bh_per_cta = 1;
   p.heads_per_cta = 1;
+  p.qk_fmt = 1;
   p.trace = nullptr;
   p.trace_z = 0;
   return p;
@@ -440,8 +442,9 @@ size_t rga_bwd3_workspace_bytes(int64_t B, int64_t h, int64_t L) {
 }
 
 // dQ from the spilled dS tiles (query-tile owner walks the key tiles at or left of it)
-int rga_bwd3_dq(const RgaArgs& a, const void* ws, const CUtensorMap& tmK, const CUtensorMap& tmE, cudaStream_t st) {
+int rga_bwd3_dq(const RgaArgs& a, const void* ws, const CUtensorMap& tmK, const CUtensorMap& tmE, int qk_fmt, cudaStream_t st) {
   Bwd3Params p = make_params3(a, ws);
+  p.qk_fmt = qk_fmt;
   // consecutive heads of one (batch row, query tile) share a CTA (same number of key tiles, same E blocks, two
   // alternating accumulators): as many as leave at least three CTAs per SM
   static const int hpc_env = getenv("MT_DQ_HPC") ? atoi(getenv("MT_DQ_HPC")) : 0;
@@ -454,8 +457,9 @@ int rga_bwd3_dq(const RgaArgs& a, const void* ws, const CUtensorMap& tmK, const 
 }
 
 // dE from the spilled dS tiles (tile-diagonal owner walks down the diagonal over a slice of (batch, head))
-int rga_bwd3_de(const RgaArgs& a, const void* ws, const CUtensorMap& tmQ, const CUtensorMap& tmE, cudaStream_t st) {
+int rga_bwd3_de(const RgaArgs& a, const void* ws, const CUtensorMap& tmQ, const CUtensorMap& tmE, int qk_fmt, cudaStream_t st) {
   Bwd3Params p = make_params3(a, ws);
+  p.qk_fmt = qk_fmt;
   const int bh = a.B * a.h;
   int slices = (2 * sm_count() + p.nT - 1) / p.nT;       // about two CTAs per SM's worth of slices
   if (slices > bh) slices = bh;

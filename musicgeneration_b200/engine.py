@@ -9,7 +9,11 @@ Precision modes
     ids exact).
   * "bf16": fp32 master weights and fp32 residual stream / LayerNorm / softmax / accumulators;
     GEMM and attention operands bf16 (activations are written once in bf16 next to the fp32
-    residual by the producing kernel) -- the throughput mode.
+    residual by the producing kernel) -- the throughput mode.  The FIRST layer's attention sees the
+    un-normalised embedding (MT/layers.py:226-229: |logit| ~ 1e3, softmax nearly one-hot), where a
+    bf16 operand error moves the attention targets (logits error 1.6e-2 at config B, above the 1e-2
+    bar); its x, Wq/Wk/Wv, q/k/v and E operands are therefore f16 (same tensor-core rate, 11-bit
+    mantissa; "hp" below): 3.9e-3 (scripts/sim_precision.py, measured values in DESIGN.md).
 """
 from __future__ import annotations
 
@@ -54,6 +58,10 @@ class LayerWeights:
     b1: torch.Tensor
     g2: torch.Tensor
     b2: torch.Tensor
+    # f16 operand copies of the first layer's attention in the bf16 mode (None elsewhere)
+    Wqkv_hp: Optional[torch.Tensor] = None
+    E_hp: Optional[torch.Tensor] = None
+    Wfc_hp: Optional[torch.Tensor] = None     # decode only (there the attention output stays f16)
 
 
 @dataclass
@@ -104,15 +112,30 @@ def linear_wgrad(dy, x, dW, db, cfg: StackCfg, ldy=None, n=None):
 # ---------------------------------------------------------------------------------------
 # relative global attention block: QKV projection -> fused attention -> fc
 # ---------------------------------------------------------------------------------------
+def hp_eligible(W: LayerWeights, cfg: StackCfg, mask: Optional[Mask]) -> bool:
+    """Whether this layer's attention runs with f16 q/k/v/E operands (the mixed mode of the tcgen05
+    kernels: causal mask, head dim 64, bf16 activations elsewhere)."""
+    return (W.Wqkv_hp is not None and W.E_hp is not None and cfg.act == torch.bfloat16 and cfg.dh == 64
+            and mask is not None and bool(mask.causal)
+            and cfg.attn_path != L.PATH_SIMT and cfg.gemm_path != L.PATH_SIMT)
+
+
 def rga_block_fwd(xq, xk, xv, W: LayerWeights, cfg: StackCfg, B: int, Lq: int, mask: Optional[Mask],
-                  need_weights: bool):
+                  need_weights: bool, x_hp: Optional[torch.Tensor] = None, x_f32: Optional[torch.Tensor] = None):
     """xq/xk/xv: [T, d] act dtype (the same tensor for self-attention).  Returns
-    (a [T,d] act dtype = fc output incl. bias, saved dict, P or None)."""
+    (a [T,d] act dtype = fc output incl. bias, saved dict, P or None).
+    ``x_hp`` (f16 copy of the self-attention input) selects the f16-operand mode of the first layer;
+    ``xq`` may then be None (the bf16 copy the weight gradient needs is cast from ``x_f32`` in the backward)."""
     d, h, dh = cfg.d, cfg.h, cfg.dh
     T = B * Lq
-    qkv = _empty((T, 3 * d), cfg.act, xq)
-    same = (xq is xk) and (xk is xv)
-    if same:
+    hp = x_hp is not None
+    like = x_hp if hp else xq
+    qkv = _empty((T, 3 * d), torch.float16 if hp else cfg.act, like)
+    same = hp or ((xq is xk) and (xk is xv))
+    E = W.E_hp if hp else W.E
+    if hp:
+        linear_fwd(x_hp, W.Wqkv_hp, W.bqkv, qkv, cfg)
+    elif same:
         linear_fwd(xq, W.Wqkv, W.bqkv, qkv, cfg)
     else:
         for i, x in enumerate((xq, xk, xv)):
@@ -120,23 +143,23 @@ def rga_block_fwd(xq, xk, xv, W: LayerWeights, cfg: StackCfg, B: int, Lq: int, m
                        cfg, ldc=3 * d)
     q, k, v = qkv[:, 0:d], qkv[:, d:2 * d], qkv[:, 2 * d:3 * d]
     strides = (Lq * 3 * d, 3 * d, dh)          # (batch, position, head) in elements
-    O = _empty((T, d), cfg.act, xq)
+    O = _empty((T, d), cfg.act, like)          # (bf16 also in the f16-operand mode: the kernel packs O separately)
     ostrides = (Lq * d, d, dh)
-    lse = _empty((B, h, Lq), torch.float32, xq)
+    lse = _empty((B, h, Lq), torch.float32, like)
     causal = bool(mask.causal) if mask is not None else False
     pad = mask.pad_keys if mask is not None else None
-    ops.rga_fwd(q, k, v, strides, W.E, pad, O, ostrides, lse, B, h, Lq, dh, cfg.max_seq, causal,
+    ops.rga_fwd(q, k, v, strides, E, pad, O, ostrides, lse, B, h, Lq, dh, cfg.max_seq, causal,
                 path=cfg.attn_path)
     P = None
     if need_weights:
-        P = _empty((B, h, Lq, Lq), torch.float32, xq)
-        ops.rga_weights(q, k, strides, W.E, pad, lse, P, B, h, Lq, dh, cfg.max_seq, causal)
+        P = _empty((B, h, Lq, Lq), torch.float32, like)
+        ops.rga_weights(q, k, strides, E, pad, lse, P, B, h, Lq, dh, cfg.max_seq, causal)
     # sublayer output in the activation dtype (bf16 mode: what a bf16 nn.Linear returns; it is read twice more,
     # by the residual+LayerNorm forward and backward, so the narrower type saves 3 x T x d x 2 bytes per sublayer)
-    a = _empty((T, d), cfg.act, xq)
+    a = _empty((T, d), cfg.act, like)
     linear_fwd(O, W.Wfc, W.bfc, a, cfg)
     saved = dict(xq=xq, xk=xk, xv=xv, same=same, qkv=qkv, O=O, lse=lse, causal=causal, pad=pad,
-                 strides=strides, ostrides=ostrides, B=B, L=Lq)
+                 strides=strides, ostrides=ostrides, B=B, L=Lq, hp=hp, x_f32=x_f32 if hp else None)
     return a, saved, P
 
 
@@ -169,14 +192,18 @@ def rga_block_bwd(d_a, s, W: LayerWeights, cfg: StackCfg, g: Dict[str, torch.Ten
     delta = _empty((B, h, Lq), torch.float32, dev)
     g["E"] = _gbuf(dst, "E", (cfg.max_seq, dh), dev, zero=True)
     qkv = s["qkv"]
-    ops.rga_bwd(qkv[:, 0:d], qkv[:, d:2 * d], qkv[:, 2 * d:3 * d], s["strides"], W.E, s["pad"],
+    ops.rga_bwd(qkv[:, 0:d], qkv[:, d:2 * d], qkv[:, 2 * d:3 * d], s["strides"], W.E_hp if s["hp"] else W.E, s["pad"],
                 s["O"], dO, s["ostrides"], s["lse"], delta, dqkv[:, 0:d], dqkv[:, d:2 * d],
                 dqkv[:, 2 * d:3 * d], g["E"], B, h, Lq, dh, cfg.max_seq, s["causal"],
                 path=cfg.attn_path)
     g["Wqkv"] = _gbuf(dst, "Wqkv", (3 * d, d), dev)
     g["bqkv"] = _gbuf(dst, "bqkv", (3 * d,), dev)
     if s["same"]:
-        linear_wgrad(dqkv, s["xq"], g["Wqkv"], g["bqkv"], cfg)
+        xw = s["xq"]
+        if xw is None:              # f16-operand layer: the weight gradient takes a bf16 copy of the input (dqkv is bf16)
+            xw = _empty((T, d), cfg.act, dev)
+            ops.cast(s["x_f32"], xw)
+        linear_wgrad(dqkv, xw, g["Wqkv"], g["bqkv"], cfg)
         # dx = dx_addend + dqkv . Wqkv, accumulated IN PLACE into the residual-path gradient (its last
         # use): the GEMM epilogue then needs no addend read (red.global.add, see gemm_tc.cu)
         dx = dx_addend if dx_addend is not None else _empty((T, d), torch.float32, dev)
@@ -202,7 +229,16 @@ def layer_fwd(x_f32, x_lp, W: LayerWeights, cfg: StackCfg, B: int, Lq: int, mask
     T = B * Lq
     p = cfg.p_drop if training else 0.0
     lp = cfg.act != torch.float32
-    a, s_att, P = rga_block_fwd(x_lp, x_lp, x_lp, W, cfg, B, Lq, mask, need_weights)
+    if hp_eligible(W, cfg, mask):
+        # first layer, bf16 mode: f16 operands for the projection and the attention logits
+        if x_lp is not None and x_lp.dtype == torch.float16:
+            x_hp, x_b = x_lp, None
+        else:
+            x_hp, x_b = _empty((T, d), torch.float16, x_f32), x_lp
+            ops.cast(x_f32, x_hp)
+        a, s_att, P = rga_block_fwd(x_b, x_b, x_b, W, cfg, B, Lq, mask, need_weights, x_hp=x_hp, x_f32=x_f32)
+    else:
+        a, s_att, P = rga_block_fwd(x_lp, x_lp, x_lp, W, cfg, B, Lq, mask, need_weights)
     out1 = _empty((T, d), torch.float32, x_f32)
     out1_lp = _empty((T, d), cfg.act, x_f32) if lp else None
     mean1 = _empty((T,), torch.float32, x_f32)
@@ -275,7 +311,9 @@ def encoder_fwd(ids: torch.Tensor, emb: torch.Tensor, pe: torch.Tensor, Ws: List
     lp = cfg.act != torch.float32
     p = cfg.p_drop if training else 0.0
     x = _empty((T, d), torch.float32, emb)
-    x_lp = _empty((T, d), cfg.act, emb) if lp else None
+    # the first layer's 16-bit input copy is f16 when that layer runs its attention on f16 operands
+    lp0 = torch.float16 if (Ws and hp_eligible(Ws[0], cfg, mask)) else cfg.act
+    x_lp = _empty((T, d), lp0, emb) if lp else None
     ops.embed_pos_fwd(ids, emb, pe, x, x_lp, pos0, math.sqrt(d), p, seed, 0)
     xl = x_lp if lp else x
     saved_layers = []

@@ -210,9 +210,17 @@ def _as_f32_2d(x: torch.Tensor, d: int) -> torch.Tensor:
     return x2.contiguous()
 
 
-def _rga_weights_for(rga: RelativeGlobalAttention, act: torch.dtype, ffn=None, lns=None) -> LayerWeights:
-    """LayerWeights for one attention block (and, when given, the FFN / LayerNorm params)."""
+def hp_first_layer() -> bool:
+    """f16 operands for the first layer's attention in the bf16 mode (engine.py docstring); MT_B200_L0_F16=0
+    turns it off (A/B measurements of the all-bf16 arithmetic)."""
+    return os.environ.get("MT_B200_L0_F16", "1") != "0"
+
+
+def _rga_weights_for(rga: RelativeGlobalAttention, act: torch.dtype, ffn=None, lns=None, hp=False) -> LayerWeights:
+    """LayerWeights for one attention block (and, when given, the FFN / LayerNorm params).  ``hp``: also
+    the f16 copies of Wq/Wk/Wv and E (first layer of a stack in the bf16 mode)."""
     wqkv, bqkv = rga.packed()
+    hp = hp and act == torch.bfloat16 and hp_first_layer()
 
     def a(t):
         return _weight_copy(t.data, act)
@@ -225,7 +233,9 @@ def _rga_weights_for(rga: RelativeGlobalAttention, act: torch.dtype, ffn=None, l
         Wsuf=a(ffn[1].weight) if ffn else z, bsuf=ffn[1].bias.data if ffn else z,
         E=a(rga.E),
         g1=lns[0].weight.data if lns else z, b1=lns[0].bias.data if lns else z,
-        g2=lns[1].weight.data if lns else z, b2=lns[1].bias.data if lns else z)
+        g2=lns[1].weight.data if lns else z, b2=lns[1].bias.data if lns else z,
+        Wqkv_hp=_act_copy(wqkv, torch.float16) if hp else None,
+        E_hp=_act_copy(rga.E.data, torch.float16) if hp else None)
 
 
 class _RGAFunction(torch.autograd.Function):
@@ -283,6 +293,9 @@ class EncoderLayer(torch.nn.Module, _PrecisionMixin):
         self.dropout1 = torch.nn.Dropout(rate)
         self.dropout2 = torch.nn.Dropout(rate)
         self.precision = default_precision()
+        # True for the first layer of an Encoder: its input is the un-normalised embedding, so in the bf16
+        # mode its attention runs on f16 operands (engine.py); a standalone layer keeps plain bf16
+        self.hp_attention = False
 
     def params(self) -> List[torch.nn.Parameter]:
         return self.rga.params() + [self.FFN_pre.weight, self.FFN_pre.bias, self.FFN_suf.weight,
@@ -296,7 +309,7 @@ class EncoderLayer(torch.nn.Module, _PrecisionMixin):
 
     def weights(self, act) -> LayerWeights:
         return _rga_weights_for(self.rga, act, ffn=(self.FFN_pre, self.FFN_suf),
-                                lns=(self.layernorm1, self.layernorm2))
+                                lns=(self.layernorm1, self.layernorm2), hp=self.hp_attention)
 
     def forward(self, x, mask=None, **kwargs):
         B, Lq, _ = x.shape
@@ -405,6 +418,8 @@ class Encoder(torch.nn.Module, _PrecisionMixin):
         self.dropout = torch.nn.Dropout(rate)
         self.max_len = max_len
         self.precision = default_precision()
+        if num_layers > 0:
+            self.enc_layers[0].hp_attention = True
 
     def params(self) -> List[torch.nn.Parameter]:
         ps = [self.embedding.weight]

@@ -78,11 +78,14 @@ class MusicTransformer(torch.nn.Module, _PrecisionMixin):
     def generate(self, prior: torch.Tensor, length=2048, tf_board_writer=None,
                  temperature: Optional[float] = None, top_k: Optional[int] = None,
                  greedy: Optional[bool] = None, uniforms: Optional[torch.Tensor] = None,
-                 return_logits: bool = False):
+                 return_logits: bool = False, graph: Optional[bool] = None):
         """prior [B, P] int -> [B, P+length] int64.  Causal KV-cached decode (the mask the
         reference builds at MT/network.py:55-56 and drops IS applied); needs P+length-1 <=
         max_seq (no sliding window -- see generate_literal for the reference's literal loop).
-        ``uniforms`` [length, B] fixes the random draws (tests); default torch.rand."""
+        ``uniforms`` [length, B] fixes the random draws (tests); default torch.rand.
+        ``return_logits``: also the last-position logits of every generated event [length, B, V].
+        ``graph``: replay one captured CUDA graph per event (default unless return_logits) or launch
+        every step from the host."""
         if not prior.is_cuda:
             raise RuntimeError("musicgeneration_b200 runs on CUDA tensors only (no CPU fallback)")
         temperature = self.temperature if temperature is None else temperature
@@ -95,7 +98,9 @@ class MusicTransformer(torch.nn.Module, _PrecisionMixin):
         dec = _DecodeSession(self, B)
         ids = torch.zeros((B, P + length), dtype=torch.int32, device=prior.device)
         ids[:, :P] = prior.to(torch.int32)
-        if not return_logits and P + length - 1 >= 4:
+        if graph is None:
+            graph = not return_logits
+        if graph and P + length - 1 >= 4:
             # one CUDA graph of a whole decode step (device-resident step index), replayed per event
             if greedy:
                 u = None
@@ -103,8 +108,10 @@ class MusicTransformer(torch.nn.Module, _PrecisionMixin):
                 u = uniforms[:length].to(torch.float32).contiguous()
             else:
                 u = torch.rand((length, B), dtype=torch.float32, device=prior.device)
-            dec.run_graph(ids, P, P + length - 1, u, float(temperature), int(top_k), bool(greedy))
-            return ids.to(torch.int64)
+            rec = torch.empty((P + length - 1, B, self.vocab_size), dtype=torch.float32, device=prior.device) \
+                if return_logits else None
+            dec.run_graph(ids, P, P + length - 1, u, float(temperature), int(top_k), bool(greedy), logits_out=rec)
+            return (ids.to(torch.int64), rec[P - 1:]) if return_logits else ids.to(torch.int64)
         step_logits = []
         logits = None
         for t in range(P + length - 1):
@@ -121,6 +128,23 @@ class MusicTransformer(torch.nn.Module, _PrecisionMixin):
                     step_logits.append(logits.clone())
         out = ids.to(torch.int64)
         return (out, torch.stack(step_logits)) if return_logits else out
+
+    @torch.no_grad()
+    def decode_logits(self, ids: torch.Tensor) -> torch.Tensor:
+        """Teacher-forced KV-cached pass over given ids [B, n] on the decode path (one graph replay per
+        position): logits [n, B, V], entry t = the distribution of token t+1 given ids[:, :t+1] under the
+        causal mask.  The same launches ``generate`` replays; used to score sequences and by the parity tests."""
+        if not ids.is_cuda:
+            raise RuntimeError("musicgeneration_b200 runs on CUDA tensors only (no CPU fallback)")
+        B, n = ids.shape
+        if n > self.max_seq:
+            raise RuntimeError(f"sequence length {n} exceeds max_seq {self.max_seq}")
+        dec = _DecodeSession(self, B)
+        buf = torch.zeros((B, n + 1), dtype=torch.int32, device=ids.device)
+        buf[:, :n] = ids.to(torch.int32)
+        rec = torch.empty((n, B, self.vocab_size), dtype=torch.float32, device=ids.device)
+        dec.run_graph(buf, n + 1, n, None, 1.0, 0, True, logits_out=rec)      # prior_len n+1: nothing is sampled
+        return rec
 
     @torch.no_grad()
     def generate_literal(self, prior: torch.Tensor, length=2048, greedy=True,
@@ -178,8 +202,14 @@ class _DecodeSession:
         self.bv = model.fc.bias.data
         self.V = model.fc.weight.shape[0]
         shape = (B, cfg.h, cfg.max_seq, cfg.dh)
-        self.kc = [torch.zeros(shape, dtype=cfg.act, device=dev) for _ in self.Ws]
-        self.vc = [torch.zeros(shape, dtype=cfg.act, device=dev) for _ in self.Ws]
+        # per-layer 16-bit type: the first layer's attention block runs on f16 operands in the bf16 mode
+        # (engine.py docstring) -- here x, Wqkv, q/k/v, the KV cache, E, the attention output and Wfc
+        self.lact = [cfg.act] * len(self.Ws)
+        if self.Ws and self.Ws[0].Wqkv_hp is not None and cfg.dh == 64 and cfg.gemm_path != L.PATH_SIMT:
+            self.lact[0] = torch.float16
+            self.Ws[0].Wfc_hp = _act_copy(enc.enc_layers[0].rga.fc.weight.data, torch.float16)
+        self.kc = [torch.zeros(shape, dtype=a, device=dev) for a in self.lact]
+        self.vc = [torch.zeros(shape, dtype=a, device=dev) for a in self.lact]
         # pad bit per cached position: a generated/prior pad token is masked as a key, exactly as
         # the look-ahead mask of MT/utils.py:73 does in the reference's recompute
         self.pad_bits = torch.zeros((B, cfg.max_seq), dtype=torch.uint8, device=dev)
@@ -195,7 +225,11 @@ class _DecodeSession:
         nl = len(self.Ws)
         self.g_x = [f32(B, d) for _ in range(nl + 1)]
         self.g_xlp = [act(B, d) if lp else None for _ in range(nl + 1)]
-        self.g_qkv, self.g_o, self.g_a = act(B, 3 * d), act(B, d), f32(B, d)
+        if lp and nl:
+            self.g_xlp[0] = torch.empty((B, d), dtype=self.lact[0], device=dev)
+        self.g_qkv = {a: torch.empty((B, 3 * d), dtype=a, device=dev) for a in set(self.lact)}
+        self.g_o = {a: torch.empty((B, d), dtype=a, device=dev) for a in set(self.lact)}
+        self.g_a = f32(B, d)
         self.g_out1, self.g_out1lp = f32(B, d), (act(B, d) if lp else None)
         self.g_hmid, self.g_f = act(B, d // 2), f32(B, d)
         self.g_mean, self.g_rstd = f32(B), f32(B)
@@ -213,10 +247,12 @@ class _DecodeSession:
                          config.pad_token, self.pad_bits)
         for li, W in enumerate(self.Ws):
             x, xl = self.g_x[li], (self.g_xlp[li] if lp else self.g_x[li])
-            engine.linear_fwd(xl, W.Wqkv, W.bqkv, self.g_qkv, cfg)
-            ops.decode_attend(self.g_qkv, 3 * d, self.kc[li], self.vc[li], W.E, self.pad_bits, self.g_o,
+            hp = self.lact[li] != cfg.act
+            g_qkv, g_o = self.g_qkv[self.lact[li]], self.g_o[self.lact[li]]
+            engine.linear_fwd(xl, W.Wqkv_hp if hp else W.Wqkv, W.bqkv, g_qkv, cfg)
+            ops.decode_attend(g_qkv, 3 * d, self.kc[li], self.vc[li], W.E_hp if hp else W.E, self.pad_bits, g_o,
                               self.t_dev, B, h, dh, cfg.max_seq, self.g_ws, append=True)
-            engine.linear_fwd(self.g_o, W.Wfc, W.bfc, self.g_a, cfg)
+            engine.linear_fwd(g_o, W.Wfc_hp if hp else W.Wfc, W.bfc, self.g_a, cfg)
             ops.add_ln_fwd(self.g_a, x, W.g1, W.b1, self.g_out1, self.g_out1lp, self.g_mean, self.g_rstd,
                            1e-6, 0.0, 0, 0)
             o1 = self.g_out1lp if lp else self.g_out1
@@ -229,8 +265,9 @@ class _DecodeSession:
         ops.decode_sample(self.g_logits, u, ids, self.t_dev, prior_len, temperature, top_k, greedy)
         ops.decode_advance(self.t_dev)
 
-    def run_graph(self, ids, prior_len, n_steps, u, temperature, top_k, greedy):
-        """Positions 0 .. n_steps-1 of ``ids`` [B, >= n_steps+1] (prior tokens kept, later ones sampled)."""
+    def run_graph(self, ids, prior_len, n_steps, u, temperature, top_k, greedy, logits_out=None):
+        """Positions 0 .. n_steps-1 of ``ids`` [B, >= n_steps+1] (prior tokens kept, later ones sampled).
+        ``logits_out`` [n_steps, B, V]: receives the step's logits after every replay."""
         self._alloc_step_buffers()
         args = (ids, prior_len, u, temperature, top_k, greedy)
         side = torch.cuda.Stream()
@@ -248,8 +285,10 @@ class _DecodeSession:
             finally:
                 ops.decode_chain(False)
         self.t_dev.zero_()
-        for _ in range(n_steps):
+        for t in range(n_steps):
             graph.replay()
+            if logits_out is not None:
+                logits_out[t].copy_(self.g_logits)
 
     def step(self, tok: torch.Tensor, t: int) -> torch.Tensor:
         """tok int32 [B] at position t -> logits fp32 [B, V] for position t+1."""
@@ -260,17 +299,20 @@ class _DecodeSession:
         ids = tok.reshape(B, 1).contiguous()
         self.pad_bits[:, t] = (tok == config.pad_token)
         x = torch.empty((B, d), dtype=torch.float32, device=dev)
-        x_lp = torch.empty((B, d), dtype=cfg.act, device=dev) if lp else None
+        x_lp = torch.empty((B, d), dtype=self.lact[0] if self.lact else cfg.act, device=dev) if lp else None
         ops.embed_pos_fwd(ids, self.emb, self.pe, x, x_lp, t, math.sqrt(d), 0.0, 0, 0)
         xl = x_lp if lp else x
         for li, W in enumerate(self.Ws):
-            qkv = torch.empty((B, 3 * d), dtype=cfg.act, device=dev)
-            engine.linear_fwd(xl, W.Wqkv, W.bqkv, qkv, cfg)
+            la = self.lact[li]
+            hp = la != cfg.act
+            qkv = torch.empty((B, 3 * d), dtype=la, device=dev)
+            engine.linear_fwd(xl, W.Wqkv_hp if hp else W.Wqkv, W.bqkv, qkv, cfg)
             ops.kv_append(qkv, self.kc[li], self.vc[li], B, h, dh, cfg.max_seq, t)
-            o = torch.empty((B, d), dtype=cfg.act, device=dev)
-            ops.rga_decode(qkv, 3 * d, self.kc[li], self.vc[li], W.E, self.pad_bits, o, B, h, dh, cfg.max_seq, t)
+            o = torch.empty((B, d), dtype=la, device=dev)
+            ops.rga_decode(qkv, 3 * d, self.kc[li], self.vc[li], W.E_hp if hp else W.E, self.pad_bits, o, B, h, dh,
+                           cfg.max_seq, t)
             a = torch.empty((B, d), dtype=torch.float32, device=dev)
-            engine.linear_fwd(o, W.Wfc, W.bfc, a, cfg)
+            engine.linear_fwd(o, W.Wfc_hp if hp else W.Wfc, W.bfc, a, cfg)
             out1 = torch.empty((B, d), dtype=torch.float32, device=dev)
             out1_lp = torch.empty((B, d), dtype=cfg.act, device=dev) if lp else None
             mean = torch.empty((B,), dtype=torch.float32, device=dev)

@@ -165,6 +165,18 @@ def transpose_cast(src, dst, rows, cols):
             "transpose_cast")
 
 
+def _rga_dtype(q, E, other) -> int:
+    """dtype code of an attention call: the tensors' common type, or MT_F16_BF16 for the mixed mode of the
+    first encoder layer (f16 q/k/v/E, bf16 everything else)."""
+    if E.dtype != q.dtype:
+        raise RuntimeError(f"rga: q/k/v are {q.dtype} but E is {E.dtype}")
+    if q.dtype == torch.float16 and other.dtype == torch.bfloat16:
+        return L.MT_F16_BF16
+    if other.dtype != q.dtype:
+        raise RuntimeError(f"rga: unsupported dtype combination q {q.dtype} / out {other.dtype}")
+    return dt(q)
+
+
 def rga_fwd(q, k, v, strides, E, pad_keys, O, ostrides, lse, B, h, Lq, dh, max_seq, causal,
             path=L.PATH_AUTO):
     _need_cuda(q, k, v, E, O, lse)
@@ -172,7 +184,7 @@ def rga_fwd(q, k, v, strides, E, pad_keys, O, ostrides, lse, B, h, Lq, dh, max_s
     ob, ol, oh = ostrides
     L.check(L.load().mt_rga_fwd(_ptr(q), _ptr(k), _ptr(v), sb, sl, sh, _ptr(E), _ptr(pad_keys),
                                 _ptr(O), ob, ol, oh, _ptr(lse), B, h, Lq, dh, max_seq, int(causal),
-                                dt(q), path, _stream()), "rga_fwd")
+                                _rga_dtype(q, E, O), path, _stream()), "rga_fwd")
 
 
 def rga_weights(q, k, strides, E, pad_keys, lse, P, B, h, Lq, dh, max_seq, causal):
@@ -186,10 +198,10 @@ def rga_weights(q, k, strides, E, pad_keys, lse, P, B, h, Lq, dh, max_seq, causa
 _RGA_WS = {}     # device index -> uint8 scratch shared by every layer's attention backward (one stream)
 
 
-def rga_bwd_workspace(q, B, h, Lq, dh):
+def rga_bwd_workspace(q, B, h, Lq, dh, code=None):
     """Scratch for the dS-spill variant of the tcgen05 backward (grow-only, one per device); None when
     that variant does not take the problem."""
-    need = L.load().mt_rga_bwd_workspace_bytes(B, h, Lq, dh, dt(q))
+    need = L.load().mt_rga_bwd_workspace_bytes(B, h, Lq, dh, dt(q) if code is None else code)
     if need == 0:
         return None
     key = q.device.index
@@ -206,11 +218,12 @@ def rga_bwd(q, k, v, strides, E, pad_keys, O, dO, ostrides, lse, delta, dq, dk, 
     _need_cuda(q, k, v, E, O, dO, lse, delta, dq, dk, dv, dE)
     sb, sl, sh = strides
     ob, ol, oh = ostrides
-    ws = rga_bwd_workspace(q, B, h, Lq, dh) if (spill and path != L.PATH_SIMT) else None
+    code = _rga_dtype(q, E, dq)
+    ws = rga_bwd_workspace(q, B, h, Lq, dh, code) if (spill and path != L.PATH_SIMT) else None
     L.check(L.load().mt_rga_bwd_ws(_ptr(q), _ptr(k), _ptr(v), sb, sl, sh, _ptr(E), _ptr(pad_keys),
                                    _ptr(O), _ptr(dO), ob, ol, oh, _ptr(lse), _ptr(delta), _ptr(dq),
                                    _ptr(dk), _ptr(dv), _ptr(dE), B, h, Lq, dh, max_seq, int(causal),
-                                   dt(q), path, _ptr(ws), ws.numel() if ws is not None else 0, _stream()),
+                                   code, path, _ptr(ws), ws.numel() if ws is not None else 0, _stream()),
             "rga_bwd")
 
 

@@ -133,9 +133,22 @@ def golden_decode(R):
             nxt = res[:, -1].argmax(-1).to(da.dtype)
             da = torch.cat((da, nxt.unsqueeze(-1)), -1)
             ra = torch.cat((ra, nxt.unsqueeze(-1)), -1)
+    # (3) causal again, pad tokens INSIDE the prior (never leading: SURVEY 0.7): they are masked as keys for
+    # every later position (MT/utils.py:73), which the KV-cached path reproduces with its pad bits
+    prior_pad = torch.tensor([[24, pad, 31, 7], [5, 9, pad, pad], [60, 1, 2, 3]], dtype=torch.long)
+    decp = prior_pad.clone()
+    zps = []
+    with torch.no_grad():
+        for _ in range(steps):
+            _, _, mask = R.utils.get_masked_with_pad_tensor(decp.size(1), decp, decp, pad)
+            hid, _ = m.Decoder(decp, mask)
+            z = m.fc(hid)[:, -1]
+            zps.append(z.numpy())
+            decp = torch.cat((decp, z.argmax(-1, keepdim=True)), -1)
     np.savez(os.path.join(OUT, "decode_small.npz"),
              meta=np.array([d, V, pad, layers, max_seq, steps, thr]), prior=prior.numpy(),
              causal_ids=dec.numpy(), causal_logits=np.stack(zs), literal_ids=ra.numpy(),
+             prior_pad=prior_pad.numpy(), causal_ids_pad=decp.numpy(), causal_logits_pad=np.stack(zps),
              **sd_np(m.state_dict()))
     print("decode_small: causal tail", dec[0, -6:].tolist(), "literal tail", ra[0, -6:].tolist())
 
@@ -171,6 +184,50 @@ def golden_config_a(R):
              logits_slice=logits[:, ::256, ::39].numpy(),
              logits_norm=np.array(float(logits.norm())))
     print("config A loss", float(loss))
+
+
+def golden_config_b(R):
+    """The BENCHMARKED model (config B: V=390/pad 388, 6L, d512, h=8, L=2048; seed-0 init, which the drop-in
+    module reproduces bit for bit under the same torch seed) on 2 sequences, fp32, unmodified reference:
+    loss, every 16th logits row, the gradients of every 1-D parameter and of a slice of each layer's E --
+    what the bf16 mode is held to at the shape every bench number is quoted on.  Second part: causal greedy
+    decode of 256 events from two 8-token priors (one with a pad token inside the prior), ids + step logits."""
+    pad = 388
+    R.config.pad_token = pad
+    torch.manual_seed(0)
+    m = R.network.MusicTransformer(embedding_dim=512, vocab_size=390, num_layer=6, max_seq=2048, dropout=0.0)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randint(0, pad, (2, 2048), generator=g, dtype=torch.int32)
+    y = torch.randint(0, pad, (2, 2048), generator=g, dtype=torch.int32)
+    m.train()
+    logits = m(x)
+    loss = R.criterion.SmoothCrossEntropyLoss(0.1, 390, pad)(logits, y)
+    loss.backward()
+    out = {"loss": loss.detach().numpy(), "logits_rows": logits[:, ::16, :].detach().numpy(),
+           "logits_norm": np.array(float(logits.norm()))}
+    for k, p in m.named_parameters():
+        gnp = p.grad.detach().numpy()
+        out["gn:" + k] = np.array(float(np.linalg.norm(gnp)))
+        if gnp.ndim == 1:
+            out["g:" + k] = gnp
+        elif k.endswith("rga.E"):
+            out["g:" + k] = gnp[::8]
+    print("config B loss", float(loss))
+    m.eval()
+    prior = torch.tensor([[24, 28, 31, 60, 5, 9, 77, 1], [200, 3, 150, pad, 42, 7, 300, 11]], dtype=torch.long)
+    steps = 256
+    dec = prior.clone()
+    zs = []
+    with torch.no_grad():
+        for _ in range(steps):
+            _, _, mask = R.utils.get_masked_with_pad_tensor(dec.size(1), dec, dec, pad)
+            hid, _ = m.Decoder(dec, mask)
+            z = m.fc(hid)[:, -1]
+            zs.append(z.numpy())
+            dec = torch.cat((dec, z.argmax(-1, keepdim=True)), -1)
+    out.update(prior=prior.numpy(), causal_ids=dec.numpy(), causal_logits=np.stack(zs))
+    np.savez_compressed(os.path.join(OUT, "config_b_summary.npz"), **out)
+    print("config B decode tail", dec[0, -6:].tolist(), dec[1, -6:].tolist())
 
 
 def data_feed_script(D, record):
@@ -266,6 +323,12 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     R = load_reference()
+    if "--only-config-b" in sys.argv:
+        golden_config_b(R)
+        sys.exit(0)
+    if "--only-decode" in sys.argv:
+        golden_decode(R)
+        sys.exit(0)
     if "--data-only" in sys.argv:
         golden_data(R)
         golden_notes(R)
@@ -278,3 +341,5 @@ if __name__ == "__main__":
     golden_misc(R)
     if "--config-a" in sys.argv:
         golden_config_a(R)
+    if "--config-b" in sys.argv:
+        golden_config_b(R)

@@ -148,14 +148,11 @@ def test_train_small_bf16_within_tolerance():
     for k, p in m.named_parameters():
         g = torch.from_numpy(z["g:" + k])
         worst[k] = float((p.grad.cpu() - g).norm()) / max(float(g.norm()), 1e-2 * scale)
-    # layer 0 sees the un-normalised embedding (|logit| ~ 1e2..1e3, near one-hot softmax), so bf16
-    # rounding of its q/k moves its attention gradients far more than any other tensor's
-    # (SURVEY 0.9); everything downstream of the first LayerNorm is held to 5e-2.
-    def lim(k):
-        # (ReLU gates decided on bf16-rounded pre-activations flip for ~0.5% of the hidden units,
-        # which alone moves the FFN_pre gradients by several percent at this tiny width)
-        return 0.3 if ("enc_layers.0.rga" in k or "embedding" in k) else 0.1
-    bad = {k: v for k, v in worst.items() if v >= lim(k)}
+    # layer 0 sees the un-normalised embedding (|logit| ~ 1e2..1e3, near one-hot softmax): with bf16 q / k its
+    # attention gradients were ~15-30 % off; its q / k / v / E operands are f16 now (engine.py), and every
+    # gradient is held to the same 5e-2
+    print("bf16 gradient errors (small fixture):", {k: round(v, 4) for k, v in sorted(worst.items(), key=lambda kv: -kv[1])[:6]})
+    bad = {k: v for k, v in worst.items() if v >= 5e-2}
     assert not bad, bad
 
 
@@ -177,11 +174,38 @@ def test_decode_small_greedy_ids_bit_exact():
     finally:
         mtb.config.threshold_len = 500
     assert (lit.cpu().numpy() == z["literal_ids"]).all()
+    # the CUDA-graph path (what generate() and bench.py run): all 40 steps bit-exact, step logits recorded
+    ids_g, logits_g = m.generate(prior, length=steps, greedy=True, return_logits=True, graph=True)
+    assert (ids_g.cpu().numpy() == z["causal_ids"]).all()
+    assert float((logits_g.cpu() - torch.from_numpy(z["causal_logits"])).abs().max()) < 5e-5
+    assert (m.generate(prior, length=steps, greedy=True).cpu().numpy() == z["causal_ids"]).all()
     # infer-mode forward returns a python list of lists (MT/network.py:42)
     m.test()
     m.greedy = True
     out = m(prior, 5)
     assert isinstance(out, list) and out == z["causal_ids"][:, :prior.shape[1] + 5].tolist()
+
+
+def test_decode_pad_tokens_inside_the_prior_match_reference():
+    """Pad tokens in the prior (and a generated pad token) are masked as keys for every later position
+    (MT/utils.py:73); fixture from the unmodified reference's causal recompute.  Graph and host-stepped paths."""
+    dev = torch.device("cuda:0")
+    z = load("decode_small.npz")
+    d, V, pad, layers, max_seq, steps, thr = z["meta"].tolist()
+    m, _ = build_model(z, dev)
+    m.eval()
+    prior = torch.from_numpy(z["prior_pad"]).to(dev)
+    assert (z["prior_pad"] == pad).any() and (z["causal_ids_pad"][:, prior.shape[1]:] == pad).any()
+    ids, step_logits = m.generate(prior, length=steps, greedy=True, return_logits=True)
+    assert (ids.cpu().numpy() == z["causal_ids_pad"]).all()
+    assert float((step_logits.cpu() - torch.from_numpy(z["causal_logits_pad"])).abs().max()) < 5e-5
+    ids_g, logits_g = m.generate(prior, length=steps, greedy=True, return_logits=True, graph=True)
+    assert (ids_g.cpu().numpy() == z["causal_ids_pad"]).all()
+    assert float((logits_g.cpu() - torch.from_numpy(z["causal_logits_pad"])).abs().max()) < 5e-5
+    # teacher-forced scoring pass over the reference's ids: same logits at every generated position
+    tf = m.decode_logits(torch.from_numpy(z["causal_ids_pad"][:, :-1]).to(dev))
+    P = prior.shape[1]
+    assert float((tf[P - 1:].cpu() - torch.from_numpy(z["causal_logits_pad"])).abs().max()) < 5e-5
 
 
 def test_decode_sampling_matches_oracle_given_uniforms():
@@ -229,12 +253,136 @@ def test_config_a_fp32_against_oracle():
     assert abs(float(loss) - float(ref_loss)) < 1e-5 * float(ref_loss)
     loss.backward()
     assert all(torch.isfinite(q.grad).all() for q in m.parameters())
-    # bf16 mode on the same weights: north-star tolerance 1e-2 relative
+    # bf16 mode on the same weights: north-star tolerance 1e-2 relative, logits AND loss
     m.set_precision("bf16")
     lb = m(x.to(dev))
     lossb = mtb.SmoothCrossEntropyLoss(0.1, V, pad)(lb, y.to(dev))
-    print("config A bf16 logits rel err", rel(lb.detach().cpu(), ref), "loss", float(lossb), float(ref_loss))
+    err = rel(lb.detach().cpu(), ref)
+    print("config A bf16 logits rel err", err, "loss", float(lossb), float(ref_loss))
+    assert err < 1e-2
     assert abs(float(lossb) - float(ref_loss)) < 1e-2 * float(ref_loss)
+
+
+def test_config_a_against_reference_summary():
+    """The same shape pinned to the UNMODIFIED reference: torch.manual_seed(0) gives the drop-in module the
+    reference's own initial weights bit for bit (same constructors in the same order), so the loss and the
+    logits slice that oracle/make_golden.py recorded from the reference apply directly."""
+    import musicgeneration_b200 as mtb
+    dev = torch.device("cuda:0")
+    z = load("config_a_summary.npz")
+    mtb.config.pad_token = 388
+    torch.manual_seed(0)
+    m = mtb.MusicTransformer(embedding_dim=256, vocab_size=390, num_layer=6, max_seq=2048, dropout=0.0).to(dev)
+    x, y = O.synthetic_ids(2, 2048, 388)
+    m.train()
+    crit = mtb.SmoothCrossEntropyLoss(0.1, 390, 388)
+    for prec, tol in (("fp32", 1e-5), ("bf16", 1e-2)):
+        m.set_precision(prec)
+        with torch.no_grad():
+            logits = m(x.to(dev))
+            loss = float(crit(logits, y.to(dev)))
+        e = rel(logits[:, ::256, ::39].cpu(), torch.from_numpy(z["logits_slice"]))
+        print(f"config A {prec}: loss {loss:.6f} (reference {float(z['loss']):.6f}), logits slice rel {e:.2e}, "
+              f"norm {float(logits.norm()):.3f} (reference {float(z['logits_norm']):.3f})")
+        assert abs(loss - float(z["loss"])) < tol * float(z["loss"])
+        assert e < tol
+        assert abs(float(logits.norm()) - float(z["logits_norm"])) < tol * float(z["logits_norm"])
+
+
+def _config_b_model(dev, precision):
+    import musicgeneration_b200 as mtb
+    mtb.config.pad_token = 388
+    torch.manual_seed(0)
+    return mtb.MusicTransformer(embedding_dim=512, vocab_size=390, num_layer=6, max_seq=2048, dropout=0.0,
+                                precision=precision).to(dev)
+
+
+def test_config_b_bf16_against_reference_summary(monkeypatch):
+    """The benchmarked model (config B: 6L / d512 / h8 / L=2048, seed-0 init = the reference's own init) in the
+    benchmarked precision against numbers recorded from the unmodified reference (oracle/make_golden.py
+    --config-b): logits and loss within the north-star 1e-2, gradients within 5e-2 of each tensor's norm."""
+    import musicgeneration_b200 as mtb
+    dev = torch.device("cuda:0")
+    z = load("config_b_summary.npz")
+    x, y = O.synthetic_ids(2, 2048, 388)
+    crit = mtb.SmoothCrossEntropyLoss(0.1, 390, 388)
+    ref_rows = torch.from_numpy(z["logits_rows"])
+    m = _config_b_model(dev, "bf16")
+    m.train()
+    logits = m(x.to(dev))
+    loss = crit(logits, y.to(dev))
+    e = rel(logits[:, ::16, :].detach().cpu(), ref_rows)
+    print(f"config B bf16: logits rel {e:.3e}, loss {float(loss):.6f} vs reference {float(z['loss']):.6f}")
+    assert e < 1e-2
+    assert abs(float(loss) - float(z["loss"])) < 1e-2 * float(z["loss"])
+    loss.backward()
+    worst = {}
+    for k, p in m.named_parameters():
+        if "g:" + k not in z:
+            continue
+        g = torch.from_numpy(z["g:" + k])
+        ours = p.grad.detach().cpu()
+        if k.endswith("rga.E"):
+            ours = ours[::8]
+        # Wk.bias has a mathematically zero gradient: measure against the layer's Wq.bias gradient norm there
+        scale = max(float(z["gn:" + k]) * (g.numel() / p.numel()) ** 0.5,
+                    1e-2 * float(z["gn:" + k.replace("Wk.bias", "Wq.bias")]))
+        worst[k] = float((ours - g).norm()) / scale
+    top = sorted(worst.items(), key=lambda kv: -kv[1])[:8]
+    print("config B bf16 gradient errors (worst):", {k: round(v, 4) for k, v in top})
+    assert max(worst.values()) < 5e-2, top
+    # the same forward with every operand bf16 (the round-1 arithmetic): measured for DESIGN.md, and the reason
+    # the first layer's attention operands are f16
+    monkeypatch.setenv("MT_B200_L0_F16", "0")
+    with torch.no_grad():
+        e_bf = rel(m(x.to(dev))[:, ::16, :].cpu(), ref_rows)
+    print(f"config B, all operands bf16: logits rel {e_bf:.3e}")
+    assert e < e_bf
+
+
+def test_config_b_fp32_against_reference_summary():
+    import musicgeneration_b200 as mtb
+    dev = torch.device("cuda:0")
+    z = load("config_b_summary.npz")
+    x, y = O.synthetic_ids(2, 2048, 388)
+    m = _config_b_model(dev, "fp32")
+    m.train()
+    with torch.no_grad():
+        logits = m(x.to(dev))
+        loss = float(mtb.SmoothCrossEntropyLoss(0.1, 390, 388)(logits, y.to(dev)))
+    e = rel(logits[:, ::16, :].cpu(), torch.from_numpy(z["logits_rows"]))
+    print(f"config B fp32: logits rel {e:.3e}, loss {loss:.6f} vs {float(z['loss']):.6f}")
+    assert e < 1e-5 and abs(loss - float(z["loss"])) < 1e-5 * float(z["loss"])
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_config_b_decode_graph_path_against_reference(precision):
+    """KV-cached decode of the benchmarked model on the CUDA-graph path bench.py times, 256 events from two
+    8-token priors (one with a pad token inside), against the unmodified reference's causal recompute:
+    teacher-forced step logits (bf16: 1e-2 relative over all steps, fp32: 1e-5), arg-max agreement with the
+    reference's greedy ids, and the free-running greedy ids (fp32: bit-exact; bf16: agreement rate)."""
+    dev = torch.device("cuda:0")
+    z = load("config_b_summary.npz")
+    m = _config_b_model(dev, precision)
+    m.eval()
+    prior = torch.from_numpy(z["prior"]).to(dev)
+    ref_ids = torch.from_numpy(z["causal_ids"])
+    ref_logits = torch.from_numpy(z["causal_logits"])          # [256, 2, V]
+    P, steps = prior.shape[1], ref_logits.shape[0]
+    tf = m.decode_logits(ref_ids[:, :-1].to(dev))[P - 1:].cpu()
+    e = rel(tf, ref_logits)
+    per_step = ((tf - ref_logits).flatten(1).norm(dim=1) / ref_logits.flatten(1).norm(dim=1)).max()
+    agree = float((tf.argmax(-1).t() == ref_ids[:, P:]).float().mean())
+    ids = m.generate(prior, length=steps, greedy=True).cpu()
+    same = (ids == ref_ids)
+    first_div = [int((~same[b]).nonzero()[0]) if (~same[b]).any() else ids.shape[1] for b in range(ids.shape[0])]
+    print(f"config B decode {precision}: teacher-forced logits rel {e:.3e} (worst step {float(per_step):.3e}), "
+          f"arg-max agreement {agree:.4f}, free-running first divergence at {first_div} of {ids.shape[1]}")
+    if precision == "fp32":
+        assert e < 1e-5 and bool(same.all())
+    else:
+        assert e < 1e-2 and float(per_step) < 3e-2
+        assert agree >= 0.97
 
 
 def test_causality_and_batch_independence_property():

@@ -317,6 +317,23 @@ def test_gemm_tc(dev, M, N, K, tA, tB):
     assert rel(C4.cpu(), ref + bias.double()) < 2e-6
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 1536, 512), (300, 392, 200)])
+def test_gemm_tc_f16_operands_and_output(dev, M, N, K):
+    """f16 x f16 -> f16 (+bias): the first encoder layer's QKV projection in the bf16 mode."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 8).to(torch.float16)
+    W = torch.randn(N, K, generator=g).to(torch.float16) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    ref = A.double() @ W.double().t() + bias.double()
+    C = torch.zeros((M, N), dtype=torch.float16, device=dev)
+    ops.gemm(A.to(dev), W.to(dev), C, M, N, K, K, K, N, False, True, bias=bias.to(dev), path=2)
+    assert rel(C.float().cpu(), ref) < 6e-4            # 11-bit output rounding
+    C32 = torch.zeros((M, N), dtype=torch.float32, device=dev)
+    ops.gemm(A.to(dev), W.to(dev), C32, M, N, K, K, K, N, False, True, bias=bias.to(dev), path=2)
+    assert rel(C32.cpu(), ref) < 2e-6
+
+
 def test_gemm_tc_split_k_weight_gradient_shape(dev):
     ops = _ops()
     g = torch.Generator().manual_seed(5)
@@ -353,6 +370,21 @@ def test_gemm_skinny_decode_shapes(dev, M, N, K, out_bf16):
     C2 = torch.empty((M, N), dtype=odt, device=dev)
     ops.gemm(Ad, Wd, C2, M, N, K, K, K, N, False, True, bias=bias.to(dev), relu=True)
     assert rel(C2.float().cpu(), torch.relu(ref)) < (4e-3 if out_bf16 else 2e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K,odt", [(32, 1536, 512, torch.float16), (32, 512, 512, torch.float32), (3, 768, 256, torch.float16)])
+def test_gemm_skinny_f16(dev, M, N, K, odt):
+    """f16 operands (and output) of the decode step's first layer."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(M * 7 + N + K)
+    A = (torch.randn(M, K, generator=g) * 8).to(torch.float16)
+    W = torch.randn(N, K, generator=g).to(torch.float16) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    ref = A.double() @ W.double().t() + bias.double()
+    C = torch.full((M, N), 7.0, dtype=odt, device=dev)
+    ops.gemm(A.to(dev), W.to(dev), C, M, N, K, K, K, N, False, True, bias=bias.to(dev))
+    assert rel(C.float().cpu(), ref) < (6e-4 if odt == torch.float16 else 2e-6)
 
 
 @pytest.mark.gpu

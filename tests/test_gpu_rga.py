@@ -18,14 +18,16 @@ def rel(a, b):
     return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
 
 
-def run_case(B, h, L, dh, max_seq, causal, pad, dtype, path, seed=0, scale=1.0, spill=True):
+def run_case(B, h, L, dh, max_seq, causal, pad, dtype, path, seed=0, scale=1.0, spill=True, io_dtype=None):
+    """io_dtype: type of O / dO / dq / dk / dv when it differs from the q / k / v / E type (the mixed mode)."""
     from musicgeneration_b200 import ops
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(seed)
     d = h * dh
     qkv = (torch.randn(B, L, 3, h, dh, generator=g) * scale).to(dtype)
     E = torch.randn(max_seq, dh, generator=g).to(dtype)
-    dO = torch.randn(B, L, h, dh, generator=g).to(dtype)
+    io_dtype = io_dtype or dtype
+    dO = torch.randn(B, L, h, dh, generator=g).to(io_dtype)
     pad_keys = None
     if pad:
         pad_keys = torch.zeros(B, L, dtype=torch.bool)
@@ -39,14 +41,14 @@ def run_case(B, h, L, dh, max_seq, causal, pad, dtype, path, seed=0, scale=1.0, 
     # ---- CUDA
     qkv_d = qkv.to(dev)
     Ed = E.to(dev)
-    Od = torch.empty(B, L, h, dh, dtype=dtype, device=dev)
+    Od = torch.empty(B, L, h, dh, dtype=io_dtype, device=dev)
     lse = torch.empty(B, h, L, device=dev)
     strides = (L * 3 * d, 3 * d, dh)
     ostr = (L * d, d, dh)
     qd, kd, vd = qkv_d[:, :, 0], qkv_d[:, :, 1], qkv_d[:, :, 2]
     pk = pad_keys.to(torch.uint8).to(dev) if pad_keys is not None else None
     ops.rga_fwd(qd, kd, vd, strides, Ed, pk, Od, ostr, lse, B, h, L, dh, max_seq, causal, path=path)
-    dqkv = torch.zeros(B, L, 3, h, dh, dtype=dtype, device=dev)
+    dqkv = torch.zeros(B, L, 3, h, dh, dtype=io_dtype, device=dev)
     dE = torch.zeros(max_seq, dh, device=dev)
     delta = torch.empty(B, h, L, device=dev)
     ops.rga_bwd(qd, kd, vd, strides, Ed, pk, Od, dO.to(dev), ostr, lse, delta, dqkv[:, :, 0],
@@ -167,6 +169,42 @@ def test_rga_bwd_tcgen05(B, h, L, max_seq, pad, spill):
     assert r["o"] < 6e-3, r
     # P and dS are rounded to bf16 before the gradient GEMMs
     assert max(r["dq"], r["dk"], r["dv"]) < 1.2e-2 and r["dE"] < 1.2e-2, r
+
+
+@pytest.mark.parametrize("B,h,L,max_seq,pad,scale", [
+    (1, 1, 128, 128, False, 1.0),
+    (2, 2, 256, 256, False, 1.0),
+    (1, 2, 200, 256, False, 1.0),           # ragged L < max_seq
+    (1, 2, 384, 512, True, 1.0),
+    (2, 4, 512, 512, False, 6.0),           # layer-0-like statistics: logits in the hundreds
+    (1, 8, 1024, 2048, True, 3.0),
+])
+def test_rga_tcgen05_mixed_f16_qkv_bf16_io(B, h, L, max_seq, pad, scale):
+    """The first encoder layer's mode (MT_F16_BF16): f16 q / k / v / E operands, bf16 O / dO / dq / dk / dv --
+    tcgen05.mma with different A and B formats in the gradient products.  fp64 oracle on the same inputs."""
+    r = run_case(B, h, L, 64, max_seq, True, pad, torch.float16, PATHS["tc"], seed=L + 3 * h, scale=scale,
+                 io_dtype=torch.bfloat16)
+    # O is rounded to bf16 on the way out (as in the bf16 mode); the logits see f16 operands and an f16 P
+    assert r["o"] < 6e-3 and r["lse"] < 2e-3 * max(1.0, scale * scale), r
+    assert max(r["dq"], r["dk"], r["dv"]) < 1.2e-2 and r["dE"] < 1.2e-2, r
+
+
+def test_rga_mixed_mode_needs_the_tensor_core_path_and_workspace():
+    from musicgeneration_b200 import ops
+    dev = torch.device("cuda:0")
+    B, h, L, dh = 1, 1, 128, 64
+    qkv = torch.zeros(B, L, 3, h, dh, dtype=torch.float16, device=dev)
+    E = torch.zeros(L, dh, dtype=torch.float16, device=dev)
+    Od = torch.zeros(B, L, h, dh, dtype=torch.bfloat16, device=dev)
+    lse = torch.zeros(B, h, L, device=dev)
+    with pytest.raises(RuntimeError, match="tcgen05 path only"):
+        ops.rga_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], (L * 192, 192, 64), E, None, Od, (L * 64, 64, 64), lse,
+                    B, h, L, dh, L, True, path=1)
+    dq = torch.zeros_like(qkv, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="workspace"):
+        ops.rga_bwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], (L * 192, 192, 64), E, None, Od, Od, (L * 64, 64, 64),
+                    lse, torch.zeros(B, h, L, device=dev), dq[:, :, 0], dq[:, :, 1], dq[:, :, 2],
+                    torch.zeros(L, dh, device=dev), B, h, L, dh, L, True, path=2, spill=False)
 
 
 def test_rga_bwd_tcgen05_matches_simt_backward():

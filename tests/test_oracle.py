@@ -96,6 +96,45 @@ def test_decode_small():
     assert (lit.numpy() == z["literal_ids"]).all()
 
 
+def test_decode_small_pad_tokens_in_prior():
+    """Pad tokens inside the prior (and a generated pad token): the causal oracle masks them as keys exactly
+    as the reference's recompute does (MT/utils.py:73)."""
+    z = load("decode_small.npz")
+    d, V, pad, layers, max_seq, steps, thr = z["meta"].tolist()
+    with torch.no_grad():
+        ids, zs = O.generate_causal_greedy(torch.from_numpy(z["prior_pad"]), steps, params_of(z), max_seq, pad)
+    assert (ids.numpy() == z["causal_ids_pad"]).all()
+    np.testing.assert_allclose(zs.numpy(), z["causal_logits_pad"], atol=2e-5)
+
+
+def _seeded_drop_in_params(d, layers, L):
+    """state_dict of the drop-in module built under torch.manual_seed(0): the reference's own seed-0 weights
+    (same constructors in the same order; test_live_reference_matches_oracle re-checks the equality live)."""
+    import musicgeneration_b200 as mtb
+    torch.manual_seed(0)
+    m = mtb.MusicTransformer(embedding_dim=d, vocab_size=390, num_layer=layers, max_seq=L, dropout=0.0)
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def test_config_a_and_b_summaries_pin_the_oracle_at_the_benchmarked_shapes():
+    """BASELINE configs A (d256) and B (d512) at L = 2048: the oracle on the seed-0 weights reproduces the loss
+    and logits the unmodified reference recorded (oracle/make_golden.py --config-a / --config-b)."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    za, zb = load("config_a_summary.npz"), load("config_b_summary.npz")
+    x, y = O.synthetic_ids(2, 2048, 388)
+    with torch.no_grad():
+        la = O.model_forward(x, _seeded_drop_in_params(256, 6, 2048), 2048, 388)
+        np.testing.assert_allclose(la[:, ::256, ::39].numpy(), za["logits_slice"], atol=3e-5)
+        assert abs(float(O.smooth_ce(la, y, 0.1, 390, 388)) - float(za["loss"])) < 1e-5
+        pb = _seeded_drop_in_params(512, 6, 2048)
+        lb = O.model_forward(x[:1], pb, 2048, 388)
+        np.testing.assert_allclose(lb[:, ::16].numpy(), zb["logits_rows"][:1], atol=5e-5)
+        # first decode steps of the config-B fixture (pad token inside the second prior)
+        ids, zs = O.generate_causal_greedy(torch.from_numpy(zb["prior"]), 6, pb, 2048, 388)
+    assert (ids.numpy() == zb["causal_ids"][:, :ids.shape[1]]).all()
+    np.testing.assert_allclose(zs.numpy(), zb["causal_logits"][:6], atol=5e-5)
+
+
 def test_pe_and_schedule():
     z = load("misc.npz")
     assert (O.sinusoid_table(40, 64).astype(np.float32) == z["pe"].astype(np.float32)).all()
@@ -143,6 +182,12 @@ def test_live_reference_matches_oracle():
     assert (ref - ours).abs().max() < 2e-5
     l_ref = R.criterion.SmoothCrossEntropyLoss(0.1, 72, 70)(ref, y)
     assert abs(float(l_ref) - float(O.smooth_ce(ours, y, 0.1, 72, 70))) < 2e-6
+    # the drop-in module built under the same seed has the reference's initial weights bit for bit
+    import musicgeneration_b200 as mtb
+    torch.manual_seed(11)
+    mine = mtb.MusicTransformer(embedding_dim=192, vocab_size=72, num_layer=2, max_seq=32, dropout=0.0)
+    sd = mine.state_dict()
+    assert list(sd.keys()) == list(p.keys()) and all(torch.equal(sd[k], p[k]) for k in p)
 
 
 # ---- data feed (MT/data.py) ---------------------------------------------------------------

@@ -20,7 +20,10 @@
  *     MT_F16_BF16 = 3 is accepted by mt_rga_fwd / mt_rga_bwd_ws (tcgen05 path) only: q, k, v and E are
  *     f16 (11-bit mantissa), every other 16-bit tensor of the call (O, dO, dq, dk, dv) is bf16 -- the
  *     mode of the FIRST encoder layer, whose input is the un-normalised embedding (MT/layers.py:226-229:
- *     |logit| ~ 1e3, a bf16 operand moves the near-one-hot softmax).
+ *     |logit| ~ 1e3, a bf16 operand moves the near-one-hot softmax).  The
+ *     backward needs the workspace of mt_rga_bwd_workspace_bytes(..., MT_F16_BF16) and a dense
+ *     [B, L, h, dh] O / dO (it keeps a loss-scaled f16 copy of dO there: the tensor cores take one
+ *     operand format per product).
  *   - tensors are row-major and dense unless strides are passed (strides are in ELEMENTS).
  */
 #ifndef MT_B200_H_
@@ -145,8 +148,8 @@ int mt_rga_bwd_ws(const void* q, const void* k, const void* v, int64_t sb, int64
                   void* dv, float* dE, int64_t B, int64_t h, int64_t L, int64_t dh,
                   int64_t max_seq, int causal, int dtype, int path, void* workspace,
                   size_t workspace_bytes, void* stream);
-/* B*h*nT*(nT+1)/2 tiles of 32 KB, nT = ceil(L/128); 0 when the tcgen05 backward does not take
- * the problem (dh != 64 or not bf16) */
+/* B*h*nT*(nT+1)/2 tiles of 32 KB, nT = ceil(L/128) (+ B*L*h*dh*2 bytes for MT_F16_BF16); 0 when the
+ * tcgen05 backward does not take the problem (dh != 64, or dtype not MT_BF16 / MT_F16_BF16) */
 size_t mt_rga_bwd_workspace_bytes(int64_t B, int64_t h, int64_t L, int64_t dh, int dtype);
 
 /* ---- K6: label-smoothed cross entropy + step metrics  (MT/criterion.py:43-67, ------------

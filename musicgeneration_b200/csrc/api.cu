@@ -99,7 +99,7 @@ int mt_rga_weights(const void* q, const void* k, int64_t sb, int64_t sl, int64_t
 
 size_t mt_rga_bwd_workspace_bytes(int64_t B, int64_t h, int64_t L, int64_t dh, int dtype) {
   if (dh != 64 || (dtype != MT_BF16 && dtype != MT_F16_BF16) || B <= 0 || h <= 0 || L <= 0) return 0;
-  return rga_bwd3_workspace_bytes(B, h, L);
+  return rga_bwd3_workspace_bytes(B, h, L) + (dtype == MT_F16_BF16 ? rga_bwd_mixed_extra_bytes(B, h, L, dh) : 0);
 }
 
 int mt_rga_bwd(const void* q, const void* k, const void* v, int64_t sb, int64_t sl, int64_t sh,

@@ -221,6 +221,10 @@ __global__ void __launch_bounds__(RTHREADS) rga_weights_kernel(RgaArgs p) {
 // delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d].  dh/8 lanes per (b,i,h) row, 16-byte loads (a
 // warp reads 512 contiguous bytes of O and of dO when the heads of a position are adjacent),
 // shuffle reduction inside the lane group; dh in {32, 64, 128} (other head sizes: one warp per row).
+__device__ __forceinline__ uint32_t rga_pack_h2(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
 template <typename T, int LPR>         // LPR = lanes per row = dh / 8
 __global__ void __launch_bounds__(256) rga_delta_vec_kernel(RgaArgs p) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -238,8 +242,15 @@ __global__ void __launch_bounds__(256) rga_delta_vec_kernel(RgaArgs p) {
     const uint4 g = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.dO) + off);
     const T* ov = reinterpret_cast<const T*>(&o);
     const T* gv = reinterpret_cast<const T*>(&g);
+    float gf[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) s += to_f<T>(ov[e]) * to_f<T>(gv[e]);
+    for (int e = 0; e < 8; ++e) { gf[e] = to_f<T>(gv[e]); s += to_f<T>(ov[e]) * gf[e]; }
+    if (p.dO_h) {          // loss-scaled f16 copy of dO for the f16 gradient mode (same addressing)
+      uint4 w;
+      w.x = rga_pack_h2(gf[0] * p.gscale, gf[1] * p.gscale); w.y = rga_pack_h2(gf[2] * p.gscale, gf[3] * p.gscale);
+      w.z = rga_pack_h2(gf[4] * p.gscale, gf[5] * p.gscale); w.w = rga_pack_h2(gf[6] * p.gscale, gf[7] * p.gscale);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.dO_h) + off) = w;
+    }
   }
 #pragma unroll
   for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -525,6 +536,11 @@ int rga_weights_simt(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
 
 int rga_delta_launch(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
   const int64_t rows = (int64_t)a.B * a.h * a.L;
+  if (a.dO_h && !(dtype == MT_BF16 && (dh == 32 || dh == 64 || dh == 128) && a.ob % 8 == 0 && a.oh % 8 == 0 &&
+                  a.ol % 8 == 0 && aligned(a.O, 16) && aligned(a.dO, 16) && aligned(a.dO_h, 16))) {
+    set_error("rga_delta: the scaled f16 copy of dO needs the vector kernel (bf16, 16-byte aligned rows)");
+    return MT_E_UNSUPPORTED;
+  }
   const bool vec = (dtype == MT_BF16 || dtype == MT_F16) && (dh == 32 || dh == 64 || dh == 128) &&
                    a.ob % 8 == 0 && a.oh % 8 == 0 && a.ol % 8 == 0 && aligned(a.O, 16) && aligned(a.dO, 16);
   if (vec) {

@@ -94,7 +94,10 @@ struct Bwd2Params {
   int bh_per_cta;                        // DE role
   uint8_t* ds_ws; int nTri;              // DKV role: spill every dS tile image here (rga_tc_bwd3.cu consumes them)
   int heads_per_cta;                     // DKV role: consecutive heads of one (batch row, key tile) walked by one CTA
-  int qk_fmt;                            // DKV role: 16-bit format of q / k / v / E (1 = bf16, 0 = f16: mixed mode); dO, P, dS, dq/dk/dv are bf16
+  int qk_fmt;                            // DKV role: 16-bit format of EVERY MMA operand of the launch (1 = bf16; 0 = f16: the first
+                                         // encoder layer -- tcgen05 kind::f16 traps on A / B of different formats, so there dO comes
+                                         // in as f16(gscale * dO) and P / dS are packed as f16; dK / dV leave as bf16 either way)
+  float gscale, inv_gscale;              // f16 mode: static loss scale of the gradient operands (dO, dS) and its inverse (outputs)
   float scale, scale_log2;
   long long* trace;                      // MT_RGA_TRACE=z: clock64 stamps of CTA (0,0,z), [4 agents][32 steps][8 events]
   int trace_z;
@@ -169,7 +172,8 @@ __device__ __forceinline__ void park64_st64(uint32_t g_lo, uint32_t g_hi, uint32
 __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
-template <int ROLE>
+// HF (dK/dV role only): the f16 mode described at Bwd2Params::qk_fmt
+template <int ROLE, bool HF = false>
 __global__ void __launch_bounds__(B2_THREADS, 1)
 rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -357,8 +361,7 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ================================ MMA issuer ============================================
     if (ROLE == R_DKV) {
       if (lane == 0) {         // S, G, dP products (dV / dK: second issuer, warp 18)
-        const uint32_t id_kk = tc::make_idesc(TT, TT, p.qk_fmt, p.qk_fmt, 0, 0);      // S, G: K-major x K-major, N = 128
-        const uint32_t id_dp = tc::make_idesc(TT, TT, 1, p.qk_fmt, 0, 0);             // dP: A = dO (bf16), B = V
+        const uint32_t id_kk = tc::make_idesc(TT, TT, p.qk_fmt, p.qk_fmt, 0, 0);      // S, G, dP: K-major x K-major, N = 128
         constexpr uint64_t TS16 = TILE >> 4;
         const uint64_t kd = tc::make_sdesc(tc::smem_u32(buf_k()), 16, 1024);
         const uint64_t vd = tc::make_sdesc(tc::smem_u32(buf_v()), 16, 1024);
@@ -397,7 +400,7 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const uint64_t dod = dod0 + (uint64_t)(n % 3) * TS16;
 #pragma unroll
           for (int k4 = 0; k4 < DHC / 16; ++k4)   // dP = dO V^T into the S columns
-            tc::umma_f16(tmem + TM_S, dod + 2 * k4, vd + 2 * k4, id_dp, k4 != 0);
+            tc::umma_f16(tmem + TM_S, dod + 2 * k4, vd + 2 * k4, id_kk, k4 != 0);
           tc::umma_commit(dp_full);
           TRACE(3, n, 1);
           if (++k == per) { k = 0; ++item; }
@@ -594,8 +597,7 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // to the products' issue time (trace: 5.7 k cycles per loop iteration = the step).  The two groups of
     // products touch disjoint TMEM columns and shared-memory stages, so they are issued by two threads.
     if (ROLE == R_DKV && MT_DKV_FUSED16 && lane == 0) {
-      const uint32_t id_mnmn = tc::make_idesc(TT, DHC, 1, 1, 1, 1);   // A MN-major (P / dS), B MN-major (dO / Q), N = 64
-      const uint32_t id_dk = tc::make_idesc(TT, DHC, 1, p.qk_fmt, 1, 1);   // dK: B = Q in its own 16-bit format
+      const uint32_t id_mnmn = tc::make_idesc(TT, DHC, p.qk_fmt, p.qk_fmt, 1, 1);   // A MN-major (P / dS), B MN-major (dO / Q), N = 64
       constexpr uint64_t STR = TILE >> 4;
       const uint64_t qd_mn0 = tc::make_sdesc(tc::smem_u32(smem + Lay2<R_DKV>::Q0), 1024, 1024);
       const uint64_t dod_mn0 = tc::make_sdesc(tc::smem_u32(smem + Lay2<R_DKV>::DO0), 1024, 1024);
@@ -619,7 +621,7 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int k16 = 0; k16 < TT / 16; ++k16) {      // contraction over the 128 query rows
           tc::umma_f16(tmem + TM_ACC1, opd0 + 128 * k16, dod_mn + 128 * k16, id_mnmn, (k | k16) != 0);   // dV += P^T dO
-          tc::umma_f16(tmem + TM_ACC0, opd1 + 128 * k16, qd_mn + 128 * k16, id_dk, (k | k16) != 0);      // dK += dS^T Q
+          tc::umma_f16(tmem + TM_ACC0, opd1 + 128 * k16, qd_mn + 128 * k16, id_mnmn, (k | k16) != 0);    // dK += dS^T Q
         }
         if (p.ds_ws) tc::bulk_wait_read0();            // the math warps overwrite dS once step_done is signalled
         tc::umma_commit(&qd_empty[n % 3]);
@@ -657,6 +659,8 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // dK (warps 0-7, ACC0) / dV (warps 8-15, ACC1) of head hh -> global; each thread 32 of the 64 columns of key row a
       auto store_acc = [&](int hh) {
         uint32_t r[32];
+        // f16 mode: dV = P^T (g dO) and dK = (g dS)^T Q carry the loss scale g
+        const float osc = HF ? p.inv_gscale : 1.f;
         tc::tmem_ld_32x32(tmem + (grp ? TM_ACC1 : TM_ACC0) + lane_base + half * 32, r);
         tc::tmem_ld_wait();
         tc::tc_fence_before();
@@ -666,17 +670,18 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                                                 (int64_t)row * p.sl + (int64_t)hh * p.sh + half * 32);
 #pragma unroll
           for (int x = 0; x < 4; ++x)
-            dst[x] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * x]), __uint_as_float(r[8 * x + 1])),
-                                pack_bf16x2(__uint_as_float(r[8 * x + 2]), __uint_as_float(r[8 * x + 3])),
-                                pack_bf16x2(__uint_as_float(r[8 * x + 4]), __uint_as_float(r[8 * x + 5])),
-                                pack_bf16x2(__uint_as_float(r[8 * x + 6]), __uint_as_float(r[8 * x + 7])));
+            dst[x] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * x]) * osc, __uint_as_float(r[8 * x + 1]) * osc),
+                                pack_bf16x2(__uint_as_float(r[8 * x + 2]) * osc, __uint_as_float(r[8 * x + 3]) * osc),
+                                pack_bf16x2(__uint_as_float(r[8 * x + 4]) * osc, __uint_as_float(r[8 * x + 5]) * osc),
+                                pack_bf16x2(__uint_as_float(r[8 * x + 6]) * osc, __uint_as_float(r[8 * x + 7]) * osc));
         }
       };
       for (int n = 0; n < nsteps; ++n, s = snext) {
         const uint32_t par = n & 1;
         const int i0 = s.it * TT, j0 = s.jt * TT;
         const bool row_ok = i0 + a < p.L;
-        const float lse2 = lse_next * LOG2E, Ds = d_next * p.scale;
+        // (f16 mode: dP arrives scaled by g, so D is scaled to match and dS = g * the true dS)
+        const float lse2 = lse_next * LOG2E, Ds = d_next * p.scale * (HF ? p.gscale : 1.f);
         step_advance<ROLE>(p, snext);
         if (n + 1 < nsteps) { lse_next = row_stat(p.lse, snext); d_next = row_stat(p.delta, snext); }
         if (pad) {
@@ -725,7 +730,7 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         uint32_t pk[16];
 #pragma unroll
-        for (int x = 0; x < 16; ++x) pk[x] = pack_bf16x2(sv[2 * x], sv[2 * x + 1]);
+        for (int x = 0; x < 16; ++x) pk[x] = HF ? pack_f16x2(sv[2 * x], sv[2 * x + 1]) : pack_bf16x2(sv[2 * x], sv[2 * x + 1]);
         if (threadIdx.x == 0) TRACE(0, n, 3);
         // dP was issued right after sg_free and has long arrived: read it BEFORE the stores of P (which wait for
         // the previous step's dV / dK products), so that dp_free -- the go-ahead of the next step's S product --
@@ -743,9 +748,12 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           // dS = P o (dP - D) / sqrt(dh), with the bf16-rounded P the dV product sees
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            const float d0 = fmaf(__uint_as_float(dp[2 * k]), p.scale, -Ds) * bf16lo(pk[k]);
-            const float d1 = fmaf(__uint_as_float(dp[2 * k + 1]), p.scale, -Ds) * bf16hi(pk[k]);
-            A16[k] = pack_bf16x2(d0, d1);
+            float p0, p1;
+            if (HF) { const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&pk[k])); p0 = pf.x; p1 = pf.y; }
+            else { p0 = bf16lo(pk[k]); p1 = bf16hi(pk[k]); }
+            const float d0 = fmaf(__uint_as_float(dp[2 * k]), p.scale, -Ds) * p0;
+            const float d1 = fmaf(__uint_as_float(dp[2 * k + 1]), p.scale, -Ds) * p1;
+            A16[k] = HF ? pack_f16x2(d0, d1) : pack_bf16x2(d0, d1);
           }
         }
         if (threadIdx.x == 0) TRACE(0, n, 5);
@@ -1041,10 +1049,10 @@ rga_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-template <int ROLE>
+template <int ROLE, bool HF = false>
 int launch_role2(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmDO,
                  const CUtensorMap& tmE, const Bwd2Params& p, dim3 grid, cudaStream_t st) {
-  auto kern = rga_bwd2_kernel<ROLE>;
+  auto kern = rga_bwd2_kernel<ROLE, HF>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_bytes<ROLE>());
@@ -1094,6 +1102,7 @@ Bwd2Params make_params2(const RgaArgs& a) {
   p.ds_ws = nullptr;
   p.heads_per_cta = 1;
   p.qk_fmt = 1;
+  p.gscale = p.inv_gscale = 1.f;
   p.nTri = p.nT * (p.nT + 1) / 2;
   p.trace = nullptr;
   p.trace_z = 0;
@@ -1104,10 +1113,12 @@ Bwd2Params make_params2(const RgaArgs& a) {
 
 // dK, dV (key-tile owner walks the query tiles at or below it); ds_ws != NULL: also spill the dS tiles
 int rga_bwd2_dkv(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
-                 const CUtensorMap& tmDO, const CUtensorMap& tmE, void* ds_ws, int qk_fmt, cudaStream_t st) {
+                 const CUtensorMap& tmDO, const CUtensorMap& tmE, void* ds_ws, int qk_fmt, float gscale, cudaStream_t st) {
   Bwd2Params p = make_params2(a);
   p.ds_ws = static_cast<uint8_t*>(ds_ws);
   p.qk_fmt = qk_fmt;
+  p.gscale = gscale;
+  p.inv_gscale = 1.f / gscale;
   // consecutive heads of one (batch row, key tile) share a CTA (same walk over the query tiles; the resident K / V
   // tiles are reloaded and dK / dV flushed at the head boundary): as many as leave at least three CTAs per SM
   static const int hpc_env = getenv("MT_DKV_HPC") ? atoi(getenv("MT_DKV_HPC")) : 0;
@@ -1116,7 +1127,9 @@ int rga_bwd2_dkv(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tm
     if ((int64_t)((a.h + c - 1) / c) * a.B * p.nT >= 3 * (int64_t)sm_count()) { hpc = c; break; }
   if (hpc_env > 0) hpc = hpc_env;
   p.heads_per_cta = hpc > a.h ? a.h : hpc;
-  return launch_role2<R_DKV>(tmQ, tmK, tmV, tmDO, tmE, p, dim3((a.h + p.heads_per_cta - 1) / p.heads_per_cta, a.B, p.nT), st);
+  const dim3 grid((a.h + p.heads_per_cta - 1) / p.heads_per_cta, a.B, p.nT);
+  if (qk_fmt == 0) return launch_role2<R_DKV, true>(tmQ, tmK, tmV, tmDO, tmE, p, grid, st);
+  return launch_role2<R_DKV>(tmQ, tmK, tmV, tmDO, tmE, p, grid, st);
 }
 
 // dQ (query-tile owner walks the key tiles at or left of it; P / dS stay in TMEM)

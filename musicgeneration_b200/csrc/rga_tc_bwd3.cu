@@ -65,7 +65,8 @@ struct Bwd3Params {
   int B, h, L, max_seq, nT, nTri;
   int bh_per_cta;                        // dE role
   int heads_per_cta;                     // dQ role: consecutive heads of one (batch row, query tile) walked by one CTA
-  int qk_fmt;                            // 16-bit format of the K / Q / E operands (1 = bf16, 0 = f16: mixed mode); dS / dG are bf16
+  int qk_fmt;                            // 16-bit format of every MMA operand (1 = bf16; 0 = f16: the dS tiles then hold f16(g * dS))
+  float out_scale;                       // 1 / g: applied to dQ / dE on the way out (1 in the bf16 mode)
   long long* trace;                      // MT_RGA_TRACE=z: clock64 stamps of CTA (0,0,z), [2 agents][32 steps][4 events]
   int trace_z;
 };
@@ -189,7 +190,7 @@ rga_bwd3_kernel(const __grid_constant__ CUtensorMap tmX,      // K (dQ role) or 
     // ================================ MMA issuer ============================================
     if (lane == 0) {
       if (ROLE == L_DQ) {
-        const uint32_t id_kmn = tc::make_idesc(TT, DHC, 1, p.qk_fmt, 0, 1);    // A K-major (TMEM dS / smem dG, bf16), B MN-major (K / E), N = 64
+        const uint32_t id_kmn = tc::make_idesc(TT, DHC, p.qk_fmt, p.qk_fmt, 0, 1);    // A K-major (TMEM dS / smem dG), B MN-major (K / E), N = 64
         const uint64_t kd_mn0 = tc::make_sdesc(tc::smem_u32(smem + LY::X0), 1024, 1024);
         const uint64_t ed_mn0 = tc::make_sdesc(tc::smem_u32(smem + LY::E0), 1024, 1024);
         const uint64_t dgd0 = tc::make_sdesc(tc::smem_u32(smem + LY::DG), 16, 1024);
@@ -220,7 +221,7 @@ rga_bwd3_kernel(const __grid_constant__ CUtensorMap tmX,      // K (dQ role) or 
           TRACE3(1, n, 2);
         }
       } else {
-        const uint32_t id_mnmn = tc::make_idesc(TT, DHC, 1, p.qk_fmt, 1, 1);   // A MN-major (dG block, bf16), B MN-major (Q), N = 64
+        const uint32_t id_mnmn = tc::make_idesc(TT, DHC, p.qk_fmt, p.qk_fmt, 1, 1);   // A MN-major (dG block), B MN-major (Q), N = 64
         const uint64_t qd_mn0 = tc::make_sdesc(tc::smem_u32(smem + LY::X0), 1024, 1024);
         const uint64_t dg_lo0 = tc::make_sdesc(tc::smem_u32(smem + LY::DG), TILE, 1024);
         const uint64_t dg_hi0 = tc::make_sdesc(tc::smem_u32(smem + LY::DG + 2 * TILE), TILE, 1024);
@@ -318,15 +319,16 @@ rga_bwd3_kernel(const __grid_constant__ CUtensorMap tmX,      // K (dQ role) or 
       tc::tc_fence_before();
       const Step3 s = step3_first<ROLE>(p, bh0);
       const int row = s.it * TT + a;
+      const float osc = p.out_scale;          // (f16 mode: the dS tiles carry the loss scale)
       if (row < p.L) {
         uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dq) + (int64_t)s.b * p.sb +
                                               (int64_t)row * p.sl + (int64_t)(s.hh + item) * p.sh + q4 * 16);
 #pragma unroll
         for (int x = 0; x < 2; ++x)
-          dst[x] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * x]), __uint_as_float(r[8 * x + 1])),
-                              pack_bf16x2(__uint_as_float(r[8 * x + 2]), __uint_as_float(r[8 * x + 3])),
-                              pack_bf16x2(__uint_as_float(r[8 * x + 4]), __uint_as_float(r[8 * x + 5])),
-                              pack_bf16x2(__uint_as_float(r[8 * x + 6]), __uint_as_float(r[8 * x + 7])));
+          dst[x] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * x]) * osc, __uint_as_float(r[8 * x + 1]) * osc),
+                              pack_bf16x2(__uint_as_float(r[8 * x + 2]) * osc, __uint_as_float(r[8 * x + 3]) * osc),
+                              pack_bf16x2(__uint_as_float(r[8 * x + 4]) * osc, __uint_as_float(r[8 * x + 5]) * osc),
+                              pack_bf16x2(__uint_as_float(r[8 * x + 6]) * osc, __uint_as_float(r[8 * x + 7]) * osc));
       }
     };
     int cjt = 0, citem = 0;                // converter-side position inside the head
@@ -363,11 +365,12 @@ rga_bwd3_kernel(const __grid_constant__ CUtensorMap tmX,      // K (dQ role) or 
         // one flush per CTA, but every CTA of a diagonal hits the same rows: vector reductions (8 instead of 32
         // L2 operations per thread; dE rows are 256-byte aligned: mt_rga_bwd checks the base)
         float* dst = p.dE + (int64_t)erow * DHC + 32 * (q4 & 1);
+        const float osc = p.out_scale;
 #pragma unroll
         for (int x = 0; x < 32; x += 4)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + x), "f"(__uint_as_float(r[x])),
-                       "f"(__uint_as_float(r[x + 1])), "f"(__uint_as_float(r[x + 2])), "f"(__uint_as_float(r[x + 3]))
-                       : "memory");
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + x), "f"(__uint_as_float(r[x]) * osc),
+                       "f"(__uint_as_float(r[x + 1]) * osc), "f"(__uint_as_float(r[x + 2]) * osc),
+                       "f"(__uint_as_float(r[x + 3]) * osc) : "memory");
       }
     }
     tc::tc_fence_before();
@@ -429,6 +432,7 @@ Bwd3Params make_params3(const RgaArgs& a, const void* ws) {
   p.bh_per_cta = 1;
   p.heads_per_cta = 1;
   p.qk_fmt = 1;
+  p.out_scale = 1.f;
   p.trace = nullptr;
   p.trace_z = 0;
   return p;
@@ -442,9 +446,10 @@ size_t rga_bwd3_workspace_bytes(int64_t B, int64_t h, int64_t L) {
 }
 
 // dQ from the spilled dS tiles (query-tile owner walks the key tiles at or left of it)
-int rga_bwd3_dq(const RgaArgs& a, const void* ws, const CUtensorMap& tmK, const CUtensorMap& tmE, int qk_fmt, cudaStream_t st) {
+int rga_bwd3_dq(const RgaArgs& a, const void* ws, const CUtensorMap& tmK, const CUtensorMap& tmE, int qk_fmt, float gscale, cudaStream_t st) {
   Bwd3Params p = make_params3(a, ws);
   p.qk_fmt = qk_fmt;
+  p.out_scale = 1.f / gscale;
   // consecutive heads of one (batch row, query tile) share a CTA (same number of key tiles, same E blocks, two
   // alternating accumulators): as many as leave at least three CTAs per SM
   static const int hpc_env = getenv("MT_DQ_HPC") ? atoi(getenv("MT_DQ_HPC")) : 0;
@@ -457,9 +462,10 @@ int rga_bwd3_dq(const RgaArgs& a, const void* ws, const CUtensorMap& tmK, const 
 }
 
 // dE from the spilled dS tiles (tile-diagonal owner walks down the diagonal over a slice of (batch, head))
-int rga_bwd3_de(const RgaArgs& a, const void* ws, const CUtensorMap& tmQ, const CUtensorMap& tmE, int qk_fmt, cudaStream_t st) {
+int rga_bwd3_de(const RgaArgs& a, const void* ws, const CUtensorMap& tmQ, const CUtensorMap& tmE, int qk_fmt, float gscale, cudaStream_t st) {
   Bwd3Params p = make_params3(a, ws);
   p.qk_fmt = qk_fmt;
+  p.out_scale = 1.f / gscale;
   const int bh = a.B * a.h;
   int slices = (2 * sm_count() + p.nT - 1) / p.nT;       // about two CTAs per SM's worth of slices
   if (slices > bh) slices = bh;

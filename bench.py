@@ -12,8 +12,10 @@ batch 16 per GPU, bf16 operands, dropout 0.2 (reference default).
 Prints ONE JSON line (rank 0).  `value` = device-timed tokens/s with the ids resident in HBM;
 `e2e` = the same step through the public module API with pinned-host ids copied in and the loss
 read back every step (each step's loss goes to a pinned slot asynchronously and is read on the host
-while the next step runs -- utils.ScalarReadback; the last one before the clock stops).  `--impl reference` times the CPU oracle port (oracle/restate.py) of the
-same step on the host cores.
+while the next step runs -- utils.ScalarReadback; the last one before the clock stops).  `--impl reference` times the reference's own
+modules (staged by oracle/make_ref.py; the oracle port only if they are absent) on the host cores: the same
+optimizer step on a bounded sample of the workload.  At N = 1 the line also carries `cpu_baseline` (that step
+timed in the same run) and `gpu_eager_baseline` (the reference modules in eager PyTorch on the same B200).
 """
 from __future__ import annotations
 
@@ -112,77 +114,193 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def run_reference(args):
-    """CPU arm: the oracle port of the same train step (forward + loss + backward, fp32) on all host
-    threads, on a bounded sample (one sequence of the workload's shape per step)."""
+def workload_config(cfg_name, Bg, world, dropout):
+    """`config` of the JSON line: shared by the GPU arm and the reference arm (the driver compares them)."""
+    d, V, pad, layers, L, _ = CONFIGS[cfg_name]
+    return {"workload": f"MusicTransformer config {cfg_name}: V={V} {layers}L d{d} h{d // 64} "
+                        f"L={L} batch {Bg}/GPU, dropout {dropout}, fwd+loss+bwd+"
+                        f"{'allreduce+' if world > 1 else ''}Adam",
+            "global_batch": Bg * world, "seq_len": L, "parallelism": f"dp{world}",
+            "l2": "per-step activations (several GB) exceed the 126 MB L2; no flush needed"}
+
+
+def reference_train_step(cfg_name, device, batch, dropout):
+    """(step_fn, kind, tokens_per_step): one optimizer step of the reference's own train loop body
+    (MT/train.py:258-277 at accum_grad 1: forward in train mode, SmoothCrossEntropyLoss, backward,
+    CustomSchedule.step() = Noam rate + torch.optim.Adam.step) on `batch` synthetic sequences.
+    kind "reference": the UNMODIFIED MT modules (sources, or the compiled modules oracle/make_ref.py staged);
+    kind "port": oracle/restate.py with torch.optim.Adam, only when neither is present."""
     import torch
+    from oracle import ref_import
     from oracle import restate as O
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    d, V, pad, layers, L, Bg = CONFIGS[args.config]
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    p = {k: v.requires_grad_(True) for k, v in O.init_params(d, V, layers, L, seed=0).items()}
-    Bs = 1
-    x, y = O.synthetic_ids(Bs, L, pad)
-    steps, warm = max(1, args.steps), max(0, args.warmup)
-    # keep the whole arm within a few minutes: stop early on a time budget
-    budget_s = float(os.environ.get("MT_REF_BUDGET_S", "150"))
+    d, V, pad, layers, L, _ = CONFIGS[cfg_name]
+    x, y = O.synthetic_ids(batch, L, pad)
+    x, y = x.to(device), y.to(device)
+    if ref_import.reference_available():
+        R = ref_import.load_reference()
+        R.config.pad_token = pad
+        torch.manual_seed(0)
+        m = R.network.MusicTransformer(embedding_dim=d, vocab_size=V, num_layer=layers, max_seq=L,
+                                       dropout=dropout).to(device)
+        m.train()
+        opt = torch.optim.Adam(m.parameters(), lr=0, betas=(0.9, 0.98), eps=1e-9)      # MT/train.py:143
+        sched = R.criterion.CustomSchedule(d, optimizer=opt)                             # MT/train.py:151
+        crit = R.criterion.SmoothCrossEntropyLoss(0.1, V, pad)                           # MT/train.py:134
+
+        def step():
+            sched.optimizer.zero_grad()
+            loss = crit(m(x), y)
+            loss.backward()
+            sched.step()
+            return loss
+        return step, "reference", batch * L
+    p = {k: v.to(device).requires_grad_(True) for k, v in O.init_params(d, V, layers, L, seed=0).items()}
+    opt = torch.optim.Adam(list(p.values()), lr=0, betas=(0.9, 0.98), eps=1e-9)
+
+    def step():
+        opt.zero_grad()
+        loss = O.smooth_ce(O.model_forward(x, p, L, pad), y, 0.1, V, pad)
+        loss.backward()
+        for g in opt.param_groups:
+            g["lr"] = O.noam_rate(max(1, step.n), d)
+        step.n += 1
+        opt.step()
+        return loss
+    step.n = 1
+    return step, "port", batch * L
+
+
+def time_cpu_steps(step, steps, warm, budget_s):
     times = []
     t_begin = time.time()
     for it in range(warm + steps):
         t0 = time.time()
-        for v in p.values():
-            v.grad = None
-        logits = O.model_forward(x, p, L, pad)
-        loss = O.smooth_ce(logits, y, 0.1, V, pad)
-        loss.backward()
+        step()
         dt_ = time.time() - t0
         if it >= warm:
             times.append(dt_)
         if time.time() - t_begin > budget_s and len(times) >= 1:
             break
+    return times
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the same train step (forward + loss + backward +
+    Adam with the Noam rate, fp32) on all host threads of the box; each step is a bounded sample of the
+    workload (one sequence of its shape -- batch 16 x 2048 materialises ~40 GB of L x L temporaries on the
+    host and takes minutes per step).  Also times BASELINE.json's configs[0] (config A forward + loss)."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    d, V, pad, layers, L, Bg = CONFIGS[args.config]
+    if args.batch:
+        Bg = args.batch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs = 1
+    step, kind, tokens = reference_train_step(args.config, torch.device("cpu"), Bs, args.dropout)
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    # keep the whole arm within a few minutes: stop early on a time budget
+    times = time_cpu_steps(step, steps, warm, float(os.environ.get("MT_REF_BUDGET_S", "150")))
     ms = 1e3 * sum(times) / len(times)
-    val = Bs * L / (ms / 1e3)
+    val = tokens / (ms / 1e3)
+    what = "unmodified MT/{network,layers,criterion,utils}.py" if kind == "reference" else "oracle/restate.py"
     line = {"impl": "reference", "metric": "train_tokens_per_s", "value": val, "unit": "tokens/s",
             "n_gpus": args.gpus, "steps": len(times), "warmup": warm, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"MusicTransformer config {args.config}: V={V} {layers}L d{d} "
-                                   f"h{d // 64} L={L}, fwd+loss+bwd", "cpu_sample_batch": Bs},
-            "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port",
-                             "sample": f"{len(times)} steps of 1 sequence x {L} tokens, oracle/restate.py "
-                                       f"(reference op sequence incl. the L x L skew), torch CPU fp32, "
+            "config": workload_config(args.config, Bg, max(1, args.gpus), args.dropout),
+            "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": kind,
+                             "sample": f"{len(times)} optimizer steps (fwd+loss+bwd+Adam) on {Bs} sequence x {L} tokens "
+                                       f"of the workload per step, {what}, torch {torch.__version__} CPU fp32, "
                                        f"{torch.get_num_threads()} threads"},
             "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    # BASELINE.json configs[0]: config A, batch 2, forward + loss on CPU (the reference's own CPU-runnable case)
+    try:
+        line["baseline_config_a_fwd_loss"] = config_a_forward_loss()
+    except Exception as e:                      # noqa: BLE001 -- an extra figure must not lose the line
+        line["baseline_config_a_fwd_loss"] = {"error": str(e)[:200]}
     emit(line)
 
 
-def cpu_baseline_leg(cfg_name, budget_s=20.0):
+def config_a_forward_loss(budget_s=30.0):
     import torch
+    from oracle import ref_import
     from oracle import restate as O
+    d, V, pad, layers, L, B = CONFIGS["A"]
+    x, y = O.synthetic_ids(B, L, pad)
+    if ref_import.reference_available():
+        R = ref_import.load_reference()
+        R.config.pad_token = pad
+        torch.manual_seed(0)
+        m = R.network.MusicTransformer(embedding_dim=d, vocab_size=V, num_layer=layers, max_seq=L, dropout=0.0)
+        m.train()
+        crit = R.criterion.SmoothCrossEntropyLoss(0.1, V, pad)
+        fn, kind = (lambda: crit(m(x), y)), "reference"
+    else:
+        p = O.init_params(d, V, layers, L, seed=0)
+        fn, kind = (lambda: O.smooth_ce(O.model_forward(x, p, L, pad), y, 0.1, V, pad)), "port"
+    times, loss = [], None
+    t_begin = time.time()
+    with torch.no_grad():
+        for it in range(4):
+            t0 = time.time()
+            loss = float(fn())
+            times.append(time.time() - t0)
+            if time.time() - t_begin > budget_s:
+                break
+    best = min(times[1:]) if len(times) > 1 else times[0]
+    return {"tokens_per_s": B * L / best, "ms": 1e3 * best, "loss": loss, "kind": kind,
+            "what": f"config A (V={V} {layers}L d{d} L={L} batch {B}) forward + loss, fp32, {os.cpu_count()} host threads"}
+
+
+def cpu_baseline_leg(cfg_name, dropout, budget_s=25.0):
+    """The same reference step on the box's host cores inside the GPU arm's run (N = 1)."""
+    import torch
     d, V, pad, layers, L, Bg = CONFIGS[cfg_name]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    p = {k: v.requires_grad_(True) for k, v in O.init_params(d, V, layers, L, seed=0).items()}
-    x, y = O.synthetic_ids(1, L, pad)
-    times = []
-    t_begin = time.time()
-    for it in range(3):
-        t0 = time.time()
-        for v in p.values():
-            v.grad = None
-        loss = O.smooth_ce(O.model_forward(x, p, L, pad), y, 0.1, V, pad)
-        loss.backward()
-        times.append(time.time() - t0)
-        if time.time() - t_begin > budget_s:
-            break
-    best = min(times[1:]) if len(times) > 1 else times[0]
-    return {"value": L / best, "unit": "tokens/s", "cores": cores, "kind": "port",
-            "sample": f"{len(times)} steps (first = warm-up) of 1 sequence x {L} tokens, fwd+loss+bwd, "
-                      f"oracle/restate.py on torch CPU fp32, {torch.get_num_threads()} threads"}
+    step, kind, tokens = reference_train_step(cfg_name, torch.device("cpu"), 1, dropout)
+    times = time_cpu_steps(step, 3, 1, budget_s)
+    best = min(times)
+    what = "unmodified MT modules" if kind == "reference" else "oracle/restate.py"
+    return {"value": tokens / best, "unit": "tokens/s", "cores": cores, "kind": kind,
+            "sample": f"{len(times)} optimizer steps after 1 warm-up (fwd+loss+bwd+Adam) on 1 sequence x {L} tokens, "
+                      f"{what}, torch CPU fp32, {torch.get_num_threads()} threads"}
+
+
+def gpu_eager_leg(dev, dropout):
+    """Second comparator: the reference modules moved to the SAME B200 and run in eager
+    PyTorch (fp32, torch defaults: no TF32 matmul) -- config A as it is, config B at batch 2 (batch 16 needs
+    ~40 GB of L x L temporaries per layer set).  One optimizer step per iteration, CUDA-event timed."""
+    import torch
+    out = {}
+    for name, cfg, batch in (("config_A_batch2", "A", 2), ("config_B_batch2", "B", 2)):
+        try:
+            step, kind, tokens = reference_train_step(cfg, dev, batch, dropout)
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 5
+            e0.record()
+            for _ in range(n):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            out[name] = {"ms_per_step": ms, "tokens_per_s": tokens / (ms / 1e3), "kind": kind, "batch": batch,
+                         "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+        except Exception as e:                  # noqa: BLE001
+            out[name] = {"error": str(e)[:200]}
+        finally:
+            step = None
+            torch.cuda.empty_cache()
+    out["what"] = ("unmodified reference modules .to(cuda), eager PyTorch fp32, fwd+loss+bwd+Adam per step, "
+                   "same B200 as the line's value")
+    return out
 
 
 def run_ours(args):
@@ -329,11 +447,7 @@ def run_ours(args):
             "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
             "data": "synthetic",
-            "config": {"workload": f"MusicTransformer config {args.config}: V={V} {layers}L d{d} h{h} "
-                                   f"L={L} batch {Bg}/GPU, dropout {args.dropout}, fwd+loss+bwd+"
-                                   f"{'allreduce+' if world > 1 else ''}Adam",
-                       "global_batch": Bg * world, "seq_len": L, "parallelism": f"dp{world}",
-                       "l2": "per-step activations (several GB) exceed the 126 MB L2; no flush needed"},
+            "config": workload_config(args.config, Bg, world, args.dropout),
             "clocks": clocks,
             "e2e": {"value": tokens * K / e2e_s, "unit": "tokens/s",
                     "h2d_bytes_per_step": 2 * Bg * L * 4, "d2h_bytes_per_step": 4, "last_loss": last,
@@ -369,7 +483,11 @@ def run_ours(args):
                               "hbm_frac": (kv + wts) * dec["events"] / (dec["ms"] / 1e3) / 1e9 / pk["hbm"],
                               "scaling": "sequences sharded over ranks, no collective"}
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline_leg(args.config)
+            line["cpu_baseline"] = cpu_baseline_leg(args.config, args.dropout)
+        if world == 1 and not args.no_eager:
+            del model, opt, sched
+            torch.cuda.empty_cache()
+            line["gpu_eager_baseline"] = gpu_eager_leg(dev, args.dropout)
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -470,6 +588,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip the eager-CUDA reference comparator (N = 1 only)")
     ap.add_argument("--decode-seqs", type=int, default=32)
     ap.add_argument("--decode-events", type=int, default=2047)
     ap.add_argument("--sweep", action="store_true", help="relative-attention microbench sweep (configs[4])")

@@ -50,6 +50,13 @@ inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_
 inline int dtype_size(int dt) { return dt == MT_F32 ? 4 : 2; }
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 int sm_count();
+// cudaFuncSetAttribute is per DEVICE: launchers remember the devices they have configured as a bit mask
+// (bit = device ordinal), not as one process-wide flag
+inline unsigned long long attr_dev_bit() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return 1ull << (dev & 63);
+}
 
 // ---------------------------------------------------------------------------------------
 // dtype conversion

@@ -821,10 +821,10 @@ int gemm_tc(const void* A, const void* B, void* C, const float* bias, const floa
 #define MT_PS_LAUNCH(BMJ, BNC)                                                                        \
     {                                                                                                 \
       auto kern = gemm_tc_persist_kernel<BMJ, BNC>;                                                   \
-      static bool attr_done = false;                                                                  \
-      if (!attr_done) {                                                                               \
+      static unsigned long long attr_done = 0; const unsigned long long attr_bit = attr_dev_bit();                                                                  \
+      if (!(attr_done & attr_bit)) {                                                                               \
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PShape<BNC>::SMEM); \
-        attr_done = (e == cudaSuccess);                                                               \
+        if (e == cudaSuccess) attr_done |= attr_bit;                                                               \
       }                                                                                               \
       if (e == cudaSuccess) kern<<<pgrid, PS_THREADS, PShape<BNC>::SMEM, stream>>>(tmA, tmB, p, fmt, tiles_n, num_tiles); \
     }
@@ -838,10 +838,10 @@ int gemm_tc(const void* A, const void* B, void* C, const float* bias, const floa
 #define MT_TC_LAUNCH(AM, BMJ, BNC)                                                                    \
   {                                                                                                   \
     auto kern = gemm_tc_kernel<AM, BMJ, BNC>;                                                         \
-    static bool attr_done = false;                                                                    \
-    if (!attr_done) {                                                                                 \
+    static unsigned long long attr_done = 0; const unsigned long long attr_bit = attr_dev_bit();                                                                    \
+    if (!(attr_done & attr_bit)) {                                                                                 \
       e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape<BNC>::SMEM); \
-      attr_done = (e == cudaSuccess);                                                                 \
+      if (e == cudaSuccess) attr_done |= attr_bit;                                                                 \
     }                                                                                                 \
     if (e == cudaSuccess) kern<<<grid, TC_THREADS, Shape<BNC>::SMEM, stream>>>(tmA, tmB, p, fmt);     \
   }
@@ -850,10 +850,10 @@ int gemm_tc(const void* A, const void* B, void* C, const float* bias, const floa
   else if (a_mn && b_mn) {
     if (p.cs_out) {
       auto kern = gemm_tc_kernel<1, 1, 128, true>;
-      static bool attr_done = false;
-      if (!attr_done) {
+      static unsigned long long attr_done = 0; const unsigned long long attr_bit = attr_dev_bit();
+      if (!(attr_done & attr_bit)) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape<128>::SMEM);
-        attr_done = (e == cudaSuccess);
+        if (e == cudaSuccess) attr_done |= attr_bit;
       }
       if (e == cudaSuccess) kern<<<grid, TC_THREADS, Shape<128>::SMEM, stream>>>(tmA, tmB, p, fmt);
     } else if (wide) MT_TC_LAUNCH(1, 1, 256) else MT_TC_LAUNCH(1, 1, 128)

@@ -427,11 +427,11 @@ int rga_fwd_tc(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
   p.fmt = (dtype == MT_BF16) ? 1 : 0;
   p.ofmt = (dtype == MT_F16) ? 0 : 1;
   p.scale_log2 = LOG2E / a.inv_scale_div;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0; const unsigned long long attr_bit = attr_dev_bit();
+  if (!(attr_done & attr_bit)) {
     cudaError_t e = cudaFuncSetAttribute(rga_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
     if (e != cudaSuccess) { set_error("rga_fwd_tc: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_done = true;
+    attr_done |= attr_bit;
   }
   // consecutive heads of one (batch row, query tile) share a CTA: same number of key tiles, same E blocks; the
   // per-CTA fixed cost (launch, TMEM allocation, barrier set-up, pipeline fill) is paid once per pair

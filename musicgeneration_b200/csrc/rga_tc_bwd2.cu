@@ -1053,11 +1053,11 @@ template <int ROLE, bool HF = false>
 int launch_role2(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmDO,
                  const CUtensorMap& tmE, const Bwd2Params& p, dim3 grid, cudaStream_t st) {
   auto kern = rga_bwd2_kernel<ROLE, HF>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0; const unsigned long long attr_bit = attr_dev_bit();
+  if (!(attr_done & attr_bit)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_bytes<ROLE>());
     if (e != cudaSuccess) { set_error("rga_bwd2: smem attribute (%d B): %s", smem2_bytes<ROLE>(), cudaGetErrorString(e)); return (int)e; }
-    attr_done = true;
+    attr_done |= attr_bit;
   }
   Bwd2Params q = p;
   static const bool want_trace = getenv("MT_RGA_TRACE") != nullptr;

@@ -385,11 +385,11 @@ rga_bwd3_kernel(const __grid_constant__ CUtensorMap tmX,      // K (dQ role) or 
 template <int ROLE>
 int launch_role3(const CUtensorMap& tmX, const CUtensorMap& tmE, const Bwd3Params& p, dim3 grid, cudaStream_t st) {
   auto kern = rga_bwd3_kernel<ROLE>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0; const unsigned long long attr_bit = attr_dev_bit();
+  if (!(attr_done & attr_bit)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3_bytes<ROLE>());
     if (e != cudaSuccess) { set_error("rga_bwd3: smem attribute (%d B): %s", smem3_bytes<ROLE>(), cudaGetErrorString(e)); return (int)e; }
-    attr_done = true;
+    attr_done |= attr_bit;
   }
   Bwd3Params q = p;
   static const bool want_trace = getenv("MT_RGA_TRACE") != nullptr;

@@ -80,7 +80,11 @@ class Data:
         self.arena = host.to(self.device, non_blocking=True)
         self.file_off = torch.from_numpy(off).to(self.device)
         self._starts_host = None
-        self._sampler_seed = seed
+        self._starts_slot = 0
+        # the device sampler is keyed by (seed, step): mix the data-parallel rank in, so that the replicas of a
+        # one-process-per-GPU job draw DIFFERENT files and windows under the default seed (the host-drawn path
+        # follows Python's `random`, which the caller seeds per rank exactly as with the reference)
+        self._sampler_seed = (int(seed) + 0x9E3779B97F4A7C15 * int(os.environ.get("RANK", "0"))) & 0xFFFFFFFFFFFFFFFF
         self._sampler_step = 0
         self._eligible = {}
         torch.cuda.current_stream(self.device).synchronize()      # the pinned staging buffer may go now
@@ -105,12 +109,34 @@ class Data:
                 raise IndexError
         return starts, batch_files
 
+    _RING = 4       # pinned staging slots for the window starts
+
     def _starts_to_device(self, starts: np.ndarray) -> torch.Tensor:
+        """Host window starts -> device.  The copy is asynchronous and the train loop lets the host run ahead of
+        the GPU, so ONE pinned buffer could be refilled with the next batch's starts before the queued copy of the
+        previous batch had run (batch N would train on batch N+1's windows).  A ring of pinned slots, each guarded
+        by an event recorded after its copy, closes that: a slot is rewritten only once its last copy has run."""
         B = starts.size
-        if self._starts_host is None or self._starts_host.numel() < B:
-            self._starts_host = torch.empty(max(B, 64), dtype=torch.int64).pin_memory()
-        self._starts_host[:B].copy_(torch.from_numpy(starts))
-        return self._starts_host[:B].to(self.device, non_blocking=True)
+        ring = self._starts_host
+        if ring is None or ring[0][0].numel() < B:
+            if ring is not None:
+                for _, ev in ring:
+                    if ev is not None:
+                        ev.synchronize()
+            ring = self._starts_host = [[torch.empty(max(B, 64), dtype=torch.int64).pin_memory(), None]
+                                        for _ in range(self._RING)]
+            self._starts_slot = 0
+        slot = ring[self._starts_slot]
+        self._starts_slot = (self._starts_slot + 1) % self._RING
+        if slot[1] is not None:
+            slot[1].synchronize()                      # the copy that last read this slot has completed
+        slot[0][:B].copy_(torch.from_numpy(starts))
+        with torch.cuda.device(self.device):
+            out = slot[0][:B].to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        slot[1] = ev
+        return out
 
     def _gather(self, starts_dev: torch.Tensor, x_len: int, y_len: int = 0, y_shift: int = 0):
         B = starts_dev.numel()

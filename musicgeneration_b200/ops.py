@@ -32,7 +32,8 @@ _cur_device = torch.cuda.current_device
 def _stream():
     """cudaStream_t of torch's current stream on the current device.  (The public
     torch.cuda.current_stream() builds a Stream object through four Python layers: 14 us per call, a
-    quarter of the host time of a train step at ~140 calls.)"""
+    quarter of the host time of a train step at ~140 calls.)  The library launches on the CURRENT device
+    (include/mt_b200.h); _need_cuda() checks that the tensors live there."""
     LAUNCH_CALLS[0] += 1
     if _raw_stream is not None:
         return _raw_stream(_cur_device())
@@ -40,10 +41,20 @@ def _stream():
 
 
 def _need_cuda(*ts):
+    cur = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("musicgeneration_b200 runs on CUDA tensors only (no CPU fallback); "
                                "move the module and its inputs to a B200 device")
+        if cur is None:
+            cur = _cur_device()
+        if t.device.index != cur:
+            # kernels are enqueued on the current device's stream: a tensor of another device would be
+            # dereferenced in the wrong context (one process per GPU is the supported layout)
+            raise RuntimeError(f"musicgeneration_b200: tensor on cuda:{t.device.index} but the current device is "
+                               f"cuda:{cur}; wrap the call in torch.cuda.device(...) or call torch.cuda.set_device")
 
 
 _ws_cache = {}

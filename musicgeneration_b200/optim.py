@@ -49,11 +49,17 @@ class FlatAdam:
                 seen.add(id(p))
                 order.append(p)
 
-        # keep Wq/Wk/Wv weights (and biases) adjacent: the packed [3d, d] operand of the QKV GEMM
+        # keep Wq/Wk/Wv weights (and biases) adjacent: the packed [3d, d] operand of the QKV GEMM.  A triple
+        # shares ONE slot (padding only after it), so adjacency holds for every d, not only d % 64 == 0
+        glue = set()            # ids of parameters that must directly follow their predecessor (no padding between)
         for mod in model.modules():
             if isinstance(mod, RelativeGlobalAttention):
-                for p in (mod.Wq.weight, mod.Wk.weight, mod.Wv.weight, mod.Wq.bias, mod.Wk.bias, mod.Wv.bias):
-                    add(p)
+                for trip in ((mod.Wq.weight, mod.Wk.weight, mod.Wv.weight), (mod.Wq.bias, mod.Wk.bias, mod.Wv.bias)):
+                    if all(id(p) not in seen and p.requires_grad for p in trip):
+                        for i, p in enumerate(trip):
+                            add(p)
+                            if i:
+                                glue.add(id(p))
         for p in model.parameters():
             add(p)
         self.params = order
@@ -61,18 +67,25 @@ class FlatAdam:
         dev = order[0].device
         if dev.type != "cuda":
             raise RuntimeError("FlatAdam needs the model on a CUDA device (no CPU fallback)")
-        sizes = [(p.numel() + 63) // 64 * 64 for p in order]    # 256-byte aligned fp32 slots = 128-byte aligned slots of the 16-bit shadow (TMA needs 16)
+        # 256-byte aligned fp32 slots = 128-byte aligned slots of the 16-bit shadow (TMA needs 16)
+        sizes = []
+        for i, p in enumerate(order):
+            last_of_group = i + 1 == len(order) or id(order[i + 1]) not in glue
+            sizes.append((p.numel() + 63) // 64 * 64 if last_of_group else p.numel())
+        # a glued group starts 64-aligned because every group END is padded; inside, offsets follow numel
         self.n = sum(sizes)
         self.flat_p = torch.zeros(self.n, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(self.n, dtype=torch.float32, device=dev)
         self.m = torch.zeros(self.n, dtype=torch.float32, device=dev)
         self.v = torch.zeros(self.n, dtype=torch.float32, device=dev)
         off = 0
+        self._offsets = []
         for p, sz in zip(order, sizes):
             view = self.flat_p[off:off + p.numel()].view(p.shape)
             view.copy_(p.data)
             p.data = view
             p.grad = self.flat_g[off:off + p.numel()].view(p.shape)
+            self._offsets.append(off)
             off += sz
         # Kernels may write a gradient straight into its flat_g view (instead of handing a temporary
         # to autograd, which then launches one `grad += tmp` per parameter) as long as that view is
@@ -81,14 +94,41 @@ class FlatAdam:
         self.flat_lp = None           # 16-bit shadow of flat_p, (re)written by refresh_lp()
         for p in order:
             p._mt_opt = self
+            # a gradient written by autograd's own accumulation (a second loss, a standalone layer backward) makes
+            # the view non-zero: kernels must then accumulate through autograd again instead of assigning
+            p.register_post_accumulate_grad_hook(lambda q, _s=self: _s.fresh.discard(id(q)))
         self.lr, self.betas, self.eps = lr, betas, eps
         self.param_groups = [{"lr": lr, "params": order}]     # what CustomSchedule.step() touches
         self.step_count = 0
         self.pg = process_group
         self.grad_accum = grad_accum
 
+    def _rebind(self):
+        """p.grad must alias flat_g and p.data flat_p (step() and the all-reduce read the flat buffers).
+        ``model.zero_grad()`` defaults to set_to_none=True in current torch, after which autograd allocates fresh
+        .grad tensors elsewhere: fold such a gradient into its view and point .grad back at it.  A parameter whose
+        DATA no longer lives in flat_p (re-assigned behind the optimizer's back) would silently stop training."""
+        gbase, pbase = self.flat_g.data_ptr(), self.flat_p.data_ptr()
+        for p, off in zip(self.params, self._offsets):
+            if p.data.data_ptr() != pbase + 4 * off:
+                raise RuntimeError("FlatAdam: a parameter's data no longer aliases the flat parameter buffer "
+                                   "(param.data was re-assigned after the optimizer was built)")
+            g = p.grad
+            if g is not None and g.data_ptr() == gbase + 4 * off:
+                continue
+            view = self.flat_g[off:off + p.numel()].view(p.shape)
+            if g is not None:
+                view.add_(g.to(view.dtype))
+                self.fresh.discard(id(p))
+            p.grad = view
+
     def zero_grad(self, set_to_none: bool = False):
+        """Always keeps the gradients as (zeroed) views of the flat buffer; ``set_to_none`` is accepted for
+        torch.optim compatibility and ignored."""
         self.flat_g.zero_()
+        for p, off in zip(self.params, self._offsets):
+            if p.grad is None or p.grad.data_ptr() != self.flat_g.data_ptr() + 4 * off:
+                p.grad = self.flat_g[off:off + p.numel()].view(p.shape)
         self.fresh = {id(p) for p in self.params}
 
     def refresh_lp(self, act: torch.dtype) -> None:
@@ -104,6 +144,7 @@ class FlatAdam:
         return all_reduce_flat_(self.flat_g, self.pg)
 
     def step(self):
+        self._rebind()
         world = self.all_reduce_grads()
         self.step_count += 1
         lr = float(self.param_groups[0]["lr"])

@@ -13,6 +13,7 @@ names so they cannot clash with our own ``utils``/``config``.
 """
 from __future__ import annotations
 
+import importlib.machinery
 import importlib.util
 import os
 import sys
@@ -22,13 +23,34 @@ _CANDIDATES = [
     os.environ.get("MT_REFERENCE_DIR", ""),
     "/root/reference/mg/model/MusicTransformer",
 ]
+# byte-compiled copy of the same files (oracle/make_ref.py): what exists on the GPU box
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "MusicTransformer")
 
 
 def reference_dir() -> str | None:
+    """Directory of the reference SOURCES (build container only)."""
     for c in _CANDIDATES:
         if c and os.path.isfile(os.path.join(c, "layers.py")):
             return os.path.abspath(c)
     return None
+
+
+def staged_dir() -> str | None:
+    """Directory of the compiled reference modules staged by oracle/make_ref.py, if built for this interpreter."""
+    man = os.path.join(_STAGED, "MANIFEST.json")
+    if not os.path.isfile(man):
+        return None
+    try:
+        import json
+        with open(man) as f:
+            magic = json.load(f).get("magic")
+    except Exception:
+        return None
+    return _STAGED if magic == importlib.util.MAGIC_NUMBER.hex() else None
+
+
+def reference_available() -> bool:
+    return reference_dir() is not None or staged_dir() is not None
 
 
 def _install_stubs() -> None:
@@ -74,8 +96,12 @@ def load_reference() -> types.SimpleNamespace:
     if _CACHE is not None:
         return _CACHE
     d = reference_dir()
+    ext = ".py"
     if d is None:
-        raise FileNotFoundError("reference MusicTransformer sources not found")
+        d, ext = staged_dir(), ".pyc"
+    if d is None:
+        raise FileNotFoundError("reference MusicTransformer not found (neither the sources nor the compiled "
+                                "modules of oracle/make_ref.py)")
     _install_stubs()
     # The reference's bare-name imports need its directory on sys.path while loading; we
     # import under the bare names (that is what the files themselves do) but snapshot and
@@ -87,7 +113,9 @@ def load_reference() -> types.SimpleNamespace:
     try:
         mods = {}
         for n in bare:
-            spec = importlib.util.spec_from_file_location(n, os.path.join(d, n + ".py"))
+            path = os.path.join(d, n + ext)
+            loader = importlib.machinery.SourcelessFileLoader(n, path) if ext == ".pyc" else None
+            spec = importlib.util.spec_from_file_location(n, path, loader=loader)
             mod = importlib.util.module_from_spec(spec)
             sys.modules[n] = mod
             spec.loader.exec_module(mod)
@@ -101,5 +129,5 @@ def load_reference() -> types.SimpleNamespace:
         sys.modules.update(saved)
     # the reference modules look each other up through their own globals (already bound),
     # so removing the bare names from sys.modules is safe.
-    _CACHE = types.SimpleNamespace(dir=d, **mods)
+    _CACHE = types.SimpleNamespace(dir=d, compiled=(ext == ".pyc"), **mods)
     return _CACHE

@@ -64,6 +64,25 @@ def test_against_oracle_same_box(tmp_path, dtype, vocab):
         assert (x.cpu().numpy() == qx).all() and (y.cpu().numpy() == qy).all()
 
 
+def test_batches_queued_behind_a_busy_gpu_keep_their_own_windows(tmp_path):
+    """The train loop lets the host run ahead of the GPU: many batches are drawn while earlier work is still
+    queued.  Every batch must see ITS window starts (a single reused pinned staging buffer would hand batch
+    N the starts of batch N+1; data.Data stages through an event-guarded ring)."""
+    O.write_token_corpus(str(tmp_path), n_files=40, seed=3)
+    D = mdata.Data(str(tmp_path), 30)
+    Q = O.DataOracle(str(tmp_path), 30)
+    a = torch.randn(4096, 4096, device="cuda")
+    random.seed(5)
+    for _ in range(60):                      # ~100 ms of queued GPU work ahead of the copies
+        a = (a @ a).clamp_(-1, 1)
+    got = [D.slide_seq2seq_batch_device(6, 40) for _ in range(12)]      # no sync in between
+    torch.cuda.synchronize()
+    random.seed(5)
+    for x, y in got:
+        qx, qy = Q.slide_seq2seq_batch(6, 40)
+        assert (x.cpu().numpy() == qx).all() and (y.cpu().numpy() == qy).all()
+
+
 def test_errors_like_reference(tmp_path):
     O.write_token_corpus(str(tmp_path), n_files=10, seed=1, lo=70, hi=90)
     D = mdata.Data(str(tmp_path), 30)

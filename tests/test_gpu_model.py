@@ -105,6 +105,42 @@ def test_flat_adam_gradients_written_in_place_match_fixture():
     assert rel(opt.flat_g.cpu(), once.cpu()) < 1e-6
 
 
+def test_flat_adam_survives_set_to_none_and_earlier_autograd_writes():
+    """(1) model.zero_grad() (set_to_none=True by default in torch) detaches .grad from the flat buffer: step()
+    folds the fresh gradients back and trains on them.  (2) a gradient autograd accumulated BEFORE the model's
+    backward (an auxiliary loss on shared parameters) must survive the kernels' in-place gradient writes."""
+    import musicgeneration_b200 as mtb
+    from musicgeneration_b200.optim import FlatAdam
+    dev = torch.device("cuda:0")
+    z = load("train_small.npz")
+    m, (d, V, pad, layers, L) = build_model(z, dev)
+    x, y = torch.from_numpy(z["x"]).to(dev), torch.from_numpy(z["y"]).to(dev)
+    m.train()
+    opt = FlatAdam(m, lr=1e-3)
+    crit = mtb.SmoothCrossEntropyLoss(0.1, V, pad)
+    # (1)
+    m.zero_grad()                                   # set_to_none=True
+    assert all(p.grad is None for p in m.parameters())
+    crit(m(x), y).backward()
+    before = opt.flat_p.clone()
+    opt.step()
+    for k, p in m.named_parameters():
+        g = z["g:" + k]
+        assert p.grad.data_ptr() >= opt.flat_g.data_ptr() and \
+            p.grad.data_ptr() < opt.flat_g.data_ptr() + opt.flat_g.numel() * 4, k
+        assert np.abs(p.grad.cpu().numpy() - g).max() <= 2e-6 + 3e-4 * np.abs(g).max(), k
+    assert float((opt.flat_p - before).abs().max()) > 0
+    # (2)
+    m.load_state_dict(params_of(z), strict=True)
+    opt.zero_grad()
+    aux = 0.5 * sum((p ** 2).sum() for p in m.parameters())       # d aux / dp = p
+    aux.backward()
+    crit(m(x), y).backward()
+    for k, p in m.named_parameters():
+        want = z["g:" + k] + z["p:" + k]
+        assert np.abs(p.grad.cpu().numpy() - want).max() <= 3e-6 + 3e-4 * np.abs(want).max(), k
+
+
 def test_train_small_eval_returns_attention_weights():
     dev = torch.device("cuda:0")
     z = load("train_small.npz")

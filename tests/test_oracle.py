@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import restate as O
-from oracle.ref_import import reference_dir
+from oracle.ref_import import reference_available, reference_dir
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -164,9 +164,39 @@ def test_sampler_semantics():
     assert (freq - pr).abs().max() < 0.03
 
 
-@pytest.mark.skipif(reference_dir() is None, reason="reference tree not present")
+def test_staged_reference_is_the_reference(tmp_path):
+    """oracle/make_ref.py byte-compiles the reference's own files; the staged modules load WITHOUT the source
+    tree (a fresh interpreter with the source candidates removed) and compute what the sources compute."""
+    import subprocess
+    import sys
+    from oracle import make_ref
+    from oracle.ref_import import staged_dir
+    if reference_dir() is not None:
+        assert make_ref.build(verbose=False) is not None
+    if staged_dir() is None:
+        pytest.skip("no staged reference (and no sources to stage it from)")
+    code = (
+        "import sys, torch; sys.path.insert(0, %r)\n"
+        "import oracle.ref_import as ri\n"
+        "ri._CANDIDATES[:] = []\n"
+        "R = ri.load_reference(); assert R.compiled\n"
+        "R.config.pad_token = 70\n"
+        "torch.manual_seed(11)\n"
+        "m = R.network.MusicTransformer(embedding_dim=192, vocab_size=72, num_layer=2, max_seq=32, dropout=0.0)\n"
+        "from oracle import restate as O\n"
+        "x, y = O.synthetic_ids(2, 32, 70, seed=5)\n"
+        "m.train(); ref = m(x)\n"
+        "ours = O.model_forward(x, {k: v.detach() for k, v in m.state_dict().items()}, 32, 70)\n"
+        "assert (ref - ours).abs().max() < 2e-5\n"
+        "print('staged ok')\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "staged ok" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.skipif(not reference_available(), reason="neither the reference tree nor its staged modules are present")
 def test_live_reference_matches_oracle():
-    """Re-run the live comparison (different seed/shape from the fixture) when possible."""
+    """Re-run the live comparison (different seed/shape from the fixture) when possible: in the build container
+    against the sources, on the GPU box against the compiled modules oracle/make_ref.py staged."""
     from oracle.ref_import import load_reference
     R = load_reference()
     R.config.pad_token = 70

@@ -4,7 +4,7 @@
 
 The reference path (``/root/reference/mg/model/MusicTransformer``) is pure Python, so "building" it means
 byte-compiling its own source files where they lie: every module the path imports is compiled with
-``py_compile`` straight from ``/root/reference`` into ``oracle/_ref/MusicTransformer/<name>.pyc``.  No
+``py_compile`` straight from ``/root/reference`` into ``oracle/_ref/MusicTransformer/<name>.bytecode`` (pyc format; the extension keeps snapshot tools that drop ``*.pyc`` from losing it).  No
 reference SOURCE is copied into this repository; ``oracle/_ref/`` is a build output (git-ignored, but it
 travels to the GPU box with the snapshot like the built ``.so``).  ``oracle/ref_import.py`` loads the
 compiled modules when the source tree is absent, which is what lets ``bench.py --impl reference`` and the
@@ -41,7 +41,7 @@ def build(verbose: bool = True) -> str | None:
         with open(src, "rb") as f:
             digest = hashlib.sha256(f.read()).hexdigest()
         # dfile: tracebacks keep pointing at the reference file the bytecode was compiled from
-        py_compile.compile(src, cfile=os.path.join(OUT, name + ".pyc"), dfile=src, doraise=True)
+        py_compile.compile(src, cfile=os.path.join(OUT, name + ".bytecode"), dfile=src, doraise=True)
         manifest["modules"][name] = digest
     with open(os.path.join(OUT, "MANIFEST.json"), "w") as f:
         json.dump(manifest, f, indent=1)

@@ -98,7 +98,7 @@ def load_reference() -> types.SimpleNamespace:
     d = reference_dir()
     ext = ".py"
     if d is None:
-        d, ext = staged_dir(), ".pyc"
+        d, ext = staged_dir(), ".bytecode"
     if d is None:
         raise FileNotFoundError("reference MusicTransformer not found (neither the sources nor the compiled "
                                 "modules of oracle/make_ref.py)")
@@ -114,7 +114,7 @@ def load_reference() -> types.SimpleNamespace:
         mods = {}
         for n in bare:
             path = os.path.join(d, n + ext)
-            loader = importlib.machinery.SourcelessFileLoader(n, path) if ext == ".pyc" else None
+            loader = importlib.machinery.SourcelessFileLoader(n, path) if ext != ".py" else None
             spec = importlib.util.spec_from_file_location(n, path, loader=loader)
             mod = importlib.util.module_from_spec(spec)
             sys.modules[n] = mod
@@ -129,5 +129,5 @@ def load_reference() -> types.SimpleNamespace:
         sys.modules.update(saved)
     # the reference modules look each other up through their own globals (already bound),
     # so removing the bare names from sys.modules is safe.
-    _CACHE = types.SimpleNamespace(dir=d, compiled=(ext == ".pyc"), **mods)
+    _CACHE = types.SimpleNamespace(dir=d, compiled=(ext != ".py"), **mods)
     return _CACHE

@@ -75,11 +75,11 @@ def test_batches_queued_behind_a_busy_gpu_keep_their_own_windows(tmp_path):
     random.seed(5)
     for _ in range(60):                      # ~100 ms of queued GPU work ahead of the copies
         a = (a @ a).clamp_(-1, 1)
-    got = [D.slide_seq2seq_batch_device(6, 40) for _ in range(12)]      # no sync in between
+    got = [D.slide_seq2seq_batch_device(6, 29) for _ in range(12)]      # no sync in between
     torch.cuda.synchronize()
     random.seed(5)
     for x, y in got:
-        qx, qy = Q.slide_seq2seq_batch(6, 40)
+        qx, qy = Q.slide_seq2seq_batch(6, 29)
         assert (x.cpu().numpy() == qx).all() and (y.cpu().numpy() == qy).all()
 
 

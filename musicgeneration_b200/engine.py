@@ -328,14 +328,18 @@ def encoder_fwd(ids: torch.Tensor, emb: torch.Tensor, pe: torch.Tensor, Ws: List
 
 def encoder_bwd(dhid: torch.Tensor, saved, Ws: List[LayerWeights], cfg: StackCfg, V: int,
                 dsts: Optional[List[Optional[Dict[str, torch.Tensor]]]] = None,
-                demb_dst: Optional[torch.Tensor] = None):
+                demb_dst: Optional[torch.Tensor] = None, on_layer_done=None):
     """dhid [T,d] f32 -> (demb [V,d] f32, [layer grad dicts]).  ``dsts`` / ``demb_dst``: zeroed
-    gradient buffers to write into (see layer_bwd)."""
+    gradient buffers to write into (see layer_bwd).  ``on_layer_done(li)`` is called once layer li's
+    backward kernels have been enqueued (its gradients are final in stream order: the data-parallel exchange
+    of that layer's bucket may start while the earlier layers' backward runs)."""
     dx = dhid
     layer_grads: List[Dict[str, torch.Tensor]] = [None] * len(Ws)
     for li in range(len(Ws) - 1, -1, -1):
         dx, layer_grads[li] = layer_bwd(dx, saved["layers"][li], Ws[li], cfg,
                                         dst=dsts[li] if dsts is not None else None)
+        if on_layer_done is not None:
+            on_layer_done(li)
     demb = demb_dst if demb_dst is not None else \
         torch.zeros((V, cfg.d), dtype=torch.float32, device=dhid.device)
     ops.embed_pos_bwd(saved["ids"], dx, demb, math.sqrt(cfg.d), saved["p"], saved["seed"], 0)

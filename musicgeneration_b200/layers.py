@@ -476,8 +476,16 @@ class _EncoderFunction(torch.autograd.Function):
         # freshly zeroed); autograd then gets None for those parameters
         dsts = [layer_direct_dst(l) for l in enc.enc_layers]
         emb_dst = _claim_direct([enc.embedding.weight])
+        opt = getattr(enc.embedding.weight, "_mt_opt", None)
+
+        def layer_done(li):          # data-parallel: this layer's gradient bucket may go on the wire now
+            if opt is not None and dsts[li] is not None:
+                opt.grads_ready(enc.enc_layers[li].params())
+
         demb, lg = engine.encoder_bwd(_as_f32_2d(d_hid, d).clone(), ctx.saved, ctx.Ws, ctx.cfg, ctx.V,
-                                      dsts=dsts, demb_dst=emb_dst[0] if emb_dst else None)
+                                      dsts=dsts, demb_dst=emb_dst[0] if emb_dst else None, on_layer_done=layer_done)
+        if opt is not None and emb_dst:
+            opt.grads_ready([enc.embedding.weight])
         grads = (None,) if emb_dst else (demb,)
         for g, dst in zip(lg, dsts):
             grads += (None,) * N_LAYER_PARAMS if dst is not None else layer_grads_in_param_order(g, d)
@@ -520,6 +528,8 @@ class _LinearFunction(torch.autograd.Function):
         dW = direct[0] if direct else torch.empty((N, K), dtype=torch.float32, device=dy.device)
         db = direct[1] if direct else torch.empty((N,), dtype=torch.float32, device=dy.device)
         engine.linear_wgrad(dy, xa, dW, db, cfg)
+        if direct:
+            ctx.weight._mt_opt.grads_ready([ctx.weight, ctx.bias])
         dx = torch.empty((T, K), dtype=torch.float32, device=dy.device)
         engine.linear_dgrad(dy, Wa, dx, cfg)
         return (None, dx.view(ctx.shape), None, None) if direct else (None, dx.view(ctx.shape), dW, db)

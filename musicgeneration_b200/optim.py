@@ -52,16 +52,24 @@ class FlatAdam:
         # keep Wq/Wk/Wv weights (and biases) adjacent: the packed [3d, d] operand of the QKV GEMM.  A triple
         # shares ONE slot (padding only after it), so adjacency holds for every d, not only d % 64 == 0
         glue = set()            # ids of parameters that must directly follow their predecessor (no padding between)
+        # ... emitted at the position of the triple's first member in model.parameters() order, so every encoder
+        # layer's parameters stay one contiguous range of the flat buffers (= one gradient-exchange bucket)
+        trip_of = {}
         for mod in model.modules():
             if isinstance(mod, RelativeGlobalAttention):
                 for trip in ((mod.Wq.weight, mod.Wk.weight, mod.Wv.weight), (mod.Wq.bias, mod.Wk.bias, mod.Wv.bias)):
-                    if all(id(p) not in seen and p.requires_grad for p in trip):
-                        for i, p in enumerate(trip):
-                            add(p)
-                            if i:
-                                glue.add(id(p))
+                    if all(p.requires_grad for p in trip):
+                        for p in trip:
+                            trip_of[id(p)] = trip
         for p in model.parameters():
-            add(p)
+            trip = trip_of.get(id(p))
+            if trip is not None and all(id(q) not in seen for q in trip):
+                for i, q in enumerate(trip):
+                    add(q)
+                    if i:
+                        glue.add(id(q))
+            else:
+                add(p)
         self.params = order
         self._model_order = [p for p in model.parameters() if p.requires_grad]
         dev = order[0].device
@@ -92,16 +100,70 @@ class FlatAdam:
         # known to be zero: ``fresh`` holds the ids of the parameters not written since zero_grad().
         self.fresh = set()
         self.flat_lp = None           # 16-bit shadow of flat_p, (re)written by refresh_lp()
+        # ---- gradient-exchange buckets: the backward finishes the vocabulary projection first, then
+        # the encoder layers last to first, then the embedding; a bucket = one layer's contiguous range (the
+        # embedding rides with layer 0, the vocabulary projection is its own bucket).  Models without
+        # ``enc_layers.<i>.`` parameter names get a single bucket.
+        import re
+        names = {id(p): n for n, p in model.named_parameters()}
+        key_of = []
+        for p in order:
+            mname = re.search(r"enc_layers\.(\d+)\.", names.get(id(p), ""))
+            key_of.append(int(mname.group(1)) if mname else None)
+        first_layer = next((k for k in key_of if k is not None), None)
+        cur, keys = (first_layer if first_layer is not None else 0), []
+        seen_layer = False
+        for k in key_of:
+            if k is not None:
+                cur, seen_layer = k, True
+            elif seen_layer:
+                cur = 1 << 30                 # parameters after the last layer (the vocabulary projection)
+            keys.append(cur)
+        self._bucket_of, bounds = {}, {}
+        for p, off, sz, k in zip(order, self._offsets, sizes, keys):
+            lo, hi = bounds.get(k, (off, off))
+            bounds[k] = (min(lo, off), max(hi, off + sz))
+        self._bucket_keys = sorted(bounds)
+        for p, k in zip(order, keys):
+            self._bucket_of[id(p)] = self._bucket_keys.index(k)
+        from .parallel import BucketedExchange
+        self.exchange = BucketedExchange(self.flat_g, [bounds[k] for k in self._bucket_keys], process_group)
+        self._bucket_size = [sum(1 for p in order if self._bucket_of[id(p)] == b) for b in range(len(self._bucket_keys))]
+        self._bucket_ready = [set() for _ in self._bucket_keys]
+        self.ready_order = []         # buckets in the order the backward completed them (since the last zero_grad)
+        self.sync_grads = True        # False on the non-final micro-batches of an accumulation window (DDP no_sync)
         for p in order:
             p._mt_opt = self
             # a gradient written by autograd's own accumulation (a second loss, a standalone layer backward) makes
             # the view non-zero: kernels must then accumulate through autograd again instead of assigning
-            p.register_post_accumulate_grad_hook(lambda q, _s=self: _s.fresh.discard(id(q)))
+            p.register_post_accumulate_grad_hook(lambda q, _s=self: _s._autograd_wrote(q))
         self.lr, self.betas, self.eps = lr, betas, eps
         self.param_groups = [{"lr": lr, "params": order}]     # what CustomSchedule.step() touches
         self.step_count = 0
         self.pg = process_group
         self.grad_accum = grad_accum
+
+    def _autograd_wrote(self, p):
+        self.fresh.discard(id(p))
+        if self.exchange.started[self._bucket_of[id(p)]]:
+            raise RuntimeError("FlatAdam: a gradient was accumulated after its bucket's all-reduce had started "
+                               "(second backward without zero_grad(), with the overlapped exchange on); set "
+                               "opt.sync_grads = False for all but the last backward of the window")
+
+    def grads_ready(self, params) -> None:
+        """The kernels that write the FINAL gradients of ``params`` (directly into the flat buffer) have been
+        enqueued: once that holds for every parameter of a bucket, its all-reduce starts (overlapping the rest
+        of the backward).  Called by the backward functions of layers.py; a no-op on one rank."""
+        if not self.sync_grads or self.exchange is None:
+            return
+        for p in params:
+            b = self._bucket_of.get(id(p))
+            if b is None:
+                continue
+            self._bucket_ready[b].add(id(p))
+            if len(self._bucket_ready[b]) == self._bucket_size[b] and b not in self.ready_order:
+                self.ready_order.append(b)
+                self.exchange.ready(b)
 
     def _rebind(self):
         """p.grad must alias flat_g and p.data flat_p (step() and the all-reduce read the flat buffers).
@@ -130,6 +192,9 @@ class FlatAdam:
             if p.grad is None or p.grad.data_ptr() != self.flat_g.data_ptr() + 4 * off:
                 p.grad = self.flat_g[off:off + p.numel()].view(p.shape)
         self.fresh = {id(p) for p in self.params}
+        self.exchange.reset()
+        self._bucket_ready = [set() for _ in self._bucket_keys]
+        self.ready_order = []
 
     def refresh_lp(self, act: torch.dtype) -> None:
         """One cast launch over the whole flat parameter buffer (always from the current fp32 values, so
@@ -139,9 +204,9 @@ class FlatAdam:
         ops.cast(self.flat_p, self.flat_lp)
 
     def all_reduce_grads(self):
-        """Data-parallel exchange: sum of the flat gradient over ranks (NCCL, one call)."""
-        from .parallel import all_reduce_flat_
-        return all_reduce_flat_(self.flat_g, self.pg)
+        """Data-parallel exchange: sum of the flat gradient over ranks.  Buckets whose all-reduce was started
+        during the backward (grads_ready) are only waited for; the rest is exchanged here."""
+        return self.exchange.finish()
 
     def step(self):
         self._rebind()

@@ -3,8 +3,10 @@ box, gloo in the CPU tests).  This takes the ROLE of the reference's vendored si
 DataParallelModel / DataParallelCriterion (MT/parallel.py:69-129 -- dead code upstream, the calls at
 MT/train.py:232-235 are commented out): identical replicas, each rank draws its own batch, ONE
 exchange step per optimizer step -- a sum all-reduce over the flat fp32 gradient buffer -- and an
-identical Adam update everywhere.  Batched sampling shards sequences across ranks with no
-communication."""
+identical Adam update everywhere.  The exchange is issued in per-layer BUCKETS while the backward is
+still running (``BucketedExchange``): a bucket's all-reduce starts on the communicator's own stream as soon
+as the kernels that write its gradients have been enqueued, so only the last bucket's transfer is exposed.
+Batched sampling shards sequences across ranks with no communication."""
 from __future__ import annotations
 
 import os
@@ -49,6 +51,53 @@ def all_reduce_flat_(flat: torch.Tensor, group=None) -> int:
     if w > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     return w
+
+
+class BucketedExchange:
+    """Sum all-reduce of a flat gradient buffer in contiguous buckets, each started as soon as it is final.
+
+    ``buckets``: [(lo, hi)] element ranges of ``flat`` (disjoint, covering what must be exchanged).
+    ``ready(i)`` enqueues bucket i's all-reduce asynchronously (torch.distributed orders it after the work
+    already enqueued on the current stream and runs it on the communicator's stream -- NCCL over NVLink on
+    the GPU box -- so it overlaps the rest of the backward); ``finish()`` exchanges every bucket that was not
+    started, makes the current stream wait for all of them and returns the world size.  With one rank both
+    are no-ops.  A bucket must not be written again between ``ready`` and ``finish``."""
+
+    def __init__(self, flat: torch.Tensor, buckets, group=None):
+        self.flat, self.group = flat, group
+        self.buckets = [(int(lo), int(hi)) for lo, hi in buckets]
+        self.started = [False] * len(self.buckets)
+        self.works = []
+        self.launch_order = []          # bucket indices in the order their exchange was started (tests / traces)
+
+    def reset(self) -> None:
+        if self.works:
+            raise RuntimeError("BucketedExchange.reset() with exchanges in flight: call finish() first")
+        self.started = [False] * len(self.buckets)
+        self.launch_order = []
+
+    def _start(self, i: int) -> None:
+        lo, hi = self.buckets[i]
+        self.started[i] = True
+        self.launch_order.append(i)
+        if hi > lo:
+            self.works.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group,
+                                              async_op=True))
+
+    def ready(self, i: int) -> None:
+        if world_size(self.group) > 1 and not self.started[i]:
+            self._start(i)
+
+    def finish(self) -> int:
+        w = world_size(self.group)
+        if w > 1:
+            for i in range(len(self.buckets)):
+                if not self.started[i]:
+                    self._start(i)
+            for wk in self.works:
+                wk.wait()
+        self.works = []
+        return w
 
 
 def broadcast_params_(model: torch.nn.Module, src: int = 0, group=None) -> None:

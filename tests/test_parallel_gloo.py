@@ -42,6 +42,16 @@ def _worker(rank, world, port, out):
     # global mean over non-pad tokens of all ranks
     m = parallel.global_mean_loss(torch.tensor(10.0 * (rank + 1)), torch.tensor(5.0 + rank))
     assert float(m) == pytest.approx((10.0 + 20.0) / (5.0 + 6.0))
+    # bucketed exchange: buckets started early (in backward order) and the rest at finish() give the same sums
+    flat = torch.arange(12, dtype=torch.float32) * (rank + 1)
+    ex = parallel.BucketedExchange(flat, [(0, 5), (5, 9), (9, 12)])
+    ex.ready(2)
+    ex.ready(1)
+    ex.ready(1)                                   # idempotent
+    assert ex.finish() == world and ex.launch_order == [2, 1, 0]
+    assert torch.equal(flat, torch.arange(12, dtype=torch.float32) * sum(k + 1 for k in range(world)))
+    ex.reset()
+    assert ex.finish() == world and ex.launch_order == [0, 1, 2]      # nothing started early: all at finish()
     # sampling shards: disjoint cover of the 7 sequences
     lo, hi = parallel.shard_range(7, rank, world)
     spans = [None] * world

@@ -106,6 +106,7 @@ class FlatAdam:
         # ``enc_layers.<i>.`` parameter names get a single bucket.
         import re
         names = {id(p): n for n, p in model.named_parameters()}
+        self._names = names
         key_of = []
         for p in order:
             mname = re.search(r"enc_layers\.(\d+)\.", names.get(id(p), ""))
@@ -131,6 +132,7 @@ class FlatAdam:
         self._bucket_size = [sum(1 for p in order if self._bucket_of[id(p)] == b) for b in range(len(self._bucket_keys))]
         self._bucket_ready = [set() for _ in self._bucket_keys]
         self.ready_order = []         # buckets in the order the backward completed them (since the last zero_grad)
+        self._hook_hits = {}
         self.sync_grads = True        # False on the non-final micro-batches of an accumulation window (DDP no_sync)
         for p in order:
             p._mt_opt = self
@@ -144,9 +146,15 @@ class FlatAdam:
         self.grad_accum = grad_accum
 
     def _autograd_wrote(self, p):
+        """Post-accumulate hook.  (torch runs it once per backward for every parameter of the graph, also when the
+        backward function returned None because a kernel wrote the gradient in place.)  From here on the view is
+        not known to be zero, so later backwards of the window accumulate through autograd; a SECOND pass over a
+        parameter whose bucket is already on the wire would add to a buffer being reduced."""
         self.fresh.discard(id(p))
-        if self.exchange.started[self._bucket_of[id(p)]]:
-            raise RuntimeError("FlatAdam: a gradient was accumulated after its bucket's all-reduce had started "
+        n = self._hook_hits.get(id(p), 0) + 1
+        self._hook_hits[id(p)] = n
+        if n > 1 and self.exchange.started[self._bucket_of[id(p)]]:
+            raise RuntimeError(f"FlatAdam: a gradient ({self._names.get(id(p), '?')}) was accumulated after its bucket's all-reduce had started "
                                "(second backward without zero_grad(), with the overlapped exchange on); set "
                                "opt.sync_grads = False for all but the last backward of the window")
 
@@ -195,6 +203,7 @@ class FlatAdam:
         self.exchange.reset()
         self._bucket_ready = [set() for _ in self._bucket_keys]
         self.ready_order = []
+        self._hook_hits = {}
 
     def refresh_lp(self, act: torch.dtype) -> None:
         """One cast launch over the whole flat parameter buffer (always from the current fp32 values, so

@@ -133,6 +133,10 @@ class FlatAdam:
         self._bucket_ready = [set() for _ in self._bucket_keys]
         self.ready_order = []         # buckets in the order the backward completed them (since the last zero_grad)
         self._hook_hits = {}
+        # MT_DDP_MODE: "overlap" (default: buckets go on the wire during the backward), "single" (everything at
+        # step(), the round-1 behaviour), "none" (no exchange at all -- timing experiments only)
+        import os
+        self._ddp_mode = os.environ.get("MT_DDP_MODE", "overlap")
         self.sync_grads = True        # False on the non-final micro-batches of an accumulation window (DDP no_sync)
         for p in order:
             p._mt_opt = self
@@ -162,7 +166,7 @@ class FlatAdam:
         """The kernels that write the FINAL gradients of ``params`` (directly into the flat buffer) have been
         enqueued: once that holds for every parameter of a bucket, its all-reduce starts (overlapping the rest
         of the backward).  Called by the backward functions of layers.py; a no-op on one rank."""
-        if not self.sync_grads or self.exchange is None:
+        if not self.sync_grads or self.exchange is None or self._ddp_mode != "overlap":
             return
         for p in params:
             b = self._bucket_of.get(id(p))
@@ -215,6 +219,9 @@ class FlatAdam:
     def all_reduce_grads(self):
         """Data-parallel exchange: sum of the flat gradient over ranks.  Buckets whose all-reduce was started
         during the backward (grads_ready) are only waited for; the rest is exchanged here."""
+        if self._ddp_mode == "none":
+            from .parallel import world_size
+            return world_size(self.pg)
         return self.exchange.finish()
 
     def step(self):

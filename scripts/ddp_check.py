@@ -4,8 +4,8 @@
 
 Every rank runs the config-B model (dropout 0) on its own batch.  (1) local gradients with the exchange off
 (sync_grads = False), all-gathered -> the expected sum; (2) the same backward with the bucketed exchange on:
-the flat gradient buffer after finish() must equal that sum on every rank (bit for bit at 2 ranks: fp32
-addition of two values is commutative), every bucket must have been started DURING the backward in the order
+the flat gradient buffer after finish() must equal that sum on every rank (1e-5 of the largest gradient: two
+backward passes differ by the order of the fp32 dE reductions), every bucket must have been started DURING the backward in the order
 vocabulary, layer n-1 .. 0, and the Adam step must leave all replicas identical."""
 import os
 import sys
@@ -52,7 +52,7 @@ def main():
     err = float((opt.flat_g - expect).abs().max())
     scale = float(expect.abs().max())
     ok = (w == world and started_in_backward == [layers] + list(range(layers - 1, -1, -1))
-          and (err == 0.0 if world == 2 else err <= 1e-6 * scale))
+          and err <= 1e-5 * scale)      # (two backward passes differ by the order of the dE reductions)
     opt.exchange.works = []
     opt.step_count += 1
     from musicgeneration_b200 import ops

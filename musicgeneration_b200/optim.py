@@ -226,11 +226,23 @@ class FlatAdam:
 
     def step(self):
         self._rebind()
-        world = self.all_reduce_grads()
+        from .parallel import world_size
+        world = world_size(self.pg)
         self.step_count += 1
         lr = float(self.param_groups[0]["lr"])
+        scale = 1.0 / (world * self.grad_accum)
+        if world > 1 and self._ddp_mode == "overlap":
+            # bucket by bucket: the update of a bucket runs as soon as ITS all-reduce has landed, under the
+            # transfers of the buckets behind it (the last one -- layer 0 + embedding -- is the only exposed one)
+            for b in self.exchange.finish_each():
+                lo, hi = self.exchange.buckets[b]
+                if hi > lo:
+                    ops.adam_step(self.flat_p[lo:hi], self.flat_g[lo:hi], self.m[lo:hi], self.v[lo:hi], None, lr,
+                                  self.betas[0], self.betas[1], self.eps, self.step_count, scale)
+            return
+        self.all_reduce_grads()
         ops.adam_step(self.flat_p, self.flat_g, self.m, self.v, None, lr, self.betas[0], self.betas[1],
-                      self.eps, self.step_count, 1.0 / (world * self.grad_accum))
+                      self.eps, self.step_count, scale)
 
     # ---- checkpoint compatibility (MT/train.py:143,151,203: torch.optim.Adam state_dict under 'optimizer') ----
     def _slots(self):

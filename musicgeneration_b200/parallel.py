@@ -88,6 +88,27 @@ class BucketedExchange:
         if world_size(self.group) > 1 and not self.started[i]:
             self._start(i)
 
+    def finish_each(self):
+        """Starts what was not started and yields every bucket index once ITS exchange has been waited for (in
+        launch order): the caller can consume a bucket -- the optimizer update of its range -- while later
+        buckets are still on the wire."""
+        w = world_size(self.group)
+        if w > 1:
+            for i in range(len(self.buckets)):
+                if not self.started[i]:
+                    self._start(i)
+            order = [i for i in self.launch_order if self.buckets[i][1] > self.buckets[i][0]]
+            for i, wk in zip(order, self.works):
+                wk.wait()
+                yield i
+            for i in self.launch_order:
+                if self.buckets[i][1] <= self.buckets[i][0]:
+                    yield i
+        else:
+            for i in range(len(self.buckets)):
+                yield i
+        self.works = []
+
     def finish(self) -> int:
         w = world_size(self.group)
         if w > 1:

@@ -52,6 +52,11 @@ def _worker(rank, world, port, out):
     assert torch.equal(flat, torch.arange(12, dtype=torch.float32) * sum(k + 1 for k in range(world)))
     ex.reset()
     assert ex.finish() == world and ex.launch_order == [0, 1, 2]      # nothing started early: all at finish()
+    ex.reset()
+    flat.copy_(torch.arange(12, dtype=torch.float32) * (rank + 1))
+    ex.ready(1)
+    assert list(ex.finish_each()) == [1, 0, 2] and not ex.works       # per-bucket completion, launch order
+    assert torch.equal(flat, torch.arange(12, dtype=torch.float32) * sum(k + 1 for k in range(world)))
     # sampling shards: disjoint cover of the 7 sequences
     lo, hi = parallel.shard_range(7, rank, world)
     spans = [None] * world

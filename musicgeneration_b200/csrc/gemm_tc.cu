@@ -697,6 +697,25 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
   return 0;
 }
 
+int make_tmap_2d_f32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                     int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return MT_E_UNSUPPORTED; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(2d f32 rows=%ld cols=%ld ld=%ld box=%dx%d) failed: %d", (long)rows, (long)cols,
+              (long)ld, box_cols, box_rows, (int)r);
+    return MT_E_ARG;
+  }
+  return 0;
+}
+
 int make_tmap_3d(CUtensorMap* map, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t s1_elems,
                  int64_t s2_elems, int box0, int box1, int box2) {
   EncodeTiledFn fn = encode_fn();

@@ -22,6 +22,8 @@
 #include "ops.cuh"
 #include "rga_tc_common.cuh"
 
+#include <stdlib.h>
+
 namespace mt {
 
 using namespace rga;
@@ -30,6 +32,8 @@ int rga_bwd2_dkv(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tm
                  const CUtensorMap& tmDO, const CUtensorMap& tmE, void* ds_ws, int qk_fmt, float gscale, cudaStream_t st);      // rga_tc_bwd2.cu
 int rga_bwd3_dq(const RgaArgs& a, const void* ws, const CUtensorMap& tmK, const CUtensorMap& tmE, int qk_fmt, float gscale, cudaStream_t st);   // rga_tc_bwd3.cu
 int rga_bwd3_de(const RgaArgs& a, const void* ws, const CUtensorMap& tmQ, const CUtensorMap& tmE, int qk_fmt, float gscale, cudaStream_t st);
+int rga_bwd3_dqe(const RgaArgs& a, const void* ws, const CUtensorMap& tmK, const CUtensorMap& tmE, const CUtensorMap& tmQ,
+                 int qk_fmt, float gscale, cudaStream_t st);
 
 constexpr float MIXED_GSCALE = 4096.f;
 // bytes of the mixed mode's extra workspace region: the scaled f16 copy of a dense [B, L, h, dh] dO
@@ -80,6 +84,9 @@ int rga_bwd_tc(const RgaArgs& a_in, int dh, int dtype, void* ws, size_t ws_bytes
   if ((rc = tc::make_tmap_2d(&tmE, a.E, a.max_seq, dh, dh, DHC, TT))) return rc;
   if ((rc = rga_bwd2_dkv(a, tmQ, tmK, tmV, tmDO, tmE, spill ? ws : nullptr, qk_fmt, gscale, st))) return rc;
   if (spill) {
+    // one consumer pass over the dS tiles (dQ and dE together); MT_RGA_SPLIT_CONSUMERS=1 keeps the two separate launches
+    static const bool split = getenv("MT_RGA_SPLIT_CONSUMERS") && atoi(getenv("MT_RGA_SPLIT_CONSUMERS")) != 0;
+    if (!split) return rga_bwd3_dqe(a, ws, tmK, tmE, tmQ, qk_fmt, gscale, st);
     if ((rc = rga_bwd3_dq(a, ws, tmK, tmE, qk_fmt, gscale, st))) return rc;
     return rga_bwd3_de(a, ws, tmQ, tmE, qk_fmt, gscale, st);
   }

@@ -133,6 +133,12 @@ __device__ __forceinline__ void bulk_store_1d(void* gdst, const void* smem_src, 
                ::"l"(reinterpret_cast<uint64_t>(gdst)), "r"(smem_u32(smem_src)), "r"(bytes)
                : "memory");
 }
+// TMA reduction: global tile (+)= shared-memory tile (fp32 tensor map; elements outside the tensor are dropped)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -281,6 +287,9 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_
 // {box_cols (<= 64), box_rows}, 128B swizzle, zero fill out of bounds.
 int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols,
                  int box_rows);
+// the same for an fp32 matrix (box_cols <= 32: 128 bytes); used as the destination of TMA reductions
+int make_tmap_2d_f32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                     int box_rows);
 // 3-D view: dims (innermost first) {d0, d1, d2} with byte strides {s1, s2} for d1, d2
 int make_tmap_3d(CUtensorMap* map, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t s1_elems,
                  int64_t s2_elems, int box0, int box1, int box2);

@@ -152,6 +152,25 @@ int mt_rga_bwd_ws(const void* q, const void* k, const void* v, int64_t sb, int64
  * tcgen05 backward does not take the problem (dh != 64, or dtype not MT_BF16 / MT_F16_BF16) */
 size_t mt_rga_bwd_workspace_bytes(int64_t B, int64_t h, int64_t L, int64_t dh, int dtype);
 
+/* Training pair of the tcgen05 path (head dim 64, causal, MT_BF16 or MT_F16_BF16).  The reference keeps the
+ * attention weights of every layer alive between forward and backward through autograd (MT/layers.py:97-99:
+ * softmax output saved for the backward, [B,h,L,L] fp32); here the forward keeps its P tiles -- the causal half,
+ * 16-bit, in the UMMA operand layout the backward's products read, plus the online-softmax row reference of each
+ * tile -- in a caller-owned stash of mt_rga_stash_bytes() bytes (128-byte aligned; one per layer, alive until
+ * that layer's backward), and the backward reads them instead of rebuilding S, the skew and the exponentials.
+ * mt_rga_bwd_stash also takes the scratch of mt_rga_bwd_workspace_bytes() (shared by all layers). */
+size_t mt_rga_stash_bytes(int64_t B, int64_t h, int64_t L, int64_t dh, int dtype);
+int mt_rga_fwd_stash(const void* q, const void* k, const void* v, int64_t sb, int64_t sl, int64_t sh,
+                     const void* E, const uint8_t* pad_keys, void* O, int64_t ob, int64_t ol,
+                     int64_t oh, float* lse, int64_t B, int64_t h, int64_t L, int64_t dh,
+                     int64_t max_seq, int causal, int dtype, void* stash, size_t stash_bytes, void* stream);
+int mt_rga_bwd_stash(const void* q, const void* k, const void* v, int64_t sb, int64_t sl, int64_t sh,
+                     const void* E, const uint8_t* pad_keys, const void* O, const void* dO, int64_t ob,
+                     int64_t ol, int64_t oh, const float* lse, float* delta, void* dq, void* dk,
+                     void* dv, float* dE, int64_t B, int64_t h, int64_t L, int64_t dh,
+                     int64_t max_seq, int causal, int dtype, const void* stash, size_t stash_bytes,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K6: label-smoothed cross entropy + step metrics  (MT/criterion.py:43-67, ------------
  *          MT/metrics.py:50-60) */
 /* row_lse: 3*T floats (lse, then per-row loss and per-row flags used by the reduction);

@@ -48,6 +48,9 @@ SIGNATURES = {
     "mt_rga_bwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _p]),
     "mt_rga_bwd_ws": (_int, [_p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _p, _sz, _p]),
     "mt_rga_bwd_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64, _int]),
+    "mt_rga_stash_bytes": (_sz, [_i64, _i64, _i64, _i64, _int]),
+    "mt_rga_fwd_stash": (_int, [_p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _int, _int, _p, _sz, _p]),
+    "mt_rga_bwd_stash": (_int, [_p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _int, _p, _sz, _p, _sz, _p]),
     "mt_smooth_ce_fwd": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _f, _i32, _p]),
     "mt_smooth_ce_bwd": (_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _f, _i32, _p]),
     "mt_adam_step": (_int, [_p, _p, _p, _p, _p, _i64, _f, _f, _f, _f, _i64, _f, _p]),

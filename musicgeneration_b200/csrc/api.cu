@@ -84,6 +84,28 @@ int mt_rga_fwd(const void* q, const void* k, const void* v, int64_t sb, int64_t 
   return rga_fwd_simt(a, (int)dh, dtype, as_stream(stream));
 }
 
+size_t mt_rga_stash_bytes(int64_t B, int64_t h, int64_t L, int64_t dh, int dtype) {
+  if (dh != 64 || (dtype != MT_BF16 && dtype != MT_F16_BF16) || B <= 0 || h <= 0 || L <= 0) return 0;
+  return rga_stash_bytes(B, h, L);
+}
+
+int mt_rga_fwd_stash(const void* q, const void* k, const void* v, int64_t sb, int64_t sl, int64_t sh,
+                     const void* E, const uint8_t* pad_keys, void* O, int64_t ob, int64_t ol,
+                     int64_t oh, float* lse, int64_t B, int64_t h, int64_t L, int64_t dh,
+                     int64_t max_seq, int causal, int dtype, void* stash, size_t stash_bytes, void* stream) {
+  RgaArgs a;
+  int rc = fill_rga(a, q, k, v, sb, sl, sh, E, pad_keys, B, h, L, dh, max_seq, causal, dtype);
+  if (rc) return rc;
+  MT_REQUIRE(v && O && lse && stash, "rga_fwd_stash: null pointer");
+  a.O = O; a.ob = ob; a.ol = ol; a.oh = oh; a.lse = lse;
+  a.pstash = stash; a.pstash_bytes = stash_bytes;
+  if (!rga_tc_supported(a, (int)dh, dtype, false) || !rga_tc_supported(a, (int)dh, dtype == MT_F16 ? MT_BF16 : dtype, true) || !causal) {
+    set_error("rga_fwd_stash: the tcgen05 training path does not take this problem (head dim 64, causal, bf16 / f16+bf16)");
+    return MT_E_UNSUPPORTED;
+  }
+  return rga_fwd_tc(a, (int)dh, dtype, as_stream(stream));
+}
+
 int mt_rga_weights(const void* q, const void* k, int64_t sb, int64_t sl, int64_t sh,
                    const void* E, const uint8_t* pad_keys, const float* lse, float* P, int64_t B,
                    int64_t h, int64_t L, int64_t dh, int64_t max_seq, int causal, int dtype,
@@ -129,6 +151,25 @@ int mt_rga_bwd_ws(const void* q, const void* k, const void* v, int64_t sb, int64
   if (path == 2 || (path == 0 && tc_ok)) return rga_bwd_tc(a, (int)dh, dtype, workspace, workspace_bytes, as_stream(stream));
   if (dtype == MT_F16_BF16) { set_error("rga_bwd: the mixed f16/bf16 mode exists on the tcgen05 path only"); return MT_E_UNSUPPORTED; }
   return rga_bwd_simt(a, (int)dh, dtype, as_stream(stream));
+}
+
+int mt_rga_bwd_stash(const void* q, const void* k, const void* v, int64_t sb, int64_t sl, int64_t sh,
+                     const void* E, const uint8_t* pad_keys, const void* O, const void* dO, int64_t ob,
+                     int64_t ol, int64_t oh, const float* lse, float* delta, void* dq, void* dk,
+                     void* dv, float* dE, int64_t B, int64_t h, int64_t L, int64_t dh,
+                     int64_t max_seq, int causal, int dtype, const void* stash, size_t stash_bytes,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  RgaArgs a;
+  int rc = fill_rga(a, q, k, v, sb, sl, sh, E, pad_keys, B, h, L, dh, max_seq, causal, dtype);
+  if (rc) return rc;
+  MT_REQUIRE(v && O && dO && lse && delta && dq && dk && dv && dE && stash, "rga_bwd_stash: null pointer");
+  a.O = const_cast<void*>(O); a.dO = dO; a.ob = ob; a.ol = ol; a.oh = oh;
+  a.lse = const_cast<float*>(lse); a.delta = delta; a.dq = dq; a.dk = dk; a.dv = dv; a.dE = dE;
+  a.pstash = const_cast<void*>(stash); a.pstash_bytes = stash_bytes;
+  if (!rga_tc_supported(a, (int)dh, dtype, true)) { set_error("rga_bwd_stash: tcgen05 path does not take this problem"); return MT_E_UNSUPPORTED; }
+  MT_REQUIRE(stash_bytes >= rga_stash_bytes(B, h, L) && aligned(stash, 128), "rga_bwd_stash: the P stash needs %zu bytes, 128-byte aligned",
+             rga_stash_bytes(B, h, L));
+  return rga_bwd_tc(a, (int)dh, dtype, workspace, workspace_bytes, as_stream(stream));
 }
 
 }  // extern "C"

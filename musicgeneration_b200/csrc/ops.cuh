@@ -16,6 +16,9 @@ struct RgaArgs {
   // f16 gradient mode of the tcgen05 backward (MT_F16_BF16): the delta kernel also writes dO_h = f16(gscale * dO)
   // with dO's own addressing; the MMAs then read dO_h
   void* dO_h; float gscale;
+  // training forward / backward of the tcgen05 path: the forward keeps its P tiles here and the backward reads them
+  // (rga_stash_bytes(); NULL = inference forward / backward that rebuilds P)
+  void* pstash; size_t pstash_bytes;
 };
 
 // gemm_simt.cu
@@ -46,6 +49,7 @@ int gemm_skinny(const void* A, const void* B, void* C, const float* bias, int64_
 bool rga_tc_supported(const RgaArgs& a, int dh, int dtype, bool backward);
 int rga_fwd_tc(const RgaArgs& a, int dh, int dtype, cudaStream_t st);
 int rga_bwd_tc(const RgaArgs& a, int dh, int dtype, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t rga_stash_bytes(int64_t B, int64_t h, int64_t L);            // P stash of a training forward (rga_tc.cu)
 size_t rga_bwd3_workspace_bytes(int64_t B, int64_t h, int64_t L);   // dS-spill workspace of the tcgen05 backward
 size_t rga_bwd_mixed_extra_bytes(int64_t B, int64_t h, int64_t L, int64_t dh);   // + the scaled f16 copy of dO (MT_F16_BF16)
 

@@ -63,6 +63,9 @@ struct FwdParams {
   int ofmt;             // 16-bit format of O (1 = bf16, 0 = f16); differs from fmt in the mixed mode (f16 q/k/v/E, bf16 O)
   int heads_per_cta;    // consecutive heads walked by one CTA (same batch row and query tile): halves the per-CTA fixed cost
   float scale_log2;     // log2(e) / sqrt(dh)
+  uint8_t* stash;       // training: every P tile (16-bit, relative to the row reference of its step) is kept
+  float* mrow;          //           for the backward (rga_tc_bwd4.cu; thread-major layout), with the row references [tile][128] (log2 domain)
+  int nTri;             //           tiles per (batch, head): nT (nT + 1) / 2, tile (it, jt) at it (it + 1) / 2 + jt
   long long* trace;     // MT_RGA_TRACE=z: clock64 stamps of CTA (0,0,z), [2 agents][32 steps][8 events]
   int trace_z;
 };
@@ -349,6 +352,18 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc::tc_fence_before();
       tc::mbar_arrive(p_full);
       if (threadIdx.x == 0) FTRACE(0, g, 7);
+      if (p.stash) {
+        // the backward reads P instead of rebuilding S, the skew and the exponentials.  Stash layout of a tile
+        // (32 KB): [warp 0..15][chunk 0..3][lane][16 B] -- the thread that owns (row a, 32 key columns) here owns them
+        // in the backward kernels too, and a warp's store (and the backward's load) of one chunk is 512 contiguous bytes
+        const int it = i0 / TT;
+        const int64_t tix = ((int64_t)b * p.h + hh0 + item) * p.nTri + (it * (it + 1) / 2 + jt);
+        uint4* dst = reinterpret_cast<uint4*>(p.stash + tix * (int64_t)(2 * TILE)) + warp * 128 + lane;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          __stcs(dst + 32 * c, make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]));
+        if (qt == 0) p.mrow[tix * TT + a] = m_use;
+      }
       if (++jt < n_kt) continue;
 
       // ---- end of a head: O / l, LSE (the row sums are exchanged through their own slot: the step slots
@@ -403,6 +418,12 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
 bool rga_bwd_tc_supported(const RgaArgs& a, int dh, int dtype);   // rga_tc_bwd.cu
 
+// P stash of a training forward: B h nT (nT + 1) / 2 tile images of 32 KB, then as many [128] fp32 row references
+size_t rga_stash_bytes(int64_t B, int64_t h, int64_t L) {
+  const int64_t nT = (L + TT - 1) / TT;
+  return (size_t)(B * h * (nT * (nT + 1) / 2)) * (size_t)(2 * TILE + TT * 4);
+}
+
 bool rga_tc_supported(const RgaArgs& a, int dh, int dtype, bool backward) {
   if (backward) return rga_bwd_tc_supported(a, dh, dtype);
   if (dh != DHC) return false;
@@ -427,6 +448,18 @@ int rga_fwd_tc(const RgaArgs& a, int dh, int dtype, cudaStream_t st) {
   p.fmt = (dtype == MT_BF16) ? 1 : 0;
   p.ofmt = (dtype == MT_F16) ? 0 : 1;
   p.scale_log2 = LOG2E / a.inv_scale_div;
+  p.stash = nullptr; p.mrow = nullptr; p.nTri = 0;
+  if (a.pstash) {
+    if (!a.causal) { set_error("rga_fwd: the P stash exists for the causal mask only"); return MT_E_UNSUPPORTED; }
+    const int64_t nTs = (a.L + TT - 1) / TT, tiles = (int64_t)a.B * a.h * (nTs * (nTs + 1) / 2);
+    if (a.pstash_bytes < rga_stash_bytes(a.B, a.h, a.L) || !aligned(a.pstash, 128)) {
+      set_error("rga_fwd: the P stash needs %zu bytes, 128-byte aligned", rga_stash_bytes(a.B, a.h, a.L));
+      return MT_E_WORKSPACE;
+    }
+    p.stash = static_cast<uint8_t*>(a.pstash);
+    p.mrow = reinterpret_cast<float*>(p.stash + tiles * (int64_t)(2 * TILE));
+    p.nTri = (int)(nTs * (nTs + 1) / 2);
+  }
   static unsigned long long attr_done = 0; const unsigned long long attr_bit = attr_dev_bit();
   if (!(attr_done & attr_bit)) {
     cudaError_t e = cudaFuncSetAttribute(rga_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);

@@ -153,6 +153,12 @@ __device__ __forceinline__ void ldg256_stream(const void* g, uint32_t& r0, uint3
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
                : "l"(reinterpret_cast<uint64_t>(g)));
 }
+// 128-bit streaming load (read-only data, no L1 allocation)
+__device__ __forceinline__ void ldg128_stream(const void* g, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "l"(reinterpret_cast<uint64_t>(g)));
+}
 // named barrier among a subset of the CTA's warps
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -188,11 +188,26 @@ def _rga_dtype(q, E, other) -> int:
     return dt(q)
 
 
+def rga_stash_new(q, E, O, B, h, Lq, dh) -> Optional[torch.Tensor]:
+    """A P stash for one training forward/backward pair of the tcgen05 path (mt_rga_stash_bytes), or None
+    when that path does not take the problem.  One per layer: it lives until the layer's backward."""
+    need = L.load().mt_rga_stash_bytes(B, h, Lq, dh, _rga_dtype(q, E, O))
+    if need == 0:
+        return None
+    return torch.empty(need, dtype=torch.uint8, device=q.device)
+
+
 def rga_fwd(q, k, v, strides, E, pad_keys, O, ostrides, lse, B, h, Lq, dh, max_seq, causal,
-            path=L.PATH_AUTO):
+            path=L.PATH_AUTO, stash: Optional[torch.Tensor] = None):
+    """stash: keep the P tiles for the backward (training step on the tcgen05 path, causal only)."""
     _need_cuda(q, k, v, E, O, lse)
     sb, sl, sh = strides
     ob, ol, oh = ostrides
+    if stash is not None:
+        L.check(L.load().mt_rga_fwd_stash(_ptr(q), _ptr(k), _ptr(v), sb, sl, sh, _ptr(E), _ptr(pad_keys),
+                                          _ptr(O), ob, ol, oh, _ptr(lse), B, h, Lq, dh, max_seq, int(causal),
+                                          _rga_dtype(q, E, O), _ptr(stash), stash.numel(), _stream()), "rga_fwd_stash")
+        return
     L.check(L.load().mt_rga_fwd(_ptr(q), _ptr(k), _ptr(v), sb, sl, sh, _ptr(E), _ptr(pad_keys),
                                 _ptr(O), ob, ol, oh, _ptr(lse), B, h, Lq, dh, max_seq, int(causal),
                                 _rga_dtype(q, E, O), path, _stream()), "rga_fwd")
@@ -223,13 +238,22 @@ def rga_bwd_workspace(q, B, h, Lq, dh, code=None):
 
 
 def rga_bwd(q, k, v, strides, E, pad_keys, O, dO, ostrides, lse, delta, dq, dk, dv, dE, B, h, Lq, dh,
-            max_seq, causal, path=L.PATH_AUTO, spill=True):
+            max_seq, causal, path=L.PATH_AUTO, spill=True, stash: Optional[torch.Tensor] = None):
     """spill=True: give the tcgen05 path its dS workspace (S, P, dS computed once); False: every
-    backward role recomputes them (no scratch memory)."""
+    backward role recomputes them (no scratch memory).  stash: the P tiles the forward of this call kept
+    (rga_fwd(..., stash=...)): nothing of S / P is rebuilt."""
     _need_cuda(q, k, v, E, O, dO, lse, delta, dq, dk, dv, dE)
     sb, sl, sh = strides
     ob, ol, oh = ostrides
     code = _rga_dtype(q, E, dq)
+    if stash is not None:
+        ws = rga_bwd_workspace(q, B, h, Lq, dh, code)
+        L.check(L.load().mt_rga_bwd_stash(_ptr(q), _ptr(k), _ptr(v), sb, sl, sh, _ptr(E), _ptr(pad_keys),
+                                          _ptr(O), _ptr(dO), ob, ol, oh, _ptr(lse), _ptr(delta), _ptr(dq),
+                                          _ptr(dk), _ptr(dv), _ptr(dE), B, h, Lq, dh, max_seq, int(causal),
+                                          code, _ptr(stash), stash.numel(), _ptr(ws),
+                                          ws.numel() if ws is not None else 0, _stream()), "rga_bwd_stash")
+        return
     ws = rga_bwd_workspace(q, B, h, Lq, dh, code) if (spill and path != L.PATH_SIMT) else None
     L.check(L.load().mt_rga_bwd_ws(_ptr(q), _ptr(k), _ptr(v), sb, sl, sh, _ptr(E), _ptr(pad_keys),
                                    _ptr(O), _ptr(dO), ob, ol, oh, _ptr(lse), _ptr(delta), _ptr(dq),

@@ -20,15 +20,17 @@ dqkv = torch.zeros(B, L, 3, h, dh, dtype=torch.bfloat16, device=dev)
 dE = torch.zeros(max_seq, dh, device=dev)
 delta = torch.empty(B, h, L, device=dev)
 SPILL = os.environ.get("SPILL", "1") == "1"
+STASH = os.environ.get("STASH", "0") == "1"      # the training pair: the forward keeps its P tiles, the backward reads them
+st = ops.rga_stash_new(qkv[:, :, 0], E, Od, B, h, L, dh) if STASH else None
 ITERS = int(os.environ.get("PITER", 3))
 hist = []
 for it in range(ITERS):
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     e[0].record()
-    ops.rga_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], strides, E, None, Od, ostr, lse, B, h, L, dh, max_seq, True, path=2)
+    ops.rga_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], strides, E, None, Od, ostr, lse, B, h, L, dh, max_seq, True, path=2, stash=st)
     e[1].record()
     ops.rga_bwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], strides, E, None, Od, dO, ostr, lse, delta,
-                dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], dE, B, h, L, dh, max_seq, True, path=2, spill=SPILL)
+                dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], dE, B, h, L, dh, max_seq, True, path=2, spill=SPILL, stash=st)
     e[2].record()
     torch.cuda.synchronize()
     hist.append((e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])))

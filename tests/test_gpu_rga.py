@@ -18,8 +18,10 @@ def rel(a, b):
     return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
 
 
-def run_case(B, h, L, dh, max_seq, causal, pad, dtype, path, seed=0, scale=1.0, spill=True, io_dtype=None, do_scale=1.0):
-    """io_dtype: type of O / dO / dq / dk / dv when it differs from the q / k / v / E type (the mixed mode)."""
+def run_case(B, h, L, dh, max_seq, causal, pad, dtype, path, seed=0, scale=1.0, spill=True, io_dtype=None, do_scale=1.0,
+             stash=False):
+    """io_dtype: type of O / dO / dq / dk / dv when it differs from the q / k / v / E type (the mixed mode).
+    stash: the training pair (the forward keeps its P tiles, the backward reads them)."""
     from musicgeneration_b200 import ops
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(seed)
@@ -47,12 +49,17 @@ def run_case(B, h, L, dh, max_seq, causal, pad, dtype, path, seed=0, scale=1.0, 
     ostr = (L * d, d, dh)
     qd, kd, vd = qkv_d[:, :, 0], qkv_d[:, :, 1], qkv_d[:, :, 2]
     pk = pad_keys.to(torch.uint8).to(dev) if pad_keys is not None else None
-    ops.rga_fwd(qd, kd, vd, strides, Ed, pk, Od, ostr, lse, B, h, L, dh, max_seq, causal, path=path)
+    st = None
+    if stash:
+        st = ops.rga_stash_new(qd, Ed, Od, B, h, L, dh)
+        assert st is not None
+        st.fill_(0xFF)           # (NaN patterns: a tile the forward fails to write shows up)
+    ops.rga_fwd(qd, kd, vd, strides, Ed, pk, Od, ostr, lse, B, h, L, dh, max_seq, causal, path=path, stash=st)
     dqkv = torch.zeros(B, L, 3, h, dh, dtype=io_dtype, device=dev)
     dE = torch.zeros(max_seq, dh, device=dev)
     delta = torch.empty(B, h, L, device=dev)
     ops.rga_bwd(qd, kd, vd, strides, Ed, pk, Od, dO.to(dev), ostr, lse, delta, dqkv[:, :, 0],
-                dqkv[:, :, 1], dqkv[:, :, 2], dE, B, h, L, dh, max_seq, causal, path=path, spill=spill)
+                dqkv[:, :, 1], dqkv[:, :, 2], dE, B, h, L, dh, max_seq, causal, path=path, spill=spill, stash=st)
     res = dict(
         o=rel(Od.float().cpu().permute(0, 2, 1, 3), o_ref.detach()),
         lse=float((lse.cpu().double() - lse_ref.detach()).abs().max()),
@@ -160,12 +167,14 @@ def test_rga_fwd_tcgen05(B, h, L, max_seq, causal, pad, dtype):
     (2, 4, 512, 512, False),
     (1, 8, 1024, 2048, True),
 ])
-@pytest.mark.parametrize("spill", [True, False])
+@pytest.mark.parametrize("spill", [True, False, "stash"])
 def test_rga_bwd_tcgen05(B, h, L, max_seq, pad, spill):
     """forward + backward both on the tcgen05 path; bf16 operands, fp64 oracle on the same inputs.
-    spill: dS tiles written once by the dK/dV kernel and consumed by the dQ / dE kernels (the default)
-    against every kernel recomputing them."""
-    r = run_case(B, h, L, 64, max_seq, True, pad, torch.bfloat16, PATHS["tc"], seed=L + 3 * h, spill=spill)
+    spill: dS tiles written once by the dK/dV kernel and consumed by the dQ / dE kernels
+    against every kernel recomputing them; "stash": the training pair -- the forward keeps its P tiles and the
+    backward reads them (what the model's train step runs)."""
+    r = run_case(B, h, L, 64, max_seq, True, pad, torch.bfloat16, PATHS["tc"], seed=L + 3 * h, spill=spill is not False,
+                 stash=spill == "stash")
     assert r["o"] < 6e-3, r
     # P and dS are rounded to bf16 before the gradient GEMMs
     assert max(r["dq"], r["dk"], r["dv"]) < 1.2e-2 and r["dE"] < 1.2e-2, r
@@ -179,13 +188,14 @@ def test_rga_bwd_tcgen05(B, h, L, max_seq, pad, spill):
     (2, 4, 512, 512, False, 6.0),           # layer-0-like statistics: logits in the hundreds
     (1, 8, 1024, 2048, True, 3.0),
 ])
-def test_rga_tcgen05_mixed_f16_qkv_bf16_io(B, h, L, max_seq, pad, scale):
+@pytest.mark.parametrize("stash", [False, True])
+def test_rga_tcgen05_mixed_f16_qkv_bf16_io(B, h, L, max_seq, pad, scale, stash):
     """The first encoder layer's mode (MT_F16_BF16): f16 q / k / v / E operands, bf16 O / dO / dq / dk / dv.  The
     tensor cores take one operand format per product, so the backward runs on f16(2^12 dO), an f16 P and an f16
     2^12 dS (rga_tc_bwd.cu); dO has the magnitude of real activation gradients (the scaled copy overflows f16
     beyond |dO| |v| ~ 16).  fp64 oracle on the same inputs."""
     r = run_case(B, h, L, 64, max_seq, True, pad, torch.float16, PATHS["tc"], seed=L + 3 * h, scale=scale,
-                 io_dtype=torch.bfloat16, do_scale=1e-3)
+                 io_dtype=torch.bfloat16, do_scale=1e-3, stash=stash)
     # O is rounded to bf16 on the way out (as in the bf16 mode); the logits see f16 operands and an f16 P
     assert r["o"] < 6e-3 and r["lse"] < 2e-3 * max(1.0, scale * scale), r
     assert max(r["dq"], r["dk"], r["dv"]) < 1.2e-2 and r["dE"] < 1.2e-2, r
@@ -221,17 +231,22 @@ def test_rga_bwd_tcgen05_matches_simt_backward():
     dO = torch.randn(B, L, h, dh, generator=g).to(torch.bfloat16).to(dev)
     strides, ostr = (L * 3 * d, 3 * d, dh), (L * d, d, dh)
     outs = {}
-    for name, path, spill in (("simt", PATHS["simt"], False), ("tc", PATHS["tc"], True), ("tc_recompute", PATHS["tc"], False)):
+    for name, path, spill in (("simt", PATHS["simt"], False), ("tc", PATHS["tc"], True), ("tc_recompute", PATHS["tc"], False),
+                              ("tc_stash", PATHS["tc"], True)):
         Od = torch.empty(B, L, h, dh, dtype=torch.bfloat16, device=dev)
         lse = torch.empty(B, h, L, device=dev)
+        st = ops.rga_stash_new(qkv[:, :, 0], E, Od, B, h, L, dh) if name == "tc_stash" else None
         ops.rga_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], strides, E, None, Od, ostr, lse, B, h, L, dh,
-                    max_seq, True, path=path)
+                    max_seq, True, path=path, stash=st)
         dqkv = torch.zeros(B, L, 3, h, dh, dtype=torch.bfloat16, device=dev)
         dE = torch.zeros(max_seq, dh, device=dev)
         delta = torch.empty(B, h, L, device=dev)
         ops.rga_bwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], strides, E, None, Od, dO, ostr, lse, delta,
-                    dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], dE, B, h, L, dh, max_seq, True, path=path, spill=spill)
+                    dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], dE, B, h, L, dh, max_seq, True, path=path, spill=spill,
+                    stash=st)
         outs[name] = (dqkv.float().cpu(), dE.cpu())
+    assert rel(outs["tc_stash"][0], outs["simt"][0]) < 1.2e-2
+    assert rel(outs["tc_stash"][1], outs["simt"][1]) < 1.2e-2
     assert rel(outs["tc"][0], outs["simt"][0]) < 1.2e-2
     assert rel(outs["tc"][1], outs["simt"][1]) < 1.2e-2
     assert float(outs["tc"][1][:max_seq - L].abs().max()) == 0.0      # only rows max_seq-L.. get gradient
@@ -265,17 +280,23 @@ def test_rga_tcgen05_long_context_matches_simt(B, h, L):
     dO = torch.randn(B, L, h, dh, generator=g).to(torch.bfloat16).to(dev)
     strides, ostr = (L * 3 * d, 3 * d, dh), (L * d, d, dh)
     outs = {}
-    for name, path in PATHS.items():
+    for name, path in list(PATHS.items()) + [("tc_stash", PATHS["tc"])]:
         Od = torch.empty(B, L, h, dh, dtype=torch.bfloat16, device=dev)
         lse = torch.empty(B, h, L, device=dev)
+        st = ops.rga_stash_new(qkv[:, :, 0], E, Od, B, h, L, dh) if name == "tc_stash" else None
         ops.rga_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], strides, E, None, Od, ostr, lse, B, h, L, dh,
-                    max_seq, True, path=path)
+                    max_seq, True, path=path, stash=st)
         dqkv = torch.zeros(B, L, 3, h, dh, dtype=torch.bfloat16, device=dev)
         dE = torch.zeros(max_seq, dh, device=dev)
         delta = torch.empty(B, h, L, device=dev)
         ops.rga_bwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], strides, E, None, Od, dO, ostr, lse, delta,
-                    dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], dE, B, h, L, dh, max_seq, True, path=path)
+                    dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], dE, B, h, L, dh, max_seq, True, path=path, stash=st)
         outs[name] = (Od.float().cpu(), lse.cpu(), dqkv.float().cpu(), dE.cpu())
+        del st
+    # the training pair (P stash) against the fp32-math kernels
+    assert rel(outs["tc_stash"][0], outs["simt"][0]) < 6e-3
+    assert rel(outs["tc_stash"][2], outs["simt"][2]) < 1.2e-2
+    assert rel(outs["tc_stash"][3], outs["simt"][3]) < 1.2e-2
     assert rel(outs["tc"][0], outs["simt"][0]) < 6e-3
     assert float((outs["tc"][1] - outs["simt"][1]).abs().max()) < 2e-3
     assert rel(outs["tc"][2], outs["simt"][2]) < 1.2e-2

@@ -341,6 +341,25 @@ rga_bwd3_kernel(const __grid_constant__ CUtensorMap tmX,      // K (dQ and fused
       tc::tc_fence_before();
       tc::mbar_arrive_warp(&de_free[slot]);
       if (erow0 >= p.max_seq || erow0 + TT <= 0) continue;      // (uniform) nothing of the block exists
+      if (erow0 < 0) {
+        // max_seq is not a multiple of the tile edge and this is the block that straddles E row 0 (once per head, on
+        // the farthest diagonal): a bulk-tensor reduction at a negative row coordinate faults on sm_100a (illegal
+        // instruction, found with L = max_seq = 64), so these rows leave through vector reductions instead
+        const int erow = erow0 + a;
+        if (erow >= 0 && erow < p.max_seq) {
+          float* dst = p.dE + (int64_t)erow * DHC;
+#pragma unroll
+          for (int x = 0; x < 32; x += 4) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + x), "f"(__uint_as_float(r0[x]) * osc),
+                         "f"(__uint_as_float(r0[x + 1]) * osc), "f"(__uint_as_float(r0[x + 2]) * osc),
+                         "f"(__uint_as_float(r0[x + 3]) * osc) : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 32 + x), "f"(__uint_as_float(r1[x]) * osc),
+                         "f"(__uint_as_float(r1[x + 1]) * osc), "f"(__uint_as_float(r1[x + 2]) * osc),
+                         "f"(__uint_as_float(r1[x + 3]) * osc) : "memory");
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         if (ftid == 0) tc::bulk_wait_read0();             // the previous reduction has read the staging tile

@@ -121,11 +121,15 @@ def hp_eligible(W: LayerWeights, cfg: StackCfg, mask: Optional[Mask]) -> bool:
 
 
 def rga_block_fwd(xq, xk, xv, W: LayerWeights, cfg: StackCfg, B: int, Lq: int, mask: Optional[Mask],
-                  need_weights: bool, x_hp: Optional[torch.Tensor] = None, x_f32: Optional[torch.Tensor] = None):
+                  need_weights: bool, x_hp: Optional[torch.Tensor] = None, x_f32: Optional[torch.Tensor] = None,
+                  keep_p: bool = False):
     """xq/xk/xv: [T, d] act dtype (the same tensor for self-attention).  Returns
     (a [T,d] act dtype = fc output incl. bias, saved dict, P or None).
     ``x_hp`` (f16 copy of the self-attention input) selects the f16-operand mode of the first layer;
-    ``xq`` may then be None (the bf16 copy the weight gradient needs is cast from ``x_f32`` in the backward)."""
+    ``xq`` may then be None (the bf16 copy the weight gradient needs is cast from ``x_f32`` in the backward).
+    ``keep_p``: a backward will follow -- on the tcgen05 path (causal mask, head dim 64, 16-bit operands) the attention
+    kernel then keeps its P tiles in a per-layer stash for it (the reference keeps the softmax output through
+    autograd, MT/layers.py:97-99)."""
     d, h, dh = cfg.d, cfg.h, cfg.dh
     T = B * Lq
     hp = x_hp is not None
@@ -148,8 +152,11 @@ def rga_block_fwd(xq, xk, xv, W: LayerWeights, cfg: StackCfg, B: int, Lq: int, m
     lse = _empty((B, h, Lq), torch.float32, like)
     causal = bool(mask.causal) if mask is not None else False
     pad = mask.pad_keys if mask is not None else None
+    stash = None
+    if keep_p and causal and cfg.attn_path != L.PATH_SIMT and qkv.dtype != torch.float32:
+        stash = ops.rga_stash_new(q, E, O, B, h, Lq, dh)          # None when the tcgen05 pair does not take the shape
     ops.rga_fwd(q, k, v, strides, E, pad, O, ostrides, lse, B, h, Lq, dh, cfg.max_seq, causal,
-                path=cfg.attn_path)
+                path=cfg.attn_path, stash=stash)
     P = None
     if need_weights:
         P = _empty((B, h, Lq, Lq), torch.float32, like)
@@ -159,7 +166,7 @@ def rga_block_fwd(xq, xk, xv, W: LayerWeights, cfg: StackCfg, B: int, Lq: int, m
     a = _empty((T, d), cfg.act, like)
     linear_fwd(O, W.Wfc, W.bfc, a, cfg)
     saved = dict(xq=xq, xk=xk, xv=xv, same=same, qkv=qkv, O=O, lse=lse, causal=causal, pad=pad,
-                 strides=strides, ostrides=ostrides, B=B, L=Lq, hp=hp, x_f32=x_f32 if hp else None)
+                 strides=strides, ostrides=ostrides, B=B, L=Lq, hp=hp, x_f32=x_f32 if hp else None, stash=stash)
     return a, saved, P
 
 
@@ -195,7 +202,8 @@ def rga_block_bwd(d_a, s, W: LayerWeights, cfg: StackCfg, g: Dict[str, torch.Ten
     ops.rga_bwd(qkv[:, 0:d], qkv[:, d:2 * d], qkv[:, 2 * d:3 * d], s["strides"], W.E_hp if s["hp"] else W.E, s["pad"],
                 s["O"], dO, s["ostrides"], s["lse"], delta, dqkv[:, 0:d], dqkv[:, d:2 * d],
                 dqkv[:, 2 * d:3 * d], g["E"], B, h, Lq, dh, cfg.max_seq, s["causal"],
-                path=cfg.attn_path)
+                path=cfg.attn_path, stash=s.get("stash"))
+    s["stash"] = None           # (its last use: the caching allocator may hand the block to the next layer's scratch)
     g["Wqkv"] = _gbuf(dst, "Wqkv", (3 * d, d), dev)
     g["bqkv"] = _gbuf(dst, "bqkv", (3 * d,), dev)
     if s["same"]:
@@ -224,7 +232,7 @@ def rga_block_bwd(d_a, s, W: LayerWeights, cfg: StackCfg, g: Dict[str, torch.Ten
 # encoder layer  (MT/layers.py:152-161)
 # ---------------------------------------------------------------------------------------
 def layer_fwd(x_f32, x_lp, W: LayerWeights, cfg: StackCfg, B: int, Lq: int, mask: Optional[Mask],
-              seed: int, site0: int, training: bool, need_weights: bool):
+              seed: int, site0: int, training: bool, need_weights: bool, keep_p: bool = False):
     d = cfg.d
     T = B * Lq
     p = cfg.p_drop if training else 0.0
@@ -236,9 +244,10 @@ def layer_fwd(x_f32, x_lp, W: LayerWeights, cfg: StackCfg, B: int, Lq: int, mask
         else:
             x_hp, x_b = _empty((T, d), torch.float16, x_f32), x_lp
             ops.cast(x_f32, x_hp)
-        a, s_att, P = rga_block_fwd(x_b, x_b, x_b, W, cfg, B, Lq, mask, need_weights, x_hp=x_hp, x_f32=x_f32)
+        a, s_att, P = rga_block_fwd(x_b, x_b, x_b, W, cfg, B, Lq, mask, need_weights, x_hp=x_hp, x_f32=x_f32,
+                                    keep_p=keep_p)
     else:
-        a, s_att, P = rga_block_fwd(x_lp, x_lp, x_lp, W, cfg, B, Lq, mask, need_weights)
+        a, s_att, P = rga_block_fwd(x_lp, x_lp, x_lp, W, cfg, B, Lq, mask, need_weights, keep_p=keep_p)
     out1 = _empty((T, d), torch.float32, x_f32)
     out1_lp = _empty((T, d), cfg.act, x_f32) if lp else None
     mean1 = _empty((T,), torch.float32, x_f32)
@@ -304,7 +313,7 @@ def layer_bwd(dout, s, W: LayerWeights, cfg: StackCfg,
 # ---------------------------------------------------------------------------------------
 def encoder_fwd(ids: torch.Tensor, emb: torch.Tensor, pe: torch.Tensor, Ws: List[LayerWeights],
                 cfg: StackCfg, mask: Optional[Mask], seed: int, training: bool, need_weights: bool,
-                pos0: int = 0):
+                pos0: int = 0, keep_p: bool = False):
     B, Lq = ids.shape
     d = cfg.d
     T = B * Lq
@@ -319,7 +328,7 @@ def encoder_fwd(ids: torch.Tensor, emb: torch.Tensor, pe: torch.Tensor, Ws: List
     saved_layers = []
     weights = []
     for li, W in enumerate(Ws):
-        x, xl, s, P = layer_fwd(x, xl, W, cfg, B, Lq, mask, seed, 1 + 2 * li, training, need_weights)
+        x, xl, s, P = layer_fwd(x, xl, W, cfg, B, Lq, mask, seed, 1 + 2 * li, training, need_weights, keep_p=keep_p)
         saved_layers.append(s)
         weights.append(P)
     saved = dict(ids=ids, layers=saved_layers, p=p, seed=seed, B=B, L=Lq)

@@ -249,7 +249,7 @@ class _RGAFunction(torch.autograd.Function):
         k2 = q2 if same else _act_copy(_as_f32_2d(xk, d), cfg.act)
         v2 = q2 if same else _act_copy(_as_f32_2d(xv, d), cfg.act)
         W = _rga_weights_for(rga, cfg.act)
-        a, saved, P = engine.rga_block_fwd(q2, k2, v2, W, cfg, B, Lq, mask, want_w)
+        a, saved, P = engine.rga_block_fwd(q2, k2, v2, W, cfg, B, Lq, mask, want_w, keep_p=any(ctx.needs_input_grad))
         ctx.rga, ctx.cfg, ctx.W, ctx.saved = rga, cfg, W, saved
         ctx.shape = (B, Lq, d)
         if P is not None:
@@ -389,7 +389,7 @@ class _LayerFunction(torch.autograd.Function):
         x2 = _as_f32_2d(x, d)
         W = layer.weights(cfg.act)
         out, _, saved, P = engine.layer_fwd(x2, _act_copy(x2, cfg.act), W, cfg, B, Lq, mask, _next_seed(),
-                                            1, layer.training, want_w)
+                                            1, layer.training, want_w, keep_p=any(ctx.needs_input_grad))
         ctx.cfg, ctx.W, ctx.saved, ctx.shape = cfg, W, saved, (B, Lq, d)
         if P is not None:
             ctx.mark_non_differentiable(P)
@@ -456,7 +456,8 @@ class _EncoderFunction(torch.autograd.Function):
         Ws = [l.weights(cfg.act) for l in enc.enc_layers]
         pe = enc.pos_encoding.table(ids.device)
         hid, hid_lp, saved, weights = engine.encoder_fwd(ids32, enc.embedding.weight.data, pe, Ws, cfg,
-                                                         mask, _next_seed(), enc.training, want_w)
+                                                         mask, _next_seed(), enc.training, want_w,
+                                                         keep_p=any(ctx.needs_input_grad))
         ctx.cfg, ctx.Ws, ctx.saved, ctx.enc = cfg, Ws, saved, enc
         ctx.V = enc.embedding.weight.shape[0]
         ctx.shape = (B, Lq, cfg.d)

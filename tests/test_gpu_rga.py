@@ -161,6 +161,7 @@ def test_rga_fwd_tcgen05(B, h, L, max_seq, causal, pad, dtype):
 
 @pytest.mark.parametrize("B,h,L,max_seq,pad", [
     (1, 1, 128, 128, False),
+    (2, 2, 64, 64, False),             # less than one tile (the parity fixtures' shape)
     (2, 2, 256, 256, False),
     (1, 2, 200, 256, False),           # ragged L < max_seq
     (1, 2, 384, 512, True),
@@ -182,6 +183,7 @@ def test_rga_bwd_tcgen05(B, h, L, max_seq, pad, spill):
 
 @pytest.mark.parametrize("B,h,L,max_seq,pad,scale", [
     (1, 1, 128, 128, False, 1.0),
+    (2, 2, 64, 64, False, 1.0),
     (2, 2, 256, 256, False, 1.0),
     (1, 2, 200, 256, False, 1.0),           # ragged L < max_seq
     (1, 2, 384, 512, True, 1.0),

@@ -38,6 +38,9 @@ int rga_bwd3_dqe(const RgaArgs& a, const void* ws, const CUtensorMap& tmK, const
 int rga_bwd4_dkv(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tmV, const CUtensorMap& tmDO,
                  void* ds_ws, int qk_fmt, float gscale, cudaStream_t st);      // rga_tc_bwd4.cu
 
+int rga_bwd4_dqe(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                 const CUtensorMap& tmDO, const CUtensorMap& tmE, int qk_fmt, float gscale, cudaStream_t st);      // rga_tc_bwd4q.cu
+
 constexpr float MIXED_GSCALE = 4096.f;
 // bytes of the mixed mode's extra workspace region: the scaled f16 copy of a dense [B, L, h, dh] dO
 size_t rga_bwd_mixed_extra_bytes(int64_t B, int64_t h, int64_t L, int64_t dh) { return (size_t)(B * L * h * dh) * 2; }
@@ -86,10 +89,16 @@ int rga_bwd_tc(const RgaArgs& a_in, int dh, int dtype, void* ws, size_t ws_bytes
   if ((rc = tc::make_tmap_blhd(&tmDO, a.dO, dh, a.L, a.h, a.B, a.ol, a.oh, a.ob, DHC, TT))) return rc;
   if ((rc = tc::make_tmap_2d(&tmE, a.E, a.max_seq, dh, dh, DHC, TT))) return rc;
   if (a.pstash) {
-    // training step: the forward kept its P tiles (rga_tc_bwd4.cu)
+    // training step: the forward kept its P tiles -- both roles read them (rga_tc_bwd4.cu, rga_tc_bwd4q.cu), nothing is
+    // spilled.  MT_RGA_STASH_SPILL=1 keeps the intermediate variant (dK/dV from the stash spilling dS, consumers of
+    // rga_tc_bwd3.cu) for comparison.
+    static const bool via_spill = getenv("MT_RGA_STASH_SPILL") && atoi(getenv("MT_RGA_STASH_SPILL")) != 0;
+    if (!via_spill) {
+      if ((rc = rga_bwd4_dkv(a, tmQ, tmV, tmDO, nullptr, qk_fmt, gscale, st))) return rc;
+      return rga_bwd4_dqe(a, tmQ, tmK, tmV, tmDO, tmE, qk_fmt, gscale, st);
+    }
     if (!spill) { set_error("rga_bwd: the stash variant needs the workspace of mt_rga_bwd_workspace_bytes (%zu bytes)", need); return MT_E_WORKSPACE; }
-    static const bool timing_nospill = getenv("MT_BWD4_NOSPILL") != nullptr;      // (timing experiments only: dQ / dE are then garbage)
-    if ((rc = rga_bwd4_dkv(a, tmQ, tmV, tmDO, timing_nospill ? nullptr : ws, qk_fmt, gscale, st))) return rc;
+    if ((rc = rga_bwd4_dkv(a, tmQ, tmV, tmDO, ws, qk_fmt, gscale, st))) return rc;
   } else if ((rc = rga_bwd2_dkv(a, tmQ, tmK, tmV, tmDO, tmE, spill ? ws : nullptr, qk_fmt, gscale, st))) return rc;
   if (spill) {
     // one consumer pass over the dS tiles (dQ and dE together); MT_RGA_SPLIT_CONSUMERS=1 keeps the two separate launches

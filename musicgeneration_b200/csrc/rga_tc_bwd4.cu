@@ -433,9 +433,11 @@ int rga_bwd4_dkv(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tm
   p.trace = nullptr; p.trace_z = 0;
   // consecutive heads of one (batch row, key tile) share a CTA: as many as leave at least three CTAs per SM
   static const int hpc_env = getenv("MT_DKV_HPC") ? atoi(getenv("MT_DKV_HPC")) : 0;
+  // (measured at config B, 16 x 8 heads x 16 tiles: 8 heads per CTA 0.546 ms for the two kernels, 4 heads 0.560 ms, 2 heads
+  // 0.587 ms -- the per-CTA fixed cost, ~17 k cycles, outweighs the coarser balance down to ~1.5 CTAs per SM)
   int hpc = 1;
-  for (int c = 4; c > 1; c >>= 1)
-    if ((int64_t)((a.h + c - 1) / c) * a.B * p.nT >= 3 * (int64_t)sm_count()) { hpc = c; break; }
+  for (int c = 8; c > 1; c >>= 1)
+    if (2 * (int64_t)((a.h + c - 1) / c) * a.B * p.nT >= 3 * (int64_t)sm_count()) { hpc = c; break; }
   if (hpc_env > 0) hpc = hpc_env;
   p.heads_per_cta = hpc > a.h ? a.h : hpc;
   const dim3 grid((a.h + p.heads_per_cta - 1) / p.heads_per_cta, a.B, p.nT);

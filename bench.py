@@ -55,6 +55,16 @@ def flops_per_token(d, V, layers, L):
     return layers * (30 * d * d + 9 * L * d) + 6 * d * V
 
 
+def traffic_of(kernel: str):
+    """(bytes per launch, source file) of the last ncu --set full capture summarised in profiles/roofline_traffic.json."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            t = json.load(f)[kernel]
+        return float(t["bytes"]), t["source"]
+    except Exception:
+        return None, None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -453,15 +463,16 @@ def run_ours(args):
                     "h2d_bytes_per_step": 2 * Bg * L * 4, "d2h_bytes_per_step": 4, "last_loss": last,
                     "loss_read": "every step, pinned + async, consumed one step late"},
             "gpu_launches": launches,
-            "roofline": {"kernel": "rga_bwd (relative attention backward of one layer: delta + dK/dV kernel that "
-                                   "spills dS + dQ kernel + dE kernel, one C-ABI call)", "bound": "tensor",
+            "roofline": {"kernel": "rga_bwd (relative attention backward of one layer, one C-ABI call mt_rga_bwd_stash: delta + "
+                                   "dK/dV kernel + dQ/dE kernel, both reading the P tiles the forward kept)", "bound": "tensor",
                          "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                          "frac": ach / pk["tf_sust"],
-                         # dram__bytes_read+write of the four kernels of one call, ncu --set full capture of the
-                         # config-B layer shape (profiles/r1e_ncu_attention_kernels.summary.txt); algorithmic
-                         # operand bytes (q,k,v,O,dO,dq,dk,dv once) are 0.27 GB -- the rest is the dS workspace
-                         "traffic": 2.23e9 if (args.config == "B" and Bg == 16) else None,
-                         "traffic_source": "profiles/r1e_ncu_attention_kernels.summary.txt",
+                         # dram__bytes_read+write of the kernels of one call from the ncu --set full capture of the
+                         # config-B layer shape named in profiles/roofline_traffic.json (written by the capture's
+                         # summary step); algorithmic operand bytes (q,k,v,O,dO,dq,dk,dv once) are 0.27 GB -- the rest
+                         # is the P stash read by either kernel and operand tiles that miss in L2
+                         "traffic": traffic_of("rga_bwd")[0] if (args.config == "B" and Bg == 16) else None,
+                         "traffic_source": traffic_of("rga_bwd")[1],
                          "peak_source": pk["src"] + " sustained",
                          "ms_per_launch": bwd_ms, "flops_per_launch": bwd_flops,
                          "fwd_ms_per_launch": fwd_ms,

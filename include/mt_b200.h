@@ -238,6 +238,25 @@ int mt_decode_sample(const float* logits, const float* u, int32_t* ids, int64_t 
                      int32_t prior_len, int64_t B, int64_t V, float temperature, int32_t top_k, int greedy,
                      void* stream);
 int mt_decode_advance(int32_t* t_dev, void* stream);
+
+/* ---- the whole generation as ONE persistent launch (MT/network.py:52-77) --------------------------------------------
+ * One CTA per SM stays resident and walks, for positions t0 .. t0 + n_steps - 1 of `ids` [B, ld_ids]: embedding + PE ->
+ * every encoder layer (QKV projection, KV-cached relative attention incl. the append of the new K / V rows, fc,
+ * residual + LayerNorm, FFN, residual + LayerNorm) -> vocabulary projection -> sampler (mt_sample's arithmetic; the
+ * event drawn at position t becomes the token at t + 1 unless t + 1 < prior_len), separated by grid-wide barriers.
+ * 16-bit mode only (B <= 64, head dim 64, d <= 1024): weights bf16 ([N, K] row-major), except that a layer
+ * with layer_f16[l] != 0 has f16 Wqkv / Wfc / E / KV cache (the first layer of the bf16 mode).
+ * layer_ptrs: [layers][15] device pointers {Wqkv, bqkv, Wfc, bfc, Wpre, bpre, Wsuf, bsuf, g1, b1, g2, b2, E, kcache,
+ * vcache} (biases / LayerNorm parameters fp32; caches [B, h, max_seq, 64]).  uniforms [n_steps.., B] as mt_decode_sample.
+ * logits_out (optional) [n_steps, B, V] receives every step's logits.  workspace: mt_decode_run_workspace_bytes(),
+ * 256-byte aligned.  Cooperative launch: needs the device to itself for the duration of the call. */
+size_t mt_decode_run_workspace_bytes(int64_t B, int64_t d, int64_t V);
+int mt_decode_run_supported(int64_t B, int64_t d, int64_t h, int64_t V, int64_t layers);
+int mt_decode_run(int32_t* ids, int64_t ld_ids, int64_t B, int64_t t0, int64_t n_steps, int64_t prior_len,
+                  const float* emb, const float* pe, const void* const* layer_ptrs, const int32_t* layer_f16,
+                  int64_t layers, const void* Wv, const float* bv, int64_t d, int64_t h, int64_t V, int64_t max_seq,
+                  int32_t pad_token, uint8_t* pad_bits, const float* uniforms, float temperature, int32_t top_k,
+                  int greedy, float* logits_out, void* workspace, size_t workspace_bytes, void* stream);
 /* Programmatic dependent launch for the kernels of a decode step (strip GEMM, residual+LayerNorm,
  * mt_decode_*): while enabled, each of them may start launching before its predecessor in the
  * stream has drained and waits for it on the device (griddepcontrol), which hides most of the

@@ -63,6 +63,10 @@ SIGNATURES = {
     "mt_decode_attend": (_int, [_p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _int, _int, _p, C.c_size_t, _p]),
     "mt_decode_sample": (_int, [_p, _p, _p, _i64, _p, _i32, _i64, _i64, _f, _i32, _int, _p]),
     "mt_decode_advance": (_int, [_p, _p]),
+    "mt_decode_run_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "mt_decode_run_supported": (_int, [_i64, _i64, _i64, _i64, _i64]),
+    "mt_decode_run": (_int, [_p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _i64,
+                             _i32, _p, _p, _f, _i32, _int, _p, _p, _sz, _p]),
     "mt_decode_chain": (_int, [_int]),
     "mt_window_gather": (_int, [_p, _int, _p, _p, _p, _i64, _i64, _i64, _i64, _p]),
     "mt_window_sample": (_int, [_p, _p, _i64, _i64, _u64, _u64, _p, _p, _i64, _p]),

@@ -84,8 +84,9 @@ class MusicTransformer(torch.nn.Module, _PrecisionMixin):
         max_seq (no sliding window -- see generate_literal for the reference's literal loop).
         ``uniforms`` [length, B] fixes the random draws (tests); default torch.rand.
         ``return_logits``: also the last-position logits of every generated event [length, B, V].
-        ``graph``: replay one captured CUDA graph per event (default unless return_logits) or launch
-        every step from the host."""
+        ``graph``: None (default) = the persistent decode kernel (one launch for the whole generation) where it takes
+        the model and pays (16-bit mode, B <= 32: _DecodeSession.persistent_default), else one captured CUDA graph
+        replayed per event; True = the graph path; False = every step launched from the host."""
         if not prior.is_cuda:
             raise RuntimeError("musicgeneration_b200 runs on CUDA tensors only (no CPU fallback)")
         temperature = self.temperature if temperature is None else temperature
@@ -98,9 +99,10 @@ class MusicTransformer(torch.nn.Module, _PrecisionMixin):
         dec = _DecodeSession(self, B)
         ids = torch.zeros((B, P + length), dtype=torch.int32, device=prior.device)
         ids[:, :P] = prior.to(torch.int32)
+        persistent = graph is None and dec.persistent_default()
         if graph is None:
-            graph = not return_logits
-        if graph and P + length - 1 >= 4:
+            graph = persistent or not return_logits
+        if graph and (persistent or P + length - 1 >= 4):
             # one CUDA graph of a whole decode step (device-resident step index), replayed per event
             if greedy:
                 u = None
@@ -110,7 +112,8 @@ class MusicTransformer(torch.nn.Module, _PrecisionMixin):
                 u = torch.rand((length, B), dtype=torch.float32, device=prior.device)
             rec = torch.empty((P + length - 1, B, self.vocab_size), dtype=torch.float32, device=prior.device) \
                 if return_logits else None
-            dec.run_graph(ids, P, P + length - 1, u, float(temperature), int(top_k), bool(greedy), logits_out=rec)
+            run = dec.run_persistent if persistent else dec.run_graph
+            run(ids, P, P + length - 1, u, float(temperature), int(top_k), bool(greedy), logits_out=rec)
             return (ids.to(torch.int64), rec[P - 1:]) if return_logits else ids.to(torch.int64)
         step_logits = []
         logits = None
@@ -130,7 +133,7 @@ class MusicTransformer(torch.nn.Module, _PrecisionMixin):
         return (out, torch.stack(step_logits)) if return_logits else out
 
     @torch.no_grad()
-    def decode_logits(self, ids: torch.Tensor) -> torch.Tensor:
+    def decode_logits(self, ids: torch.Tensor, graph: Optional[bool] = None) -> torch.Tensor:
         """Teacher-forced KV-cached pass over given ids [B, n] on the decode path (one graph replay per
         position): logits [n, B, V], entry t = the distribution of token t+1 given ids[:, :t+1] under the
         causal mask.  The same launches ``generate`` replays; used to score sequences and by the parity tests."""
@@ -143,7 +146,11 @@ class MusicTransformer(torch.nn.Module, _PrecisionMixin):
         buf = torch.zeros((B, n + 1), dtype=torch.int32, device=ids.device)
         buf[:, :n] = ids.to(torch.int32)
         rec = torch.empty((n, B, self.vocab_size), dtype=torch.float32, device=ids.device)
-        dec.run_graph(buf, n + 1, n, None, 1.0, 0, True, logits_out=rec)      # prior_len n+1: nothing is sampled
+        # prior_len n+1: nothing is sampled
+        if graph is None and dec.persistent_default():
+            dec.run_persistent(buf, n + 1, n, None, 1.0, 0, True, logits_out=rec)
+        else:
+            dec.run_graph(buf, n + 1, n, None, 1.0, 0, True, logits_out=rec)
         return rec
 
     @torch.no_grad()
@@ -213,6 +220,45 @@ class _DecodeSession:
         # pad bit per cached position: a generated/prior pad token is masked as a key, exactly as
         # the look-ahead mask of MT/utils.py:73 does in the reference's recompute
         self.pad_bits = torch.zeros((B, cfg.max_seq), dtype=torch.uint8, device=dev)
+
+    # ---- persistent mode: the whole generation is one launch (csrc/decode_step.cu) ----------------
+    def persistent_ok(self) -> bool:
+        cfg = self.cfg
+        return (cfg.act == torch.bfloat16 and cfg.dh == 64 and cfg.gemm_path != L.PATH_SIMT
+                and cfg.attn_path != L.PATH_SIMT
+                and ops.decode_run_supported(self.B, cfg.d, cfg.h, self.V, len(self.Ws)))
+
+    def persistent_default(self) -> bool:
+        """Whether generate() takes the persistent kernel by itself.  Measured on B200 at config B (us per event,
+        persistent / graph path): 8 sequences 269 / 345, 32 sequences 463 / 472, 64 sequences 632 / 628 -- the one
+        launch wins where the step is launch- and fill-latency (few sequences) and ties once the KV stream and the
+        per-phase L2 traffic dominate, so it is the default up to 32 sequences.  MT_DECODE_PERSISTENT=1 / 0 forces it
+        on (wherever it is supported) / off."""
+        env = os.environ.get("MT_DECODE_PERSISTENT")
+        if env is not None:
+            return env != "0" and self.persistent_ok()
+        return self.B <= 32 and self.persistent_ok()
+
+    def run_persistent(self, ids, prior_len, n_steps, u, temperature, top_k, greedy, logits_out=None):
+        """Positions 0 .. n_steps-1 of ``ids`` [B, >= n_steps+1] in ONE launch (same contract as run_graph)."""
+        cfg = self.cfg
+        rows, f16 = [], []
+        for li, W in enumerate(self.Ws):
+            hp = self.lact[li] != cfg.act
+            ts = [W.Wqkv_hp if hp else W.Wqkv, W.bqkv, W.Wfc_hp if hp else W.Wfc, W.bfc, W.Wpre, W.bpre, W.Wsuf, W.bsuf,
+                  W.g1, W.b1, W.g2, W.b2, W.E_hp if hp else W.E, self.kc[li], self.vc[li]]
+            for x in ts:
+                if not x.is_contiguous():
+                    raise RuntimeError("decode_run: non-contiguous layer operand")
+            rows.append([x.data_ptr() for x in ts])
+            f16.append(1 if hp else 0)
+            self._keep = getattr(self, "_keep", []) + ts
+        ptrs = torch.tensor(rows, dtype=torch.int64)
+        flags = torch.tensor(f16, dtype=torch.int32)
+        ws = torch.empty(L.load().mt_decode_run_workspace_bytes(self.B, cfg.d, self.V), dtype=torch.uint8,
+                         device=self.emb.device)
+        ops.decode_run(ids, 0, n_steps, prior_len, self.emb, self.pe, ptrs, flags, self.Wv, self.bv, cfg.d, cfg.h,
+                       cfg.max_seq, config.pad_token, self.pad_bits, u, temperature, top_k, greedy, logits_out, ws)
 
     # ---- graph mode: every buffer preallocated, the position read from device memory ----------
     def _alloc_step_buffers(self):

@@ -334,6 +334,22 @@ def decode_sample(logits, u, ids, t_dev, prior_len, temperature, top_k, greedy):
             "decode_sample")
 
 
+def decode_run_supported(B, d, h, V, layers) -> bool:
+    return bool(L.load().mt_decode_run_supported(B, d, h, V, layers))
+
+
+def decode_run(ids, t0, n_steps, prior_len, emb, pe, layer_ptrs, layer_f16, Wv, bv, d, h, max_seq, pad_token, pad_bits,
+               uniforms, temperature, top_k, greedy, logits_out, ws):
+    """The whole generation in one persistent launch (include/mt_b200.h: mt_decode_run).  ``layer_ptrs``: host int64
+    tensor [layers, 15] of device addresses, ``layer_f16``: host int32 tensor [layers]."""
+    B, ld = ids.shape
+    V = Wv.shape[0]
+    L.check(L.load().mt_decode_run(_ptr(ids), ld, B, t0, n_steps, prior_len, _ptr(emb), _ptr(pe),
+                                   layer_ptrs.data_ptr(), layer_f16.data_ptr(), layer_ptrs.shape[0], _ptr(Wv), _ptr(bv),
+                                   d, h, V, max_seq, pad_token, _ptr(pad_bits), _ptr(uniforms), temperature, top_k,
+                                   int(greedy), _ptr(logits_out), _ptr(ws), ws.numel(), _stream()), "decode_run")
+
+
 def decode_chain(enable: bool):
     """Programmatic dependent launch for the kernels of a decode step (see include/mt_b200.h)."""
     L.load().mt_decode_chain(int(enable))

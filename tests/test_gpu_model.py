@@ -430,9 +430,10 @@ def test_config_b_fp32_against_reference_summary():
     assert e < 1e-5 and abs(loss - float(z["loss"])) < 1e-5 * float(z["loss"])
 
 
-@pytest.mark.parametrize("precision", ["bf16", "fp32"])
-def test_config_b_decode_graph_path_against_reference(precision):
-    """KV-cached decode of the benchmarked model on the CUDA-graph path bench.py times, 256 events from two
+@pytest.mark.parametrize("precision,graph", [("bf16", None), ("bf16", True), ("fp32", None)])
+def test_config_b_decode_graph_path_against_reference(precision, graph):
+    """KV-cached decode of the benchmarked model on the paths bench.py times (graph=None: the persistent decode kernel
+    in the bf16 mode -- one launch for the whole generation --, the CUDA-graph path otherwise), 256 events from two
     8-token priors (one with a pad token inside), against the unmodified reference's causal recompute:
     teacher-forced step logits (bf16: 1e-2 relative over all steps, fp32: 1e-5), arg-max agreement with the
     reference's greedy ids, and the free-running greedy ids (fp32: bit-exact; bf16: agreement rate)."""
@@ -444,11 +445,14 @@ def test_config_b_decode_graph_path_against_reference(precision):
     ref_ids = torch.from_numpy(z["causal_ids"])
     ref_logits = torch.from_numpy(z["causal_logits"])          # [256, 2, V]
     P, steps = prior.shape[1], ref_logits.shape[0]
-    tf = m.decode_logits(ref_ids[:, :-1].to(dev))[P - 1:].cpu()
+    if precision == "bf16" and graph is None:      # (this case must really run the persistent kernel, not fall back)
+        from musicgeneration_b200.network import _DecodeSession
+        assert _DecodeSession(m, prior.shape[0]).persistent_ok()
+    tf = m.decode_logits(ref_ids[:, :-1].to(dev), graph=graph)[P - 1:].cpu()
     e = rel(tf, ref_logits)
     per_step = ((tf - ref_logits).flatten(1).norm(dim=1) / ref_logits.flatten(1).norm(dim=1)).max()
     agree = float((tf.argmax(-1).t() == ref_ids[:, P:]).float().mean())
-    ids = m.generate(prior, length=steps, greedy=True).cpu()
+    ids = m.generate(prior, length=steps, greedy=True, graph=graph).cpu()
     same = (ids == ref_ids)
     first_div = [int((~same[b]).nonzero()[0]) if (~same[b]).any() else ids.shape[1] for b in range(ids.shape[0])]
     print(f"config B decode {precision}: teacher-forced logits rel {e:.3e} (worst step {float(per_step):.3e}), "
@@ -458,6 +462,30 @@ def test_config_b_decode_graph_path_against_reference(precision):
     else:
         assert e < 1e-2 and float(per_step) < 3e-2
         assert agree >= 0.97
+
+
+def test_persistent_decode_matches_the_graph_path():
+    """The persistent decode kernel (one launch per generation) against the per-kernel CUDA-graph path on the small
+    fixture model in the bf16 mode: same operands and arithmetic, different summation order -- teacher-forced logits
+    within 2e-3, sampled ids (given uniforms, top-k) equal wherever the two logits agree on the draw."""
+    dev = torch.device("cuda:0")
+    z = load("decode_small.npz")
+    m, (d, V, pad, layers, L) = build_model(z, dev, precision="bf16")
+    m.eval()
+    from musicgeneration_b200.network import _DecodeSession
+    assert _DecodeSession(m, 5).persistent_ok()
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(0, V - 2, (5, 48), generator=g)
+    ids[1, 7] = pad
+    a = m.decode_logits(ids.to(dev))
+    b = m.decode_logits(ids.to(dev), graph=True)
+    assert rel(a.cpu(), b.cpu()) < 2e-3
+    prior = ids[:, :6].to(dev)
+    u = torch.rand(20, 5, generator=g).to(dev)
+    ia = m.generate(prior, length=20, temperature=0.9, top_k=8, greedy=False, uniforms=u)
+    ib = m.generate(prior, length=20, temperature=0.9, top_k=8, greedy=False, uniforms=u, graph=True)
+    assert float((ia == ib).float().mean()) > 0.9
+    assert (ia[:, :6].cpu() == ids[:, :6]).all()
 
 
 def test_causality_and_batch_independence_property():

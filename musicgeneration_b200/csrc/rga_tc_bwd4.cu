@@ -435,9 +435,12 @@ int rga_bwd4_dkv(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tm
   static const int hpc_env = getenv("MT_DKV_HPC") ? atoi(getenv("MT_DKV_HPC")) : 0;
   // (measured at config B, 16 x 8 heads x 16 tiles: 8 heads per CTA 0.546 ms for the two kernels, 4 heads 0.560 ms, 2 heads
   // 0.587 ms -- the per-CTA fixed cost, ~17 k cycles, outweighs the coarser balance down to ~1.5 CTAs per SM)
+  // ... but the longest CTA (c heads x nT steps) must stay near the per-SM average of the launch, or it alone sets the
+  // makespan (config C, 12 heads x 32 tiles: 8 + 4 heads per CTA made the longest CTA 256 steps against an average of 171)
   int hpc = 1;
+  const int64_t avg_steps = (int64_t)a.B * a.h * p.nTri / sm_count();
   for (int c = 8; c > 1; c >>= 1)
-    if (2 * (int64_t)((a.h + c - 1) / c) * a.B * p.nT >= 3 * (int64_t)sm_count()) { hpc = c; break; }
+    if (2 * (int64_t)((a.h + c - 1) / c) * a.B * p.nT >= 3 * (int64_t)sm_count() && 10 * (int64_t)c * p.nT <= 11 * avg_steps) { hpc = c; break; }
   if (hpc_env > 0) hpc = hpc_env;
   p.heads_per_cta = hpc > a.h ? a.h : hpc;
   const dim3 grid((a.h + p.heads_per_cta - 1) / p.heads_per_cta, a.B, p.nT);

@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "libmt_b200.so")
 SOURCES = ["elementwise.cu", "gemm_simt.cu", "rga_simt.cu", "decode.cu", "decode_step.cu", "gemm_tc.cu", "gemm_skinny.cu", "rga_tc.cu", "rga_tc_bwd.cu", "rga_tc_bwd2.cu", "rga_tc_bwd3.cu", "rga_tc_bwd4.cu", "rga_tc_bwd4q.cu",
            "feed.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"] + os.environ.get("MT_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

@@ -31,6 +31,10 @@ namespace {
 // the key-column quarter qt = w>>2, i.e. 32 logits per thread and step.  Four warps per scheduler
 // hide each other's TMEM / shared-memory / MUFU latency; the per-thread state stays below the
 // 112-register budget of a 576-thread CTA.
+// 1: the skew runs through the register barrel shifter (rga_tc_common.cuh) instead of the per-thread scratch
+#ifndef MT_FWD_SKEW_REGS
+#define MT_FWD_SKEW_REGS 0
+#endif
 constexpr int FW_MATH_WARPS = 16;
 constexpr int FW_MATH_THREADS = FW_MATH_WARPS * 32;
 constexpr int FW_THREADS = FW_MATH_THREADS + 64;     // + TMA producer warp + MMA issuer warp
@@ -255,8 +259,13 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const uint32_t g_lo = tmem + ((jt & 1) ? TM_G1 : TM_G0);
       const uint32_t g_hi = tmem + (((jt + 1) & 1) ? TM_G1 : TM_G0);
 
-      // band window -> scratch, then S; the skewed read of the scratch overlaps the S load
+      // band window -> scratch (or, MT_FWD_SKEW_REGS, registers), then S; the skewed read of the scratch overlaps the S load
+#if MT_FWD_SKEW_REGS
+      uint32_t Wn[32];
+      skew_window_64(g_lo, g_hi, lane_base, w0, Wn);
+#else
       skew_park_64(g_lo, g_hi, lane_base, w0, scr);
+#endif
       float sv[32];
       {
         uint32_t r[32];
@@ -269,7 +278,11 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc::tc_fence_before();
       tc::mbar_arrive(s_consumed);
       if (threadIdx.x == 0) FTRACE(0, g, 2);
+#if MT_FWD_SKEW_REGS
+      skew_shift_add_32(sv, Wn, lane);
+#else
       skew_fetch_add_32(sv, scr, lane);
+#endif
 
       // ---- mask (only on the diagonal / ragged / padded tiles) + online softmax (log2 domain)
       const bool diag = p.causal && (j0 == i0);

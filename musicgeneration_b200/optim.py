@@ -8,6 +8,8 @@ state_dict keys and shapes are untouched; Wq/Wk/Wv stay adjacent so the fused QK
 repacking)."""
 from __future__ import annotations
 
+import os
+
 from typing import Iterable, List, Optional
 
 import torch
@@ -102,7 +104,7 @@ class FlatAdam:
         self.flat_lp = None           # 16-bit shadow of flat_p, (re)written by refresh_lp()
         # ---- gradient-exchange buckets: the backward finishes the vocabulary projection first, then
         # the encoder layers last to first, then the embedding; a bucket = one layer's contiguous range (the
-        # embedding rides with layer 0, the vocabulary projection is its own bucket).  Models without
+        # embedding and the vocabulary projection are buckets of their own).  Models without
         # ``enc_layers.<i>.`` parameter names get a single bucket.
         import re
         names = {id(p): n for n, p in model.named_parameters()}
@@ -113,6 +115,11 @@ class FlatAdam:
             key_of.append(int(mname.group(1)) if mname else None)
         first_layer = next((k for k in key_of if k is not None), None)
         cur, keys = (first_layer if first_layer is not None else 0), []
+        # MT_DDP_SPLIT_EMB=1: the parameters in front of the first layer (the embedding, whose gradient is the LAST
+        # thing the backward produces) get a bucket of their own, so that layer 0's bucket -- 16 x larger -- goes on
+        # the wire one kernel earlier
+        if os.environ.get("MT_DDP_SPLIT_EMB", "1") != "0" and first_layer is not None:
+            cur = -1
         seen_layer = False
         for k in key_of:
             if k is not None:
@@ -135,7 +142,6 @@ class FlatAdam:
         self._hook_hits = {}
         # MT_DDP_MODE: "overlap" (default: buckets go on the wire during the backward), "single" (everything at
         # step(), the round-1 behaviour), "none" (no exchange at all -- timing experiments only)
-        import os
         self._ddp_mode = os.environ.get("MT_DDP_MODE", "overlap")
         self.sync_grads = True        # False on the non-final micro-batches of an accumulation window (DDP no_sync)
         for p in order:

@@ -26,6 +26,10 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
+            # the per-layer gradient buckets (a few MB each) run UNDER the backward, whose kernels fill every SM: a
+            # communicator that takes fewer SMs hides better than one that moves the bytes a little faster (8 GPUs,
+            # config B: 9.82 -> 9.77 ms per step); the user's own setting wins
+            os.environ.setdefault("NCCL_MAX_CTAS", "8")
             torch.cuda.set_device(local)
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         else:

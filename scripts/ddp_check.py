@@ -6,7 +6,7 @@ Every rank runs the config-B model (dropout 0) on its own batch.  (1) local grad
 (sync_grads = False), all-gathered -> the expected sum; (2) the same backward with the bucketed exchange on:
 the flat gradient buffer after finish() must equal that sum on every rank (1e-5 of the largest gradient: two
 backward passes differ by the order of the fp32 dE reductions), every bucket must have been started DURING the backward in the order
-vocabulary, layer n-1 .. 0, and the Adam step must leave all replicas identical."""
+vocabulary, layer n-1 .. 0, embedding, and the Adam step must leave all replicas identical."""
 import os
 import sys
 
@@ -51,7 +51,7 @@ def main():
     torch.cuda.synchronize()
     err = float((opt.flat_g - expect).abs().max())
     scale = float(expect.abs().max())
-    ok = (w == world and started_in_backward == [layers] + list(range(layers - 1, -1, -1))
+    ok = (w == world and started_in_backward == [layers + 1] + list(range(layers, -1, -1))        # vocabulary, layers n-1 .. 0, embedding
           and err <= 1e-5 * scale)      # (two backward passes differ by the order of the dE reductions)
     opt.exchange.works = []
     opt.step_count += 1

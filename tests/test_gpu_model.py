@@ -106,10 +106,10 @@ def test_flat_adam_gradients_written_in_place_match_fixture():
 
 
 def test_flat_adam_buckets_follow_the_backward_order():
-    """Gradient-exchange buckets: one contiguous range of the flat buffer per encoder layer (the
-    embedding rides with layer 0), the vocabulary projection last in memory and FIRST to complete; the backward
-    reports the buckets complete in the order vocabulary, layer n-1 ... layer 0 -- the order their all-reduces
-    are started under data parallelism (the NCCL side is covered by the gloo test and the multi-GPU bench)."""
+    """Gradient-exchange buckets: the embedding (first in memory, LAST to complete), then one contiguous
+    range of the flat buffer per encoder layer, then the vocabulary projection (last in memory, FIRST to complete); the
+    backward reports the buckets complete in the order vocabulary, layer n-1 ... layer 0, embedding -- the order their
+    all-reduces are started under data parallelism (the NCCL side is covered by the gloo test and the multi-GPU bench)."""
     import musicgeneration_b200 as mtb
     from musicgeneration_b200.optim import FlatAdam
     dev = torch.device("cuda:0")
@@ -118,19 +118,19 @@ def test_flat_adam_buckets_follow_the_backward_order():
     m.train()
     opt = FlatAdam(m, lr=0.0)
     bk = opt.exchange.buckets
-    assert len(bk) == layers + 1
+    assert len(bk) == layers + 2
     assert all(bk[i][1] == bk[i + 1][0] for i in range(len(bk) - 1)) and bk[0][0] == 0 and bk[-1][1] == opt.n
     names = dict((id(p), n) for n, p in m.named_parameters())
     for p, off in zip(opt.params, opt._offsets):
         b = opt._bucket_of[id(p)]
         assert bk[b][0] <= off and off + p.numel() <= bk[b][1]
         n = names[id(p)]
-        want = layers if n.startswith("fc.") else (0 if "embedding" in n else int(n.split("enc_layers.")[1].split(".")[0]))
+        want = layers + 1 if n.startswith("fc.") else (0 if "embedding" in n else 1 + int(n.split("enc_layers.")[1].split(".")[0]))
         assert b == want, (n, b)
     x, y = torch.from_numpy(z["x"]).to(dev), torch.from_numpy(z["y"]).to(dev)
     opt.zero_grad()
     mtb.SmoothCrossEntropyLoss(0.1, V, pad)(m(x), y).backward()
-    assert opt.ready_order == [layers] + list(range(layers - 1, -1, -1))
+    assert opt.ready_order == [layers + 1] + list(range(layers, -1, -1))
     opt.step()                                     # one rank: finish() is a no-op
     # accumulation window: nothing is reported complete while sync_grads is off
     opt.zero_grad()

@@ -375,7 +375,7 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           __stcs(dst + 32 * c, make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]));
-        if (qt == 0) p.mrow[tix * TT + a] = m_use;
+        if ((qt & 1) == 0) p.mrow[(tix * 2 + (qt >> 1)) * TT + a] = m_use;      // [tile][key half][row]: one reference for both halves here
       }
       if (++jt < n_kt) continue;
 
@@ -427,14 +427,23 @@ rga_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
+// Measured and dropped (round 2): a second-generation forward with TWO SOFTMAX GROUPS ON THE TWO KEY HALVES of a tile --
+// groups A / B own keys 0..63 / 64..127 of every tile, each with its own S sub-accumulator (N = 64 product), online
+// softmax and O accumulator (P overwriting the S sub-accumulator frees the TMEM columns of the second O), merged at the
+// end of a head like split-KV decoding.  Parity-green on every case of tests/test_gpu_rga.py, but 0.312 ms against
+// 0.286 ms per config-B layer: the G ring still couples the groups every step (a block may only be overwritten when BOTH
+// have parked their windows, and the next S product is committed behind the next G), so they never drift apart by more
+// than one parking phase, and the N = 64 score products fetch the Q operand twice.  Real alternation (one group per key
+// tile, as in the backward kernels) needs S and the G ring twice: 640 TMEM columns at 128-key steps.
+
 }  // namespace
 
 bool rga_bwd_tc_supported(const RgaArgs& a, int dh, int dtype);   // rga_tc_bwd.cu
 
-// P stash of a training forward: B h nT (nT + 1) / 2 tile images of 32 KB, then as many [128] fp32 row references
+// P stash of a training forward: B h nT (nT + 1) / 2 tiles of 32 KB, then per tile [2 key halves][128 rows] fp32 row references
 size_t rga_stash_bytes(int64_t B, int64_t h, int64_t L) {
   const int64_t nT = (L + TT - 1) / TT;
-  return (size_t)(B * h * (nT * (nT + 1) / 2)) * (size_t)(2 * TILE + TT * 4);
+  return (size_t)(B * h * (nT * (nT + 1) / 2)) * (size_t)(2 * TILE + 2 * TT * 4);
 }
 
 bool rga_tc_supported(const RgaArgs& a, int dh, int dtype, bool backward) {

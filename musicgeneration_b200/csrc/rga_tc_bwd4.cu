@@ -151,7 +151,7 @@ rga_bwd4_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (i3 < n_items) {
             const int64_t tix = tile_index(p, b, hh0 + i3, jt + k3, jt);
             tc::bulk_prefetch_l2(p.stash + tix * (int64_t)PT_BYTES, PT_BYTES);
-            tc::bulk_prefetch_l2(p.mrow + tix * TT, TT * 4);
+            tc::bulk_prefetch_l2(p.mrow + tix * 2 * TT, 2 * TT * 4);
             if ((p.L & 3) == 0) {
               const int i3row = (jt + k3) * TT;
               const int64_t ro = ((int64_t)b * p.h + hh0 + i3) * p.L + i3row;
@@ -275,7 +275,7 @@ rga_bwd4_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // (raw values only: any arithmetic here would wait for the loads inside the fetch)
         lse_raw = 0.f; d_raw = 0.f;
         if (i < p.L) { lse_raw = __ldg(p.lse + ro); d_raw = __ldg(p.delta + ro); }
-        mref = __ldg(p.mrow + tix * TT + a);
+        mref = __ldg(p.mrow + (tix * 2 + hq) * TT + a);       // the row reference of this thread's key half
         fk += 2;
         while (fk >= per) { fk -= per; ++fitem; }
       }
@@ -424,7 +424,7 @@ int rga_bwd4_dkv(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tm
   p.nT = (a.L + TT - 1) / TT;
   p.nTri = p.nT * (p.nT + 1) / 2;
   p.stash = static_cast<const uint8_t*>(a.pstash);
-  p.mrow = reinterpret_cast<const float*>(p.stash + (int64_t)a.B * a.h * p.nTri * (int64_t)PT_BYTES);
+  p.mrow = reinterpret_cast<const float*>(p.stash + (int64_t)a.B * a.h * p.nTri * (int64_t)PT_BYTES);      // then [tile][key half][128 rows] fp32
   p.ds_ws = static_cast<uint8_t*>(ds_ws);
   p.qk_fmt = qk_fmt;
   p.gscale = gscale;

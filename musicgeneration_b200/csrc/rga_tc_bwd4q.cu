@@ -166,7 +166,7 @@ rga_bwd4_dqe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (i3 < n_items) {
             const int64_t tix = tile_index_q(p, b, hh0 + i3, it, j3);
             tc::bulk_prefetch_l2(p.stash + tix * (int64_t)PT_BYTES, PT_BYTES);
-            tc::bulk_prefetch_l2(p.mrow + tix * TT, TT * 4);
+            tc::bulk_prefetch_l2(p.mrow + tix * 2 * TT, 2 * TT * 4);
           }
         }
         if (++jt == per) { jt = 0; ++item; }
@@ -391,7 +391,7 @@ rga_bwd4_dqe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // tile (head hh0 + x, it, j) of the stash = tile0 + x nTri + j; the row statistics of head hh0 + x = row0 + x L
     const int64_t tile0 = tile_index_q(p, b, hh0, it, 0);
     const uint8_t* const stash0 = p.stash + tile0 * (int64_t)PT_BYTES + my_off;
-    const float* const mrow0 = p.mrow + tile0 * TT + a;
+    const float* const mrow0 = p.mrow + (tile0 * 2 + hq) * TT + a;        // [tile][key half][row]: this thread's half
     const bool row_ok = it * TT + a < p.L;
     const int64_t row0 = ((int64_t)b * p.h + hh0) * p.L + (row_ok ? it * TT + a : 0);
     auto fetch = [&](uint32_t (&R)[32], float& lse_raw, float& d_raw, float& mref) {
@@ -404,7 +404,7 @@ rga_bwd4_dqe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // (raw values only: any arithmetic here would wait for the loads inside the fetch)
         const int64_t ro = row0 + (int64_t)fitem * p.L;
         lse_raw = __ldg(p.lse + ro); d_raw = __ldg(p.delta + ro);
-        mref = __ldg(mrow0 + (int64_t)trel * TT);
+        mref = __ldg(mrow0 + (int64_t)trel * 2 * TT);
         fj += 2;
         while (fj >= per) { fj -= per; ++fitem; }
       }
@@ -566,7 +566,7 @@ int rga_bwd4_dqe(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tm
   p.nT = (a.L + TT - 1) / TT;
   p.nTri = p.nT * (p.nT + 1) / 2;
   p.stash = static_cast<const uint8_t*>(a.pstash);
-  p.mrow = reinterpret_cast<const float*>(p.stash + (int64_t)a.B * a.h * p.nTri * (int64_t)PT_BYTES);
+  p.mrow = reinterpret_cast<const float*>(p.stash + (int64_t)a.B * a.h * p.nTri * (int64_t)PT_BYTES);      // then [tile][key half][128 rows] fp32
   p.qk_fmt = qk_fmt;
   p.gscale = gscale;
   p.out_scale = 1.f / gscale;

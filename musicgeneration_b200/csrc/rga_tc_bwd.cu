@@ -92,7 +92,8 @@ int rga_bwd_tc(const RgaArgs& a_in, int dh, int dtype, void* ws, size_t ws_bytes
     // training step: the forward kept its P tiles -- both roles read them (rga_tc_bwd4.cu, rga_tc_bwd4q.cu), nothing is
     // spilled.  MT_RGA_STASH_SPILL=1 keeps the intermediate variant (dK/dV from the stash spilling dS, consumers of
     // rga_tc_bwd3.cu) for comparison.
-    static const bool via_spill = getenv("MT_RGA_STASH_SPILL") && atoi(getenv("MT_RGA_STASH_SPILL")) != 0;
+    const char* vs = getenv("MT_RGA_STASH_SPILL");      // (read per call: tests/test_gpu_rga.py switches it)
+    const bool via_spill = vs && atoi(vs) != 0;
     if (!via_spill) {
       if ((rc = rga_bwd4_dkv(a, tmQ, tmV, tmDO, nullptr, qk_fmt, gscale, st))) return rc;
       return rga_bwd4_dqe(a, tmQ, tmK, tmV, tmDO, tmE, qk_fmt, gscale, st);

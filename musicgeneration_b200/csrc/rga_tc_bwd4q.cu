@@ -63,7 +63,6 @@ struct BwdQParams {
   int qk_fmt;                                  // 1 = bf16; 0 = f16 (dO arrives as f16(g dO), g dS is packed as f16)
   float gscale, out_scale;                     // out_scale = 1 / g on dQ and dE
   float scale;
-  int dbg;                                     // timing experiments (MT_Q4_DBG): 1 = no band stores, 2 = no TMEM dS store
   long long* trace; int trace_z;               // MT_RGA_TRACE=z: clock64 stamps of CTA (0,0,z), [4 agents][32 steps][8 events]
 };
 
@@ -302,8 +301,9 @@ rga_bwd4_dqe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (erow0 < 0) {
           // the block that straddles E row 0 (max_seq not a multiple of the tile edge; once per head): a bulk-tensor
           // reduction at a negative row coordinate faults on sm_100a, so these rows leave through vector reductions
+          // (as the general flush they measured 0.66 vs 0.556 ms for the backward of a config-B layer)
           const int erow = erow0 + a;
-          if (erow >= 0) {
+          if (erow >= 0 && erow < p.max_seq) {
             float* dst = p.dE + (int64_t)erow * DHC;
 #pragma unroll
             for (int x = 0; x < 32; x += 4) {
@@ -469,7 +469,7 @@ rga_bwd4_dqe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const float d1 = fmaf(__uint_as_float(dp[2 * y + 1]), sf, -Dsf) * p1;
           D8[y] = HF ? pack_f16x2(d0, d1) : pack_bf16x2(d0, d1);
         }
-        if (!(p.dbg & 2)) tc::tmem_st_32x8(ds_addr + 8 * q, D8);      // A operand of dS . K_j: row = lane, 16 keys = 8 columns
+        tc::tmem_st_32x8(ds_addr + 8 * q, D8);      // A operand of dS . K_j: row = lane, 16 keys = 8 columns
         // band stores: words base_w + 8 q + y.  Three chunk addresses cover the eight (nine) words.  Branch-free: the
         // shift parity alternates from lane to lane, so the odd case is a byte permute with a per-lane selector (even
         // lanes select the word itself), and only the two ends of the run are 16-bit stores.
@@ -479,7 +479,7 @@ rga_bwd4_dqe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int y = 0; y < 8; ++y) {
           const uint32_t wp = (y < 4 ? (wcarry[y] ? ca1 : ca0) : (wcarry[y - 4] ? ca2 : ca1)) + woff[y & 3];
           const uint32_t ow = __byte_perm(y == 0 ? prev : D8[y - 1], D8[y], sel);
-          const bool ok = (w0 + y < wlim) && !(p.dbg & 1);
+          const bool ok = (w0 + y < wlim);
           if (q == 0 && y == 0) {                   // the run's first word: an odd shift owns its high half only
             sts16_if(wp + 2, ow >> 16, ok);
             sts16_if(wp, ow, ok && !odd);
@@ -489,7 +489,7 @@ rga_bwd4_dqe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         prev = D8[7];
         if (q == 3)                                 // odd shift: the run's last value is the low half of word base_w + 32
-          sts16_if(ca2 + woff[0], prev >> 16, odd && (w0 + 8 < wlim) && !(p.dbg & 1));
+          sts16_if(ca2 + woff[0], prev >> 16, odd && (w0 + 8 < wlim));
       }
       if (tr) TRACEQ(0, n, 3);
       tc::tmem_st_wait();
@@ -572,7 +572,6 @@ int rga_bwd4_dqe(const RgaArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tm
   p.out_scale = 1.f / gscale;
   p.scale = 1.f / a.inv_scale_div;
   p.trace = nullptr; p.trace_z = 0;
-  p.dbg = getenv("MT_Q4_DBG") ? atoi(getenv("MT_Q4_DBG")) : 0;
   CUtensorMap tmDE;
   int rc;
   if ((rc = tc::make_tmap_2d_f32(&tmDE, a.dE, a.max_seq, DHC, DHC, 32, TT))) return rc;

@@ -203,6 +203,18 @@ def test_rga_tcgen05_mixed_f16_qkv_bf16_io(B, h, L, max_seq, pad, scale, stash):
     assert max(r["dq"], r["dk"], r["dv"]) < 1.2e-2 and r["dE"] < 1.2e-2, r
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_rga_bwd_stash_with_spilled_ds_variant(monkeypatch, dtype):
+    """MT_RGA_STASH_SPILL=1: the intermediate training variant kept for comparison (dK/dV from the P stash, dS spilled
+    once, dQ / dE by the fused consumer of rga_tc_bwd3.cu) against the fp64 closed form, bf16 and the f16 layer-0 mode."""
+    monkeypatch.setenv("MT_RGA_STASH_SPILL", "1")
+    io = torch.bfloat16 if dtype == torch.float16 else None
+    r = run_case(2, 4, 512, 64, 512, True, False, dtype, PATHS["tc"], seed=9, io_dtype=io,
+                 do_scale=1e-3 if io is not None else 1.0, stash=True)
+    assert r["o"] < 6e-3, r
+    assert max(r["dq"], r["dk"], r["dv"]) < 1.2e-2 and r["dE"] < 1.2e-2, r
+
+
 def test_rga_mixed_mode_needs_the_tensor_core_path_and_workspace():
     from musicgeneration_b200 import ops
     dev = torch.device("cuda:0")

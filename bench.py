@@ -313,6 +313,72 @@ def gpu_eager_leg(dev, dropout):
     return out
 
 
+def extra_legs(dev, dropout, precision):
+    """N = 1 only, outside the timed region of the headline: the other single-GPU configurations of BASELINE.json as
+    short device-timed measurements, so that they are visible in the driver's record -- config C (REMI: V=337, 12 layers,
+    d768, 12 heads, L=4096, batch 4; fwd+loss+bwd+Adam) and the decode leg with 256 sequences on one GPU."""
+    import torch
+    import musicgeneration_b200 as mtb
+    from musicgeneration_b200.optim import FlatAdam
+    out = {}
+    d, V, pad, layers, L, Bg = CONFIGS["C"]
+    mtb.config.pad_token = pad
+    torch.manual_seed(0)
+    model = mtb.MusicTransformer(embedding_dim=d, vocab_size=V, num_layer=layers, max_seq=L, dropout=dropout,
+                                 precision=precision).to(dev)
+    model.train()
+    crit = mtb.SmoothCrossEntropyLoss(0.1, V, pad)
+    opt = FlatAdam(model, lr=0.0, betas=(0.9, 0.98), eps=1e-9)
+    sched = mtb.CustomSchedule(d, optimizer=opt)
+    g = torch.Generator().manual_seed(4321)
+    xs = [torch.randint(0, pad, (Bg, L), generator=g, dtype=torch.int32).to(dev) for _ in range(2)]
+    ys = [torch.randint(0, pad, (Bg, L), generator=g, dtype=torch.int32).to(dev) for _ in range(2)]
+
+    def step(i):
+        opt.zero_grad()
+        crit(model(xs[i & 1]), ys[i & 1]).backward()
+        sched.step()
+
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    K = 6
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    out["config_C"] = {"workload": workload_config("C", Bg, 1, dropout)["workload"], "train_tokens_per_s": Bg * L / (ms / 1e3),
+                       "ms_per_step": ms, "steps": K, "warmup": 3,
+                       "step_model_tflops": flops_per_token(d, V, layers, L) * Bg * L / (ms / 1e3) / 1e12}
+    del model, opt, sched, crit
+    torch.cuda.empty_cache()
+    # decode, 256 sequences x 2047 events on this one GPU (config B's model; the CUDA-graph path: beyond the persistent
+    # kernel's 64 rows)
+    d, V, pad, layers, L, _ = CONFIGS["B"]
+    mtb.config.pad_token = pad
+    model = mtb.MusicTransformer(embedding_dim=d, vocab_size=V, num_layer=layers, max_seq=L, dropout=0.0,
+                                 precision=precision).to(dev)
+    model.eval()
+    seqs, events = 256, L - 1
+    prior = torch.randint(0, pad, (seqs, 1), generator=g, dtype=torch.int64).to(dev)
+    with torch.no_grad():
+        model.generate(prior, length=8, temperature=1.0, top_k=32)
+        torch.cuda.synchronize()
+        e0.record()
+        model.generate(prior, length=events, temperature=1.0, top_k=32)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    out["decode_256"] = {"decode_events_per_s": seqs * events / (ms / 1e3), "sequences": seqs, "events_per_sequence": events,
+                         "top_k": 32, "ms_total": ms}
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -499,6 +565,11 @@ def run_ours(args):
             del model, opt, sched
             torch.cuda.empty_cache()
             line["gpu_eager_baseline"] = gpu_eager_leg(dev, args.dropout)
+            if args.config == "B" and not args.no_extras:
+                try:          # (never at the price of the headline line)
+                    line["other_configs"] = extra_legs(dev, args.dropout, args.precision)
+                except Exception as e:  # noqa: BLE001
+                    line["other_configs"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -599,6 +670,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short config C / decode-256 legs (N = 1 only)")
     ap.add_argument("--no-eager", action="store_true", help="skip the eager-CUDA reference comparator (N = 1 only)")
     ap.add_argument("--decode-seqs", type=int, default=32)
     ap.add_argument("--decode-events", type=int, default=2047)

@@ -52,7 +52,7 @@ static_assert(SMEM4 <= 232448, "shared memory budget");
 constexpr uint32_t TM4_DP = 0, TM4_ACC = 256;
 
 enum { B4_VF = 0, B4_VE = 2, B4_QF = 4, B4_QE = 6, B4_DOF = 8, B4_DOE = 11, B4_DPF = 14, B4_DPE = 16,
-       B4_PPE = 18, B4_DSE = 20, B4_RDY = 22, B4_ACC = 24, B4_TMEM = 26 };
+       B4_PPE = 18, B4_DSE = 20, B4_RDY = 22, B4_ACC = 24, B4_ACF = 26, B4_TMEM = 28 };
 
 struct Bwd4Params {
   void* dk; void* dv;
@@ -99,6 +99,12 @@ rga_bwd4_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* ds_empty = bars + B4_DSE;     // [2] dK product (and the spill's read) of a step done
   uint64_t* ready = bars + B4_RDY;        // [2] math -> dV/dK issuer: P and dS of the step are in shared memory
   uint64_t* acc_done = bars + B4_ACC;     // [2] dV/dK issuer -> math: the head's accumulators are final
+  uint64_t* acc_free = bars + B4_ACF;     // [2] math -> dV/dK issuer: the set has been read out (one group: 8 warps).  Without this
+                                          // back-pressure the set's reuse two heads later was only ordered by timing: with one
+                                          // step per head (the last key tile) a drain delayed by a step -- its code is cold, an
+                                          // instruction-cache miss is enough -- let the issuer overwrite the set and complete
+                                          // acc_done a second time, after which the drain's parity wait could never succeed
+                                          // (one hang in ~10^4 launches)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B4_TMEM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -114,7 +120,7 @@ rga_bwd4_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc::mbar_init(&q_full[s], 1); tc::mbar_init(&q_empty[s], 1);
       tc::mbar_init(&dp_full[s], 1); tc::mbar_init(&dp_empty[s], K4_MATH / 64);      // (one math group: 8 warps)
       tc::mbar_init(&ds_empty[s], 1); tc::mbar_init(&ready[s], K4_MATH / 64);
-      tc::mbar_init(&acc_done[s], 1);
+      tc::mbar_init(&acc_done[s], 1); tc::mbar_init(&acc_free[s], K4_MATH / 64);
     }
     for (int s = 0; s < 3; ++s) { tc::mbar_init(&do_full[s], 1); tc::mbar_init(&do_empty[s], 1); }
     tc::mbar_init(v_full, 1); tc::mbar_init(v_empty, 1);
@@ -217,6 +223,10 @@ rga_bwd4_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                             smem + Lay4::DS0 + (n & 1) * PT_BYTES, PT_BYTES);
           tc::bulk_commit();
         }
+        if (k == 0 && item >= 2) {      // the set held head item - 2: its drain must be over
+          tc::mbar_wait(&acc_free[item & 1], ((item >> 1) - 1) & 1);
+          tc::tc_fence_after();
+        }
         const uint32_t acc = tmem + TM4_ACC + 128 * (uint32_t)(item & 1);
         const uint64_t dod_mn = dod_mn0 + (uint64_t)(n % 3) * TS16, qd_mn = qd_mn0 + (uint64_t)(n & 1) * TS16;
         const uint64_t dsd = dsd0 + (uint64_t)(n & 1) * 2 * TS16, ppd = ppd0 + (uint64_t)(n & 1) * 2 * TS16;
@@ -293,6 +303,10 @@ rga_bwd4_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         uint32_t r[32];
         tc::tmem_ld_32x32(tmem + TM4_ACC + 128 * (uint32_t)(it_ & 1) + 64 * (uint32_t)hq + 32 * hf + lane_base, r);
         tc::tmem_ld_wait();
+        if (hf == 1) {                  // this warp's part of the set is in registers
+          tc::tc_fence_before();
+          tc::mbar_arrive_warp(&acc_free[it_ & 1]);
+        }
         if (row < p.L) {
 #pragma unroll
           for (int x = 0; x < 4; ++x)

@@ -348,6 +348,40 @@ def test_rga_module_against_reference_fixture(case, tag):
         assert np.abs(p.grad.cpu().numpy() - g).max() <= 2e-5 + 3e-4 * np.abs(g).max(), k
 
 
+@pytest.mark.parametrize("path,dtype", [("simt", torch.float32), ("tc", torch.bfloat16)])
+def test_rga_fully_masked_rows_are_zero_by_definition(path, dtype):
+    """The documented deviation: a query row whose every visible key is a pad
+    token -- only possible when a sequence STARTS with pads -- gets output 0 and LSE 0 here.  The reference adds -1e9 to
+    every logit of such a row (MT/layers.py:93-95), fp32 absorbs the logits, and softmax returns the uniform
+    distribution over ALL L keys, future ones included: the mean of V.  Every other row of the same call must still agree
+    with the closed form."""
+    from musicgeneration_b200 import ops
+    dev = torch.device("cuda:0")
+    B, h, L, dh, max_seq, npad = 2, 2, 160, 64, 160, 3
+    d = h * dh
+    g = torch.Generator().manual_seed(21)
+    qkv = torch.randn(B, L, 3, h, dh, generator=g).to(dtype)
+    E = torch.randn(max_seq, dh, generator=g).to(dtype)
+    pad_keys = torch.zeros(B, L, dtype=torch.bool)
+    pad_keys[0, :npad] = True                      # sequence 0 starts with three pad tokens
+    q, k, v = [qkv[:, :, i].permute(0, 2, 1, 3).double() for i in range(3)]
+    o_ref, lse_ref = O.rga_closed_form(q, k, v, E.double(), max_seq, True, pad_keys)      # NaN on the dead rows
+    qkv_d, Ed = qkv.to(dev), E.to(dev)
+    Od = torch.full((B, L, h, dh), 7.0, dtype=dtype, device=dev)
+    lse = torch.full((B, h, L), 7.0, device=dev)
+    ops.rga_fwd(qkv_d[:, :, 0], qkv_d[:, :, 1], qkv_d[:, :, 2], (L * 3 * d, 3 * d, dh), Ed, pad_keys.to(torch.uint8).to(dev), Od,
+                (L * d, d, dh), lse, B, h, L, dh, max_seq, True, path=PATHS[path])
+    o = Od.float().cpu().permute(0, 2, 1, 3)
+    assert float(o[0, :, :npad].abs().max()) == 0.0 and float(lse.cpu()[0, :, :npad].abs().max()) == 0.0
+    live = torch.ones(B, h, L, dtype=torch.bool)
+    live[0, :, :npad] = False
+    tol = 2e-6 if dtype == torch.float32 else 6e-3
+    assert rel(o[live], o_ref[live]) < tol
+    # what the reference returns on those rows: softmax of fp32(s - 1e9) = uniform over all keys -> mean of V
+    s_row = torch.full((L,), -1e9, dtype=torch.float32) + torch.randn(L, generator=g)
+    assert torch.allclose(torch.softmax(s_row, -1), torch.full((L,), 1.0 / L), atol=1e-6)
+
+
 def test_rga_argument_errors():
     from musicgeneration_b200 import ops
     dev = torch.device("cuda:0")

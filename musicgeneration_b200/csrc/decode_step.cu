@@ -166,6 +166,15 @@ __device__ __forceinline__ void stage_ln(const DsSmem& s, const float* u, const 
                                          float* out_f32, int B, int d, int mtiles, bool f16) {
   const int pitch = d + DS_PAD, d4 = d >> 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // gamma / beta of this lane's columns, requested first: every grid barrier invalidates L1 (gpu-scope fence), so they come
+  // from L2 in every phase -- loaded after the reductions, that round trip sat at the end of each row's chain
+  float4 gam[NV], bet[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + i * 32;
+    gam[i] = bet[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < d4) { gam[i] = *reinterpret_cast<const float4*>(gamma + c4 * 4); bet[i] = *reinterpret_cast<const float4*>(beta + c4 * 4); }
+  }
   for (int row0 = warp; row0 < mtiles * 16; row0 += 4 * DS_WARPS) {
     // four rows of this warp at a time, every load issued before the first reduction (a row by itself is two L2 round
     // trips plus two warp reductions: ~2 us, four rows in sequence were the most expensive part of a phase)
@@ -212,8 +221,7 @@ __device__ __forceinline__ void stage_ln(const DsSmem& s, const float* u, const 
       for (int i = 0; i < NV; ++i) {
         const int c4 = lane + i * 32;
         if (c4 < d4) {
-          const float4 g = *reinterpret_cast<const float4*>(gamma + c4 * 4);
-          const float4 bt = *reinterpret_cast<const float4*>(beta + c4 * 4);
+          const float4 g = gam[i], bt = bet[i];
           const float4 o = make_float4((z[q][i].x - mu) * rs * g.x + bt.x, (z[q][i].y - mu) * rs * g.y + bt.y,
                                        (z[q][i].z - mu) * rs * g.z + bt.z, (z[q][i].w - mu) * rs * g.w + bt.w);
           *reinterpret_cast<uint2*>(dst + c4 * 4) = make_uint2(pack16(o.x, o.y, f16), pack16(o.z, o.w, f16));
@@ -268,6 +276,8 @@ __device__ __forceinline__ void run_strips(const DsSmem& s, const DsParams& p, c
       __syncthreads();
     }
     const uint16_t* sW = s.W + (slot >= 2 ? 0 : slot) * DS_BN * pitch;
+    const int ncol = st * DS_BN + (tid & 7);                     // the column every epilogue element of this thread falls into
+    const float bias_c = ncol < N ? __ldg(bias + ncol) : 0.f;    // (requested before the products: L1 is cold after a barrier)
     float acc[4][4];
 #pragma unroll
     for (int m = 0; m < 4; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
@@ -303,7 +313,7 @@ __device__ __forceinline__ void run_strips(const DsSmem& s, const DsParams& p, c
       float v = 0.f;
 #pragma unroll
       for (int w = 0; w < DS_WARPS; ++w) v += s.red[w * mt * 16 * 8 + e];
-      v += bias[n];
+      v += bias_c;
       if (relu) v = fmaxf(v, 0.f);
       if (out_kind == OUT_F32) {
         reinterpret_cast<float*>(C)[(int64_t)r * N + n] = v;
@@ -378,6 +388,8 @@ __device__ __forceinline__ void attend_unit(const DsSmem& s, DsRing& ring, const
   const uint8_t* vb = reinterpret_cast<const uint8_t*>(Ly.vc) + bh * (int64_t)max_seq * 128;
   const uint8_t* eb = reinterpret_cast<const uint8_t*>(Ly.E) + (int64_t)(max_seq - 1 - t) * 128;     // E row of key 0
   const int nblk = (t + DS_BLK - 1) / DS_BLK;                 // blocks of cached keys 0 .. t-1
+  const uint4 enew = *reinterpret_cast<const uint4*>(eb + (int64_t)t * 128 + sub * 16);      // (requested with q: cold L1)
+  const bool pad_new = pad[t] != 0;
   float m_run = -INFINITY, l_run = 0.f, o8[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) o8[e] = 0.f;
@@ -406,26 +418,63 @@ __device__ __forceinline__ void attend_unit(const DsSmem& s, DsRing& ring, const
       *reinterpret_cast<uint4*>(const_cast<uint8_t*>(kb) + (int64_t)t * 128 + sub * 16) = knew;
       *reinterpret_cast<uint4*>(const_cast<uint8_t*>(vb) + (int64_t)t * 128 + sub * 16) = vnew;
     }
-    if (grp == 0) {       // (whole key groups take the branch: the shuffles stay inside a group)
-      const uint4 enew = *reinterpret_cast<const uint4*>(eb + (int64_t)t * 128 + sub * 16);
-      one_key(knew, enew, vnew, !pad[t]);
-    }
+    if (grp == 0) one_key(knew, enew, vnew, !pad_new);       // (whole key groups take the branch: the shuffles stay inside a group)
   }
   // ---- the cached keys, block by block out of the ring
   for (int blk = 0; blk < nblk; ++blk) {
     const uint32_t c = ring.consumed, slot = c % DS_STAGES;
-    tc::mbar_wait(&ring.full[slot], (c / DS_STAGES) & 1);
-    const uint8_t* src = ring.buf + slot * DS_STAGE_BYTES + sub * 16;
     const int j0 = blk * DS_BLK, nk = min(DS_BLK, t - j0);
+    // the block's pad flags BEFORE the wait for its rows: every grid barrier invalidates L1 (gpu-scope fence), so each
+    // phase re-reads the flags from L2 -- inside the softmax chain that round trip was exposed once per block
+    bool padk[DS_BLK / KPI];
 #pragma unroll
     for (int ps = 0; ps < DS_BLK / KPI; ++ps) {
       const int jj = ps * KPI + grp;
+      padk[ps] = (jj < nk) ? (pad[j0 + jj] != 0) : true;
+    }
+    tc::mbar_wait(&ring.full[slot], (c / DS_STAGES) & 1);
+    const uint8_t* src = ring.buf + slot * DS_STAGE_BYTES + sub * 16;
+    // the block's four keys of this key group at once: four independent dot products and group reductions, then ONE
+    // update of the running (max, sum, o) -- key by key the update chain (reduction -> max -> exp -> fma, ~250 cycles)
+    // ran four times per block with only two warps per scheduler to hide it
+    float acc4[4];
+    uint4 vr4[4];
+#pragma unroll
+    for (int ps = 0; ps < DS_BLK / KPI; ++ps) {
+      const int jj = ps * KPI + grp;
+      acc4[ps] = -INFINITY;
+      vr4[ps] = make_uint4(0, 0, 0, 0);
       if (jj < nk) {       // (uniform per key group)
         const uint4 kr = *reinterpret_cast<const uint4*>(src + jj * 128);
         const uint4 er = *reinterpret_cast<const uint4*>(src + DS_BLK * 128 + jj * 128);
-        const uint4 vr = *reinterpret_cast<const uint4*>(src + 2 * DS_BLK * 128 + jj * 128);
-        one_key(kr, er, vr, !pad[j0 + jj]);
+        vr4[ps] = *reinterpret_cast<const uint4*>(src + 2 * DS_BLK * 128 + jj * 128);
+        float kf[8], ef[8];
+        unpack8(kr, kf, f16); unpack8(er, ef, f16);
+        float acc = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc = fmaf(q8[e], kf[e] + ef[e], acc);
+#pragma unroll
+        for (int o = LPK / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(LMASK, acc, o);
+        acc4[ps] = padk[ps] ? -INFINITY : acc;
       }
+    }
+    {
+      const float m_new = fmaxf(fmaxf(m_run, fmaxf(acc4[0], acc4[1])), fmaxf(acc4[2], acc4[3]));
+      const float corr = (m_new == -INFINITY) ? 1.f : __expf(m_run - m_new);
+      float pj[4];
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) pj[ps] = (acc4[ps] == -INFINITY) ? 0.f : __expf(acc4[ps] - m_new);
+      l_run = fmaf(l_run, corr, (pj[0] + pj[1]) + (pj[2] + pj[3]));
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o8[e] *= corr;
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) {
+        float vf[8];
+        unpack8(vr4[ps], vf, f16);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o8[e] = fmaf(pj[ps], vf[e], o8[e]);
+      }
+      m_run = m_new;
     }
     ring.consumed = c + 1;
     tc::mbar_arrive_warp(&ring.empty[slot]);
@@ -480,6 +529,7 @@ __device__ __forceinline__ void sample_row_warp(const DsParams& p, int b, int t)
     keep[i] = false;
   }
   int32_t* out = p.ids + (int64_t)b * p.ld_ids + (t + 1);
+  const float u_row = p.greedy ? 0.f : __ldg(p.uniforms + (int64_t)(t + 1 - p.prior_len) * p.B + b);
   const bool full = p.greedy || p.top_k <= 0 || p.top_k >= V;
   const int rounds = p.greedy ? 1 : (full ? 0 : p.top_k);
   for (int it = 0; it < rounds; ++it) {
@@ -533,7 +583,7 @@ __device__ __forceinline__ void sample_row_warp(const DsParams& p, int b, int t)
   }
   const float total = __shfl_sync(0xffffffffu, incl, 31);
   float cdf = incl - lnorm;
-  const float target = p.uniforms[(int64_t)(t + 1 - p.prior_len) * p.B + b] * total;
+  const float target = u_row * total;
   int pick = 0x7fffffff;
 #pragma unroll
   for (int i = 0; i < C; ++i) {

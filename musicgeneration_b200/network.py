@@ -230,9 +230,8 @@ class _DecodeSession:
 
     def persistent_default(self) -> bool:
         """Whether generate() takes the persistent kernel by itself.  Measured on B200 at config B (us per event,
-        persistent / graph path): 8 sequences 269 / 345, 32 sequences 463 / 472, 64 sequences 632 / 628 -- the one
-        launch wins where the step is launch- and fill-latency (few sequences) and ties once the KV stream and the
-        per-phase L2 traffic dominate, so it is the default up to 32 sequences.  MT_DECODE_PERSISTENT=1 / 0 forces it
+        persistent / graph path): 8 sequences 243 / 345, 32 sequences 408 / 472 -- the one launch wins most where the
+        step is launch- and fill-latency (few sequences); it is the default up to 32 sequences (what was measured).  MT_DECODE_PERSISTENT=1 / 0 forces it
         on (wherever it is supported) / off."""
         env = os.environ.get("MT_DECODE_PERSISTENT")
         if env is not None:

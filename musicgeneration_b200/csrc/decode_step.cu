@@ -15,9 +15,14 @@
 // 5 barriers per layer + 2.  A projection phase gives each CTA strips of 8 output columns (mma.sync.m16n8k16, the 8
 // warps split K); the strip's weight rows are requested BEFORE the barrier that ends the previous phase -- weights
 // are constant, so their latency runs under the predecessor's tail -- and the LayerNorm of the few activation rows is
-// recomputed by every CTA in its prologue instead of being a phase of its own.  Arithmetic is that of the per-kernel
-// path (gemm_skinny.cu, decode.cu, elementwise.cu): 16-bit operands (f16 in the first layer's attention block,
-// DESIGN.md section 2), fp32 accumulation, fp32 residual stream / LayerNorm / softmax.
+// recomputed by every CTA that owns a strip in its prologue instead of being a phase of its own.  The attention phase
+// streams the cached K / V / E rows through a shared-memory ring of bulk copies (requested across the CTA's units and
+// before the phase's barrier); the sampler is one warp per row on register-resident logits.
+// One rule shaped every phase: the gpu-scope fence of a grid barrier INVALIDATES L1, so nothing is "cached" from phase to
+// phase -- every operand a dependency chain needs (pad flags, gamma / beta, biases, uniforms, the new key's rows) is
+// requested at the top of the phase, before the chain, or its L2 round trip is exposed once per use.
+// Arithmetic is that of the per-kernel path (gemm_skinny.cu, decode.cu, elementwise.cu): 16-bit operands (f16 in the
+// first layer's attention block), fp32 accumulation, fp32 residual stream / LayerNorm / softmax.
 #include "ops.cuh"
 #include "tc_common.cuh"
 

@@ -241,7 +241,7 @@ class _DecodeSession:
     def run_persistent(self, ids, prior_len, n_steps, u, temperature, top_k, greedy, logits_out=None):
         """Positions 0 .. n_steps-1 of ``ids`` [B, >= n_steps+1] in ONE launch (same contract as run_graph)."""
         cfg = self.cfg
-        rows, f16 = [], []
+        rows, f16, keep = [], [], []          # keep: the operand tensors stay referenced until the launch has been enqueued
         for li, W in enumerate(self.Ws):
             hp = self.lact[li] != cfg.act
             ts = [W.Wqkv_hp if hp else W.Wqkv, W.bqkv, W.Wfc_hp if hp else W.Wfc, W.bfc, W.Wpre, W.bpre, W.Wsuf, W.bsuf,
@@ -251,13 +251,14 @@ class _DecodeSession:
                     raise RuntimeError("decode_run: non-contiguous layer operand")
             rows.append([x.data_ptr() for x in ts])
             f16.append(1 if hp else 0)
-            self._keep = getattr(self, "_keep", []) + ts
+            keep.extend(ts)
         ptrs = torch.tensor(rows, dtype=torch.int64)
         flags = torch.tensor(f16, dtype=torch.int32)
         ws = torch.empty(L.load().mt_decode_run_workspace_bytes(self.B, cfg.d, self.V), dtype=torch.uint8,
                          device=self.emb.device)
         ops.decode_run(ids, 0, n_steps, prior_len, self.emb, self.pe, ptrs, flags, self.Wv, self.bv, cfg.d, cfg.h,
                        cfg.max_seq, config.pad_token, self.pad_bits, u, temperature, top_k, greedy, logits_out, ws)
+        self._keep = (keep, ws)               # (stream-ordered use: released with the session)
 
     # ---- graph mode: every buffer preallocated, the position read from device memory ----------
     def _alloc_step_buffers(self):

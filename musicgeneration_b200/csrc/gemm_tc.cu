@@ -602,6 +602,10 @@ __global__ void __launch_bounds__(256) tc_splitk_fold_kernel(TcGemmParams p) {
   else reinterpret_cast<float*>(p.C)[m * p.ldc + n] = s;
 }
 
+// (Measured and dropped, round 2: the fold INSIDE the GEMM launch -- an arrival counter per output tile, the tile's last
+// CTA sums its partials in the same order -- is parity-green but 10.08 vs 9.42 ms per config-B step: one CTA folding a
+// 128 x 128 tile over its splits is a chain of L2 round trips at the tail of every weight-gradient launch (~25 us),
+// where this launch spreads the same loads over the whole chip in 8 us.)
 // The weight-gradient case (fp32 output, no epilogue, N % 4 == 0): one quad per thread, the partial
 // loads of eight splits in flight at a time; same ascending-z summation order as the scalar kernel.
 __global__ void __launch_bounds__(256) tc_splitk_fold_vec_kernel(TcGemmParams p) {

@@ -529,6 +529,9 @@ def run_ours(args):
                     "h2d_bytes_per_step": 2 * Bg * L * 4, "d2h_bytes_per_step": 4, "last_loss": last,
                     "loss_read": "every step, pinned + async, consumed one step late"},
             "gpu_launches": launches,
+            "gpu_launches_what": "launching C-ABI calls of libmt_b200.so inside the timed region (a lower bound on kernels: an "
+                                 "attention backward call is 3 kernels, a split-K weight gradient 2; the ncu launch list "
+                                 "profiles/r2f_launches_bench_configB.summary.txt has ~172 mt:: kernels per step)",
             "roofline": {"kernel": "rga_bwd (relative attention backward of one layer, one C-ABI call mt_rga_bwd_stash: delta + "
                                    "dK/dV kernel + dQ/dE kernel, both reading the P tiles the forward kept)", "bound": "tensor",
                          "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",

@@ -34,6 +34,24 @@ def test_library_exports_every_declared_symbol(built_lib):
     assert _lib.load().mt_version() >= 100
 
 
+def test_size_queries_of_the_training_pair_and_the_persistent_decode(built_lib):
+    """The size queries are plain arithmetic (no device): the P stash is B h nT (nT + 1) / 2 tiles of 32 KB plus 2 x 128 fp32
+    row references per tile; shapes the tcgen05 training pair does not take report 0 (the engine then keeps no stash)."""
+    from musicgeneration_b200 import _lib
+    lib = _lib.load()
+    for B, h, L in ((16, 8, 2048), (4, 12, 4096), (2, 2, 64), (1, 3, 200)):
+        nT = (L + 127) // 128
+        tiles = B * h * nT * (nT + 1) // 2
+        assert lib.mt_rga_stash_bytes(B, h, L, 64, _lib.MT_BF16) == tiles * (32768 + 1024)
+        assert lib.mt_rga_stash_bytes(B, h, L, 64, _lib.MT_F16_BF16) == tiles * (32768 + 1024)
+        assert lib.mt_rga_bwd_workspace_bytes(B, h, L, 64, _lib.MT_BF16) == tiles * 32768
+    assert lib.mt_rga_stash_bytes(2, 2, 64, 128, _lib.MT_BF16) == 0           # head dim 128: fp32-math kernels, no stash
+    assert lib.mt_rga_stash_bytes(2, 2, 64, 64, _lib.MT_F32) == 0
+    ws = lib.mt_decode_run_workspace_bytes(32, 512, 390)
+    assert ws >= 256 + 4 * 32 * 512 * 4 + 32 * 390 * 4 + 32 * (3 * 512 + 512 + 256) * 2 and ws % 256 == 0
+    assert lib.mt_decode_run_workspace_bytes(0, 512, 390) == 0
+
+
 def test_ops_refuse_cpu_tensors(built_lib):
     import musicgeneration_b200 as mtb
     m = mtb.MusicTransformer(embedding_dim=64, vocab_size=20, num_layer=1, max_seq=8, dropout=0.0)

@@ -642,20 +642,23 @@ def run_sweep(args):
             delta = torch.empty(B, h, L, device=dev)
             iters = 10 if dh == 64 else 3
             ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(iters)]
+            # the pair a training step runs: the forward keeps its P tiles, the backward reads them (head dim 64)
+            stash = ops.rga_stash_new(qkv[:, :, 0], E, Od, B, h, L, dh)
             for it in range(-2, iters):
                 e = ev[max(it, 0)]
                 e[0].record()
-                ops.rga_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], strides, E, None, Od, ostr, lse, B, h, L, dh, L, True)
+                ops.rga_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], strides, E, None, Od, ostr, lse, B, h, L, dh, L, True,
+                            stash=stash)
                 e[1].record()
                 ops.rga_bwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], strides, E, None, Od, dO, ostr, lse, delta,
-                            dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], dE, B, h, L, dh, L, True)
+                            dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], dE, B, h, L, dh, L, True, stash=stash)
                 e[2].record()
             torch.cuda.synchronize()
             fwd = sum(e[0].elapsed_time(e[1]) for e in ev) / iters
             bwd = sum(e[1].elapsed_time(e[2]) for e in ev) / iters
             U = L * L * dh * B * h
             emit(({"metric": "rga_fwd_bwd_ms", "L": L, "dh": dh, "B": B, "h": h,
-                              "kernels": "tcgen05" if dh == 64 else "simt fp32 math",
+                              "kernels": "tcgen05, training pair (P stash)" if stash is not None else "simt fp32 math",
                               "fwd_ms": fwd, "bwd_ms": bwd, "tokens_per_s": B * L / ((fwd + bwd) / 1e3),
                               "fwd_tflops": 3 * U / (fwd / 1e3) / 1e12, "bwd_tflops": 6 * U / (bwd / 1e3) / 1e12,
                               "fwd_bwd_frac_of_bf16_sustained": 9 * U / ((fwd + bwd) / 1e3) / 1e12 / pk["tf_sust"]}))
